@@ -1,0 +1,961 @@
+// C ABI of libcardelino_b200.so (include/cardelino_b200.h): handle, data loading, the Gibbs driver
+// loop of clone_id_Gibbs (R/clone_id.R:351-675), clone_id_EM (:240-326) and get_logLik (:734-752).
+#include "../../include/cardelino_b200.h"
+#include "internal.h"
+
+#include <dlfcn.h>
+#include <algorithm>
+#include <cmath>
+#include <cstdio>
+#include <cstring>
+#include <memory>
+#include <vector>
+
+using namespace cdl;
+
+namespace {
+
+thread_local std::string g_create_error;
+
+template <typename T>
+struct DevBuf {
+    T* p = nullptr;
+    size_t n = 0;
+    DevBuf() = default;
+    explicit DevBuf(size_t count) { alloc(count); }
+    DevBuf(const DevBuf&) = delete;
+    DevBuf& operator=(const DevBuf&) = delete;
+    DevBuf(DevBuf&& o) noexcept : p(o.p), n(o.n) { o.p = nullptr; o.n = 0; }
+    DevBuf& operator=(DevBuf&& o) noexcept {
+        if (this != &o) { release(); p = o.p; n = o.n; o.p = nullptr; o.n = 0; }
+        return *this;
+    }
+    ~DevBuf() { release(); }
+    void release() { if (p) cudaFree(p); p = nullptr; n = 0; }
+    void alloc(size_t count) {
+        release();
+        n = count;
+        const size_t bytes = sizeof(T) * (count ? count : 1);
+        cudaError_t e = cudaMalloc(&p, bytes);
+        if (e != cudaSuccess) {
+            p = nullptr;
+            throw Error(CDL_ERR_NOMEM, "cudaMalloc of " + std::to_string(bytes) + " bytes failed: " +
+                                           cudaGetErrorString(e));
+        }
+    }
+    void zero(cudaStream_t st) { CDL_CUDA(cudaMemsetAsync(p, 0, sizeof(T) * (n ? n : 1), st)); }
+    void upload(const T* h, size_t count, cudaStream_t st) {
+        CDL_CUDA(cudaMemcpyAsync(p, h, sizeof(T) * count, cudaMemcpyHostToDevice, st));
+    }
+    void download(T* h, size_t count, cudaStream_t st, size_t offset = 0) const {
+        CDL_CUDA(cudaMemcpyAsync(h, p + offset, sizeof(T) * count, cudaMemcpyDeviceToHost, st));
+        CDL_CUDA(cudaStreamSynchronize(st));
+    }
+};
+
+// ---- NCCL through dlopen: the host plumbing (torch.distributed) already has libnccl loaded; we bind the
+// same copy instead of linking a second one. ----
+struct Id128 { char b[128]; };   // ncclUniqueId is passed BY VALUE (128 bytes)
+struct NcclApi {
+    void* lib = nullptr;
+    int (*GetUniqueId)(void*) = nullptr;
+    int (*CommInitRank)(void**, int, Id128, int) = nullptr;
+    int (*AllReduce)(const void*, void*, size_t, int, int, void*, cudaStream_t) = nullptr;
+    int (*CommDestroy)(void*) = nullptr;
+    const char* (*GetErrorString)(int) = nullptr;
+};
+
+struct Chain {
+    ChainDev dev{};
+    DevBuf<double> scal, l1, l1c, theta0_all, theta1_all, loglik_all, relax_all, prob_all, prob_acc, part_d;
+    DevBuf<uint32_t> mask;
+    DevBuf<uint8_t> z, config_all, assign_all;
+    DevBuf<unsigned long long> sab, part_u;
+    DevBuf<unsigned int> ticket;
+    DevBuf<double2> tab_g;
+    // summaries
+    DevBuf<double> prob_mean, config_prob, theta1_mean;
+    double theta0_mean = 0.0, relax_mean = 0.0;
+    cdl_gibbs_info info{};
+    bool done = false;
+};
+
+}  // namespace
+
+struct cdl_handle_s {
+    int device = 0;
+    int sm_count = 148;
+    cudaStream_t st = nullptr;
+    std::string err;
+    Donor donor;
+    bool has_data = false;
+    // last Gibbs run
+    std::vector<std::unique_ptr<Chain>> chains;
+    cdl_gibbs_params gp{};
+    int K = 0;
+    int64_t T = 0, n_el = 0;
+    DevBuf<uint32_t> cfg0;
+    DevBuf<double> prior1_mat;
+    SweepArgs sweep{};        // template of the last run (bench hook)
+    bool have_sweep = false;
+    // comm
+    NcclApi nccl;
+    void* comm = nullptr;
+    int rank = 0, world = 1;
+    int64_t launches = 0;
+};
+
+namespace {
+
+void use_device(cdl_handle h) { CDL_CUDA(cudaSetDevice(h->device)); }
+
+template <typename F>
+int guard(cdl_handle h, F&& f) {
+    try {
+        if (!h) throw Error(CDL_ERR_INVALID, "null handle");
+        use_device(h);
+        f();
+        return CDL_OK;
+    } catch (const Error& e) {
+        if (h) h->err = e.what(); else g_create_error = e.what();
+        return e.code;
+    } catch (const std::bad_alloc&) {
+        if (h) h->err = "host allocation failed";
+        return CDL_ERR_NOMEM;
+    } catch (const std::exception& e) {
+        if (h) h->err = e.what();
+        return CDL_ERR_INVALID;
+    }
+}
+
+void nccl_load(cdl_handle h, const char* path) {
+    if (h->nccl.lib) return;
+    const char* cand[] = {path, "libnccl.so.2", "libnccl.so"};
+    void* lib = nullptr;
+    for (const char* c : cand) {
+        if (!c || !*c) continue;
+        lib = dlopen(c, RTLD_NOW | RTLD_GLOBAL);
+        if (lib) break;
+    }
+    if (!lib) throw Error(CDL_ERR_COMM, std::string("cannot dlopen NCCL: ") + dlerror());
+    h->nccl.lib = lib;
+    h->nccl.GetUniqueId = (int (*)(void*))dlsym(lib, "ncclGetUniqueId");
+    h->nccl.CommInitRank = (int (*)(void**, int, Id128, int))dlsym(lib, "ncclCommInitRank");
+    h->nccl.AllReduce = (int (*)(const void*, void*, size_t, int, int, void*, cudaStream_t))dlsym(lib, "ncclAllReduce");
+    h->nccl.CommDestroy = (int (*)(void*))dlsym(lib, "ncclCommDestroy");
+    h->nccl.GetErrorString = (const char* (*)(int))dlsym(lib, "ncclGetErrorString");
+    if (!h->nccl.GetUniqueId || !h->nccl.CommInitRank || !h->nccl.AllReduce || !h->nccl.CommDestroy)
+        throw Error(CDL_ERR_COMM, "NCCL symbols missing");
+}
+
+void nccl_check(cdl_handle h, int rc, const char* what) {
+    if (rc != 0) {
+        const char* s = h->nccl.GetErrorString ? h->nccl.GetErrorString(rc) : "?";
+        throw Error(CDL_ERR_COMM, std::string(what) + ": " + s);
+    }
+}
+
+// ncclDataType_t / ncclRedOp_t values (nccl.h): ncclUint64 = 5, ncclFloat64 = 8, ncclSum = 0
+constexpr int NCCL_U64 = 5, NCCL_F64 = 8, NCCL_SUM = 0;
+
+void allreduce_u64(cdl_handle h, unsigned long long* buf, size_t n) {
+    if (h->world <= 1) return;
+    nccl_check(h, h->nccl.AllReduce(buf, buf, n, NCCL_U64, NCCL_SUM, h->comm, h->st), "ncclAllReduce(u64)");
+}
+double allreduce_scalar_d(cdl_handle h, double v) {
+    if (h->world <= 1) return v;
+    DevBuf<double> b(1);
+    b.upload(&v, 1, h->st);
+    nccl_check(h, h->nccl.AllReduce(b.p, b.p, 1, NCCL_F64, NCCL_SUM, h->comm, h->st), "ncclAllReduce(f64)");
+    double out = 0;
+    b.download(&out, 1, h->st);
+    return out;
+}
+
+// ---- host-side input normalisation -----------------------------------------------------------
+
+struct RawCsc {
+    std::vector<int64_t> p;
+    std::vector<int32_t> i;
+    std::vector<uint16_t> a, d;
+};
+
+inline bool is_na(double x) { return x != x; }
+
+void check_count(double v, const char* what) {
+    if (v != std::floor(v)) throw Error(CDL_ERR_INVALID, "A and/or D contain non-integer values.");
+    if (v < 0) throw Error(CDL_ERR_INVALID, std::string("negative count in ") + what);
+    if (v > 65535.0)
+        throw Error(CDL_ERR_UNSUPPORTED, std::string("count above 65535 in ") + what + " (uint16 storage)");
+}
+
+void upload_raw(cdl_handle h, int64_t N, int64_t M, const RawCsc& r) {
+    const int64_t nnz = (int64_t)r.i.size();
+    DevBuf<int64_t> p((size_t)M + 1);
+    DevBuf<int32_t> vi((size_t)nnz);
+    DevBuf<uint16_t> a((size_t)nnz), d((size_t)nnz);
+    p.upload(r.p.data(), (size_t)M + 1, h->st);
+    if (nnz) {
+        vi.upload(r.i.data(), (size_t)nnz, h->st);
+        a.upload(r.a.data(), (size_t)nnz, h->st);
+        d.upload(r.d.data(), (size_t)nnz, h->st);
+    }
+    cudaFree(h->donor.labels);
+    h->donor.labels = nullptr;
+    h->donor.M_total = 0;
+    h->donor.cell_offset = 0;
+    donor_build(h->donor, N, M, nnz, p.p, vi.p, a.p, d.p, h->st);
+    h->has_data = true;
+    h->chains.clear();
+    h->have_sweep = false;
+}
+
+void require_data(cdl_handle h) {
+    if (!h->has_data) throw Error(CDL_ERR_STATE, "no donor loaded (call cdl_load_* first)");
+}
+
+Chain& get_chain(cdl_handle h, int c) {
+    if (c < 0 || c >= (int)h->chains.size() || !h->chains[(size_t)c]->done)
+        throw Error(CDL_ERR_STATE, "no finished Gibbs chain with that index");
+    return *h->chains[(size_t)c];
+}
+
+std::vector<uint32_t> config_masks(const double* Config, int64_t N, int K, bool require_binary) {
+    std::vector<uint32_t> m((size_t)N, 0u);
+    for (int k = 0; k < K; ++k)
+        for (int64_t i = 0; i < N; ++i) {
+            const double v = Config[i + (int64_t)k * N];
+            if (v == 1.0) m[(size_t)i] |= 1u << k;
+            else if (v != 0.0 && require_binary)
+                throw Error(CDL_ERR_UNSUPPORTED, "Config must be binary (0/1) for this path");
+        }
+    return m;
+}
+
+void fill_logpsi(const double* Psi, int K, double* out) {
+    for (int k = 0; k < KMAX; ++k) out[k] = 0.0;
+    for (int k = 0; k < K; ++k) {
+        const double p = Psi ? Psi[k] : 1.0 / K;
+        if (!(p > 0.0)) throw Error(CDL_ERR_INVALID, "Psi must be positive");
+        out[k] = std::log(p);
+    }
+}
+
+void dic_from_trace(const std::vector<double>& ll, double logLik_post, double out[6]) {
+    const size_t n = ll.size();
+    double m = 0;
+    for (double v : ll) m += v;
+    m /= (double)n;
+    double var = NAN;
+    if (n > 1) {
+        double s = 0;
+        for (double v : ll) s += (v - m) * (v - m);
+        var = s / (double)(n - 1);
+    }
+    const double pDS = -2 * m - (-2 * logLik_post);
+    const double DICS = -2 * logLik_post + 2 * pDS;
+    const double DICG = -2 * logLik_post + 2 * (2 * var);
+    out[0] = DICG; out[1] = var; out[2] = -2 * m; out[3] = -2 * logLik_post; out[4] = DICG; out[5] = DICS;
+}
+
+void one_sweep(cdl_handle h, Chain& ch, SweepArgs& a, uint32_t it, const cdl_replay* rp_dev, int64_t n_el) {
+    a.it = it;
+    const cdl_gibbs_params& gp = h->gp;
+    a.learn_relax_next = (a.relax && !a.relax_fixed_set && ((double)(it + 1) > 0.1 * gp.min_iter + 5.0)) ? 1 : 0;
+    if (rp_dev) {
+        const int64_t row = (int64_t)it - 1;
+        a.rp_u_assign = rp_dev->u_assign ? rp_dev->u_assign + row * a.M : nullptr;
+        a.rp_u_config = rp_dev->u_config ? rp_dev->u_config + row * a.N * a.K : nullptr;
+        a.rp_theta0 = rp_dev->theta0 ? rp_dev->theta0 + row : nullptr;
+        a.rp_theta1 = rp_dev->theta1 ? rp_dev->theta1 + row * n_el : nullptr;
+        a.rp_relax_next = (rp_dev->relax_rate && (int64_t)it < a.T) ? rp_dev->relax_rate + row + 1 : nullptr;
+    }
+    launch_cells(h->donor, a, ch.dev, h->sm_count, h->st);
+    launch_stats(h->donor, a, ch.dev, h->sm_count, h->st);
+    allreduce_u64(h, ch.dev.sab, (size_t)(a.N * a.K));
+    launch_table(h->donor, a, ch.dev, h->st);
+    h->launches += 4;
+}
+
+double geweke_fraction(cdl_handle h, Chain& ch, int64_t n_rows, DevBuf<unsigned long long>& counts) {
+    launch_geweke(ch.dev.prob_all, h->donor.M * h->K, n_rows, counts.p, h->st);
+    if (h->world > 1) allreduce_u64(h, counts.p, 2);
+    unsigned long long c[2];
+    counts.download(c, 2, h->st);
+    if (c[0] == 0) return NAN;
+    return (double)c[1] / (double)c[0];
+}
+
+double r_round3_percent(double frac) {   // round(x, 3) * 100 (R/clone_id.R:585,595)
+    if (frac != frac) return frac;
+    return std::nearbyint(frac * 1000.0) / 1000.0 * 100.0;
+}
+
+}  // namespace
+
+// =================================================================================================
+extern "C" {
+
+int cdl_version(void) { return 100; }
+
+const char* cdl_last_error(cdl_handle h) { return h ? h->err.c_str() : g_create_error.c_str(); }
+
+int cdl_create(int device, cdl_handle* out) {
+    if (!out) return CDL_ERR_INVALID;
+    *out = nullptr;
+    try {
+        int n = 0;
+        cudaError_t e = cudaGetDeviceCount(&n);
+        if (e != cudaSuccess || n == 0)
+            throw Error(CDL_ERR_CUDA, std::string("no CUDA device available (this library has no CPU path): ") +
+                                          cudaGetErrorString(e));
+        if (device < 0 || device >= n) throw Error(CDL_ERR_INVALID, "device index out of range");
+        CDL_CUDA(cudaSetDevice(device));
+        cudaDeviceProp prop;
+        CDL_CUDA(cudaGetDeviceProperties(&prop, device));
+        if (prop.major < 10)
+            throw Error(CDL_ERR_CUDA, std::string("device ") + prop.name + " is not sm_100-class; kernels are built for sm_100a only");
+        std::unique_ptr<cdl_handle_s> h(new cdl_handle_s());
+        h->device = device;
+        h->sm_count = prop.multiProcessorCount;
+        CDL_CUDA(cudaStreamCreateWithFlags(&h->st, cudaStreamNonBlocking));
+        *out = h.release();
+        return CDL_OK;
+    } catch (const Error& e) {
+        g_create_error = e.what();
+        return e.code;
+    } catch (const std::exception& e) {
+        g_create_error = e.what();
+        return CDL_ERR_CUDA;
+    }
+}
+
+int cdl_destroy(cdl_handle h) {
+    if (!h) return CDL_OK;
+    cudaSetDevice(h->device);
+    if (h->comm && h->nccl.CommDestroy) h->nccl.CommDestroy(h->comm);
+    h->chains.clear();
+    donor_free(h->donor);
+    if (h->st) cudaStreamDestroy(h->st);
+    delete h;
+    return CDL_OK;
+}
+
+int cdl_load_dense(cdl_handle h, int64_t N, int64_t M, const double* A, const double* D) {
+    return guard(h, [&] {
+        if (!A || !D || N <= 0 || M <= 0) throw Error(CDL_ERR_INVALID, "A and D must be non-empty matrices");
+        RawCsc r;
+        r.p.assign((size_t)M + 1, 0);
+        for (int64_t j = 0; j < M; ++j) {
+            for (int64_t i = 0; i < N; ++i) {
+                const double dv = D[i + j * N], av = A[i + j * N];
+                if (!is_na(av)) { if (av != std::floor(av)) throw Error(CDL_ERR_INVALID, "A and/or D contain non-integer values."); }
+                if (is_na(dv)) {
+                    if (!is_na(av) && av != 0.0)
+                        throw Error(CDL_ERR_INVALID, "A has a count where D is missing (NA); the reference would "
+                                                     "count those reads with zero depth");
+                    continue;
+                }
+                check_count(dv, "D");
+                if (dv == 0.0) continue;               // D == 0 -> NA (R/clone_id.R:380-381)
+                double a_use = is_na(av) ? 0.0 : av;   // A NA where D > 0 -> 0 (:382)
+                check_count(a_use, "A");
+                if (a_use > dv) throw Error(CDL_ERR_INVALID, "A exceeds D for some entry");
+                r.i.push_back((int32_t)i);
+                r.a.push_back((uint16_t)a_use);
+                r.d.push_back((uint16_t)dv);
+            }
+            r.p[(size_t)j + 1] = (int64_t)r.i.size();
+        }
+        upload_raw(h, N, M, r);
+    });
+}
+
+int cdl_load_csc(cdl_handle h, int64_t N, int64_t M, const int64_t* d_p, const int32_t* d_i, const double* d_x,
+                 const int64_t* a_p, const int32_t* a_i, const double* a_x) {
+    return guard(h, [&] {
+        if (!d_p || !a_p || N <= 0 || M <= 0) throw Error(CDL_ERR_INVALID, "bad sparse input");
+        RawCsc r;
+        r.p.assign((size_t)M + 1, 0);
+        for (int64_t j = 0; j < M; ++j) {
+            int64_t ea = a_p[j];
+            const int64_t ea1 = a_p[j + 1];
+            for (int64_t e = d_p[j]; e < d_p[j + 1]; ++e) {
+                const int32_t i = d_i[e];
+                const double dv = d_x[e];
+                if (i < 0 || i >= N) throw Error(CDL_ERR_INVALID, "row index out of range in D");
+                if (is_na(dv) || dv == 0.0) continue;
+                check_count(dv, "D");
+                while (ea < ea1 && a_i[ea] < i) {
+                    if (!is_na(a_x[ea]) && a_x[ea] != 0.0)
+                        throw Error(CDL_ERR_INVALID, "A has a count where D is zero/missing");
+                    ++ea;
+                }
+                double av = 0.0;
+                if (ea < ea1 && a_i[ea] == i) { av = is_na(a_x[ea]) ? 0.0 : a_x[ea]; ++ea; }
+                check_count(av, "A");
+                if (av > dv) throw Error(CDL_ERR_INVALID, "A exceeds D for some entry");
+                r.i.push_back(i);
+                r.a.push_back((uint16_t)av);
+                r.d.push_back((uint16_t)dv);
+            }
+            r.p[(size_t)j + 1] = (int64_t)r.i.size();
+        }
+        upload_raw(h, N, M, r);
+    });
+}
+
+int cdl_load_csc_u16(cdl_handle h, int64_t N, int64_t M, const int64_t* p, const int32_t* i, const uint16_t* a,
+                     const uint16_t* d) {
+    return guard(h, [&] {
+        if (!p || N <= 0 || M <= 0) throw Error(CDL_ERR_INVALID, "bad sparse input");
+        const int64_t nnz = p[M];
+        if (p[0] != 0 || nnz < 0) throw Error(CDL_ERR_INVALID, "bad column pointers");
+        DevBuf<int64_t> pd((size_t)M + 1);
+        DevBuf<int32_t> vi((size_t)nnz);
+        DevBuf<uint16_t> ad((size_t)nnz), dd((size_t)nnz);
+        pd.upload(p, (size_t)M + 1, h->st);
+        if (nnz) {
+            vi.upload(i, (size_t)nnz, h->st);
+            ad.upload(a, (size_t)nnz, h->st);
+            dd.upload(d, (size_t)nnz, h->st);
+        }
+        cudaFree(h->donor.labels);
+        h->donor.labels = nullptr;
+        h->donor.M_total = 0;
+        h->donor.cell_offset = 0;
+        donor_build(h->donor, N, M, nnz, pd.p, vi.p, ad.p, dd.p, h->st);
+        h->has_data = true;
+        h->chains.clear();
+        h->have_sweep = false;
+    });
+}
+
+int cdl_synth_generate(cdl_handle h, int64_t N, int64_t M_total, int64_t cell_offset, int64_t M_local, int32_t K,
+                       const double* Config, double coverage, uint64_t seed) {
+    return guard(h, [&] {
+        if (!Config || N <= 0 || M_local <= 0 || cell_offset < 0 || cell_offset + M_local > M_total)
+            throw Error(CDL_ERR_INVALID, "bad synthetic donor shape");
+        synth_generate(h->donor, N, M_total, cell_offset, M_local, K, Config, coverage, seed, h->st);
+        h->has_data = true;
+        h->chains.clear();
+        h->have_sweep = false;
+    });
+}
+
+int cdl_synth_labels(cdl_handle h, int32_t* labels_out) {
+    return guard(h, [&] {
+        require_data(h);
+        if (!h->donor.labels) throw Error(CDL_ERR_STATE, "donor is not synthetic");
+        CDL_CUDA(cudaMemcpyAsync(labels_out, h->donor.labels, 4 * (size_t)h->donor.M, cudaMemcpyDeviceToHost, h->st));
+        CDL_CUDA(cudaStreamSynchronize(h->st));
+    });
+}
+
+int cdl_export_csc_u16(cdl_handle h, int64_t* p, int32_t* i, uint16_t* a, uint16_t* d) {
+    return guard(h, [&] {
+        require_data(h);
+        donor_export(h->donor, p, i, a, d, h->st);
+    });
+}
+
+int cdl_data_info(cdl_handle h, int64_t* N, int64_t* M, int64_t* nnz, double* W_log) {
+    return guard(h, [&] {
+        require_data(h);
+        if (N) *N = h->donor.N;
+        if (M) *M = h->donor.M;
+        if (nnz) *nnz = h->donor.nnz;
+        if (W_log) *W_log = h->donor.W_log;
+    });
+}
+
+int cdl_comm_unique_id(cdl_handle h, const char* nccl_lib_path, uint8_t* id128) {
+    return guard(h, [&] {
+        nccl_load(h, nccl_lib_path);
+        nccl_check(h, h->nccl.GetUniqueId(id128), "ncclGetUniqueId");
+    });
+}
+
+int cdl_comm_init(cdl_handle h, const char* nccl_lib_path, const uint8_t* id128, int32_t rank, int32_t world) {
+    return guard(h, [&] {
+        if (world < 1 || rank < 0 || rank >= world) throw Error(CDL_ERR_INVALID, "bad rank/world");
+        nccl_load(h, nccl_lib_path);
+        Id128 id;
+        std::memcpy(id.b, id128, 128);
+        nccl_check(h, h->nccl.CommInitRank(&h->comm, world, id, rank), "ncclCommInitRank");
+        h->rank = rank;
+        h->world = world;
+    });
+}
+
+void cdl_gibbs_defaults(cdl_gibbs_params* p) {
+    if (!p) return;
+    std::memset(p, 0, sizeof(*p));
+    p->relax_Config = 1;
+    p->relax_rate_fixed_set = 0;
+    p->relax_rate_prior[0] = 1; p->relax_rate_prior[1] = 9;
+    p->keep_base_clone = 1;
+    p->prior0[0] = 0.2; p->prior0[1] = 99.8;
+    p->prior1[0] = 0.45; p->prior1[1] = 0.55;
+    p->min_iter = 5000; p->max_iter = 20000;
+    p->buin_frac = 0.5;
+    p->wise = CDL_WISE_VARIANT;
+    p->n_chain = 1;
+    p->seed = 1;
+    p->keep_prob_all = -1;
+    p->trace_budget_bytes = (int64_t)48 << 30;
+    p->check_every = 100;
+}
+
+int cdl_gibbs_run(cdl_handle h, const double* Config, int32_t K, const double* Psi, const cdl_gibbs_params* params,
+                  const cdl_replay* replay) {
+    return guard(h, [&] {
+        require_data(h);
+        if (!Config || !params) throw Error(CDL_ERR_INVALID, "Config and params are required");
+        const cdl_gibbs_params gp = *params;
+        const Donor& d = h->donor;
+        if (K < 1 || K > KMAX) throw Error(CDL_ERR_UNSUPPORTED, "number of clones must be in 1..32");
+        if (gp.wise != CDL_WISE_GLOBAL && gp.wise != CDL_WISE_VARIANT) {
+            if (gp.wise == CDL_WISE_ELEMENT)
+                throw Error(CDL_ERR_UNSUPPORTED, "wise = \"element\" is not implemented yet in this build");
+            throw Error(CDL_ERR_INVALID, "Input wise mode: unknown, while only supporting: element, variant, global");
+        }
+        if (gp.max_iter < 2) throw Error(CDL_ERR_INVALID, "max_iter must be at least 2");
+        if (gp.relax_Config && gp.relax_rate_fixed_set && (gp.relax_rate_fixed > 1 || gp.relax_rate_fixed < 0))
+            throw Error(CDL_ERR_INVALID, "relax_rate_fixed needs to be NULL or in [0, 1].");
+        if (gp.n_chain < 1) throw Error(CDL_ERR_INVALID, "n_chain must be >= 1");
+        if (replay && gp.n_chain != 1) throw Error(CDL_ERR_INVALID, "replay mode runs a single chain");
+        if (replay && replay->n_rows < gp.max_iter) throw Error(CDL_ERR_INVALID, "replay arrays shorter than max_iter");
+        if (gp.acc_fp32) throw Error(CDL_ERR_UNSUPPORTED, "acc_fp32 is reserved");
+        if (d.max_variant_depth >= (1ull << 32))
+            throw Error(CDL_ERR_UNSUPPORTED, "a variant's total depth exceeds 2^32 (packed statistics)");
+
+        h->chains.clear();
+        h->gp = gp;
+        h->K = K;
+        const int64_t N = d.N, M = d.M, T = gp.max_iter;
+        const int64_t n_el = gp.wise == CDL_WISE_VARIANT ? N : 1;
+        h->T = T;
+        h->n_el = n_el;
+        std::vector<uint32_t> masks = config_masks(Config, N, K, true);
+        h->cfg0.alloc((size_t)N);
+        h->cfg0.upload(masks.data(), (size_t)N, h->st);
+        if (gp.prior1_matrix) {
+            h->prior1_mat.alloc((size_t)n_el * 2);
+            h->prior1_mat.upload(gp.prior1_matrix, (size_t)n_el * 2, h->st);
+        } else {
+            h->prior1_mat.release();
+        }
+
+        SweepArgs a{};
+        a.N = N; a.M = M; a.M_total = d.M_total; a.cell_offset = d.cell_offset;
+        a.K = K; a.wise = gp.wise; a.relax = gp.relax_Config ? 1 : 0; a.keep_base = gp.keep_base_clone ? 1 : 0;
+        for (int q = 0; q < 2; ++q) {
+            a.prior0[q] = gp.prior0[q]; a.prior1[q] = gp.prior1[q]; a.relax_prior[q] = gp.relax_rate_prior[q];
+        }
+        a.prior1_mat = gp.prior1_matrix ? h->prior1_mat.p : nullptr;
+        a.relax_fixed = gp.relax_rate_fixed; a.relax_fixed_set = gp.relax_rate_fixed_set ? 1 : 0;
+        fill_logpsi(Psi, K, a.logPsi);
+        a.cfg0 = h->cfg0.p;
+        a.W_log = allreduce_scalar_d(h, d.W_log);
+        a.key = PhiloxKey{(uint32_t)(gp.seed & 0xffffffffu), (uint32_t)(gp.seed >> 32)};
+        a.T = T;
+
+        // replay arrays -> device
+        DevBuf<double> r_ua, r_uc, r_t0, r_t1, r_rr;
+        cdl_replay rp_dev{};
+        const cdl_replay* rp = nullptr;
+        if (replay) {
+            const size_t R = (size_t)replay->n_rows;
+            auto up = [&](DevBuf<double>& b, const double* src, size_t n) -> const double* {
+                if (!src) return nullptr;
+                b.alloc(n);
+                b.upload(src, n, h->st);
+                return b.p;
+            };
+            rp_dev.n_rows = replay->n_rows;
+            rp_dev.u_assign = up(r_ua, replay->u_assign, R * (size_t)M);
+            rp_dev.u_config = up(r_uc, replay->u_config, R * (size_t)(N * K));
+            rp_dev.theta0 = up(r_t0, replay->theta0, R);
+            rp_dev.theta1 = up(r_t1, replay->theta1, R * (size_t)n_el);
+            rp_dev.relax_rate = up(r_rr, replay->relax_rate, R);
+            rp = &rp_dev;
+        }
+
+        // exact mode?
+        const double trace_bytes = (double)T * (double)M * (double)K * 8.0;
+        bool exact = gp.keep_prob_all == 1 || (gp.keep_prob_all == -1 && trace_bytes <= (double)gp.trace_budget_bytes);
+        const int check_every = gp.check_every > 0 ? gp.check_every : 100;
+        const int64_t n_buin_planned = (int64_t)std::ceil((double)T * gp.buin_frac);
+        DevBuf<unsigned long long> gcounts(2);
+
+        for (int c = 0; c < gp.n_chain; ++c) {
+            std::unique_ptr<Chain> chp(new Chain());
+            Chain& ch = *chp;
+            ch.scal.alloc(16); ch.scal.zero(h->st);
+            ch.l1.alloc((size_t)n_el); ch.l1c.alloc((size_t)n_el);
+            ch.mask.alloc((size_t)N);
+            ch.z.alloc((size_t)M); ch.z.zero(h->st);
+            ch.sab.alloc((size_t)(N * K)); ch.sab.zero(h->st);
+            ch.theta0_all.alloc((size_t)T); ch.theta0_all.zero(h->st);
+            ch.theta1_all.alloc((size_t)(T * n_el)); ch.theta1_all.zero(h->st);
+            ch.loglik_all.alloc((size_t)T); ch.loglik_all.zero(h->st);
+            ch.relax_all.alloc((size_t)T);
+            {
+                std::vector<double> rr((size_t)T, (gp.relax_Config && gp.relax_rate_fixed_set) ? gp.relax_rate_fixed : 0.0);
+                ch.relax_all.upload(rr.data(), (size_t)T, h->st);
+                CDL_CUDA(cudaStreamSynchronize(h->st));
+            }
+            ch.config_all.alloc((size_t)(T * N * K)); ch.config_all.zero(h->st);
+            if (exact) { ch.prob_all.alloc((size_t)(T * M * K)); ch.prob_all.zero(h->st); }
+            else { ch.prob_acc.alloc((size_t)(M * K)); ch.prob_acc.zero(h->st); }
+            if (gp.keep_assign_all) { ch.assign_all.alloc((size_t)(T * M)); ch.assign_all.zero(h->st); }
+            const size_t tgrid = (size_t)((N + 255) / 256) + 1;
+            ch.part_d.alloc(tgrid * 4); ch.part_u.alloc(tgrid * 8);
+            ch.ticket.alloc(1); ch.ticket.zero(h->st);
+            if (cells_smem_bytes(N, K) > 200 * 1024) ch.tab_g.alloc((size_t)N);
+            ch.dev.scal = ch.scal.p; ch.dev.l1 = ch.l1.p; ch.dev.l1c = ch.l1c.p; ch.dev.mask = ch.mask.p;
+            ch.dev.z = ch.z.p; ch.dev.sab = ch.sab.p;
+            ch.dev.theta0_all = ch.theta0_all.p; ch.dev.theta1_all = ch.theta1_all.p;
+            ch.dev.loglik_all = ch.loglik_all.p; ch.dev.relax_all = ch.relax_all.p;
+            ch.dev.config_all = ch.config_all.p;
+            ch.dev.prob_all = exact ? ch.prob_all.p : nullptr;
+            ch.dev.assign_all = gp.keep_assign_all ? ch.assign_all.p : nullptr;
+            ch.dev.prob_acc = nullptr;
+            ch.dev.part_d = ch.part_d.p; ch.dev.part_u = ch.part_u.p; ch.dev.ticket = ch.ticket.p;
+            ch.dev.tab_g = ch.tab_g.p;
+
+            a.chain = (uint32_t)c;
+            // initial draws (row 1)
+            a.it = 1;
+            a.learn_relax_next = (a.relax && !a.relax_fixed_set && (2.0 > 0.1 * gp.min_iter + 5.0)) ? 1 : 0;
+            if (rp) {
+                a.rp_theta0 = rp->theta0; a.rp_theta1 = rp->theta1;
+                a.rp_relax_next = rp->relax_rate ? rp->relax_rate + 1 : nullptr;
+            }
+            launch_init_chain(a, ch.dev, h->st);
+            // with relax off, Config_all rows hold Config (resolution of reference quirk 1); row 1 stays 0
+            int64_t it_final = T;
+            double frac = NAN;
+            for (int64_t it = 2; it <= T; ++it) {
+                ch.dev.prob_acc = (!exact && it >= n_buin_planned) ? ch.prob_acc.p : nullptr;
+                one_sweep(h, ch, a, (uint32_t)it, rp, n_el);
+                if (exact && it >= gp.min_iter && it % check_every == 0) {
+                    frac = geweke_fraction(h, ch, it, gcounts);
+                    if (gp.verbose) std::printf("%g%% converged.\n", r_round3_percent(frac));
+                    if (frac > 0.995) { it_final = it; break; }
+                }
+            }
+            const int64_t itf = it_final;
+            if (exact) frac = geweke_fraction(h, ch, itf, gcounts);
+            ch.info.n_iter = (int32_t)itf;
+            ch.info.percent_converged = r_round3_percent(frac);
+            const int64_t n_buin = exact ? (int64_t)std::ceil((double)itf * gp.buin_frac) : n_buin_planned;
+            ch.info.n_buin = (int32_t)n_buin;
+            ch.info.n_element = (int32_t)n_el;
+            ch.info.exact_trace = exact ? 1 : 0;
+            ch.info.W_log = a.W_log;
+            const int64_t r0 = n_buin - 1, r1 = itf;
+            // posterior means (:645-653)
+            ch.prob_mean.alloc((size_t)(M * K));
+            if (exact) launch_col_means_d(ch.prob_all.p, M * K, r0, r1, ch.prob_mean.p, h->st);
+            else {
+                // accumulator holds the sum over rows [n_buin_planned, T]
+                std::vector<double> acc((size_t)(M * K));
+                ch.prob_acc.download(acc.data(), acc.size(), h->st);
+                const double inv = 1.0 / (double)(r1 - r0);
+                for (double& v : acc) v *= inv;
+                ch.prob_mean.upload(acc.data(), acc.size(), h->st);
+                CDL_CUDA(cudaStreamSynchronize(h->st));
+            }
+            ch.config_prob.alloc((size_t)(N * K));
+            launch_col_means_u8(ch.config_all.p, N * K, r0, r1, ch.config_prob.p, h->st);
+            ch.theta1_mean.alloc((size_t)n_el);
+            launch_col_means_d(ch.theta1_all.p, n_el, r0, r1, ch.theta1_mean.p, h->st);
+            std::vector<double> t0((size_t)itf), rr((size_t)itf), ll((size_t)itf);
+            ch.theta0_all.download(t0.data(), (size_t)itf, h->st);
+            ch.relax_all.download(rr.data(), (size_t)itf, h->st);
+            ch.loglik_all.download(ll.data(), (size_t)itf, h->st);
+            double s0 = 0, sr = 0;
+            for (int64_t r = r0; r < r1; ++r) { s0 += t0[(size_t)r]; sr += rr[(size_t)r]; }
+            ch.theta0_mean = s0 / (double)(r1 - r0);
+            ch.relax_mean = sr / (double)(r1 - r0);
+            // logLik_post + DIC (:656-657)
+            double llp = loglik_general(d, ch.config_prob.p, K, nullptr, ch.prob_mean.p, ch.theta0_mean,
+                                        ch.theta1_mean.p, n_el, h->st);
+            if (h->world > 1) llp = allreduce_scalar_d(h, llp);
+            ch.info.logLik_post = llp;
+            std::vector<double> llw(ll.begin() + r0, ll.begin() + r1);
+            dic_from_trace(llw, llp, ch.info.dic);
+            ch.done = true;
+            h->chains.push_back(std::move(chp));
+        }
+        a.rp_u_assign = a.rp_u_config = a.rp_theta0 = a.rp_theta1 = a.rp_relax_next = nullptr;
+        h->sweep = a;
+        h->have_sweep = true;
+        CDL_CUDA(cudaStreamSynchronize(h->st));
+    });
+}
+
+int cdl_gibbs_info_get(cdl_handle h, int32_t chain, cdl_gibbs_info* out) {
+    return guard(h, [&] { *out = get_chain(h, chain).info; });
+}
+
+int cdl_fetch_prob(cdl_handle h, int32_t chain, double* out) {
+    return guard(h, [&] {
+        Chain& ch = get_chain(h, chain);
+        const int64_t M = h->donor.M, K = h->K;
+        std::vector<double> t((size_t)(M * K));
+        ch.prob_mean.download(t.data(), t.size(), h->st);
+        for (int64_t j = 0; j < M; ++j)
+            for (int64_t k = 0; k < K; ++k) out[j + k * M] = t[(size_t)(j * K + k)];
+    });
+}
+
+int cdl_fetch_config_prob(cdl_handle h, int32_t chain, double* out) {
+    return guard(h, [&] {
+        Chain& ch = get_chain(h, chain);
+        ch.config_prob.download(out, (size_t)(h->donor.N * h->K), h->st);
+    });
+}
+
+int cdl_fetch_theta(cdl_handle h, int32_t chain, double* theta0, double* theta1_elems) {
+    return guard(h, [&] {
+        Chain& ch = get_chain(h, chain);
+        if (theta0) *theta0 = ch.theta0_mean;
+        if (theta1_elems) ch.theta1_mean.download(theta1_elems, (size_t)h->n_el, h->st);
+    });
+}
+
+int cdl_fetch_theta_traces(cdl_handle h, int32_t chain, double* theta0_all, double* theta1_all) {
+    return guard(h, [&] {
+        Chain& ch = get_chain(h, chain);
+        const size_t n = (size_t)ch.info.n_iter;
+        if (theta0_all) ch.theta0_all.download(theta0_all, n, h->st);
+        if (theta1_all) {
+            // R shape n_iter x n_element column-major
+            std::vector<double> t(n * (size_t)h->n_el);
+            ch.theta1_all.download(t.data(), t.size(), h->st);
+            for (size_t r = 0; r < n; ++r)
+                for (size_t e = 0; e < (size_t)h->n_el; ++e) theta1_all[r + e * n] = t[r * (size_t)h->n_el + e];
+        }
+    });
+}
+
+int cdl_fetch_loglik_trace(cdl_handle h, int32_t chain, double* out) {
+    return guard(h, [&] {
+        Chain& ch = get_chain(h, chain);
+        ch.loglik_all.download(out, (size_t)ch.info.n_iter, h->st);
+    });
+}
+
+int cdl_fetch_relax_rate(cdl_handle h, int32_t chain, double* mean_out, double* all_out) {
+    return guard(h, [&] {
+        Chain& ch = get_chain(h, chain);
+        if (mean_out) *mean_out = ch.relax_mean;
+        if (all_out) ch.relax_all.download(all_out, (size_t)ch.info.n_iter, h->st);
+    });
+}
+
+int cdl_fetch_prob_all(cdl_handle h, int32_t chain, double* out) {
+    return guard(h, [&] {
+        Chain& ch = get_chain(h, chain);
+        if (!ch.info.exact_trace) throw Error(CDL_ERR_STATE, "prob_all was not kept (streaming mode)");
+        const int64_t M = h->donor.M, K = h->K, n = ch.info.n_iter;
+        std::vector<double> row((size_t)(M * K));
+        for (int64_t t = 0; t < n; ++t) {
+            ch.prob_all.download(row.data(), row.size(), h->st, (size_t)(t * M * K));
+            double* o = out + t * M * K;
+            for (int64_t j = 0; j < M; ++j)
+                for (int64_t k = 0; k < K; ++k) o[k * M + j] = row[(size_t)(j * K + k)];
+        }
+    });
+}
+
+int cdl_fetch_config_all(cdl_handle h, int32_t chain, double* out) {
+    return guard(h, [&] {
+        Chain& ch = get_chain(h, chain);
+        const size_t n = (size_t)ch.info.n_iter * (size_t)(h->donor.N * h->K);
+        std::vector<uint8_t> t(n);
+        ch.config_all.download(t.data(), n, h->st);
+        for (size_t q = 0; q < n; ++q) out[q] = (double)t[q];
+    });
+}
+
+int cdl_fetch_assign_all(cdl_handle h, int32_t chain, int32_t* out) {
+    return guard(h, [&] {
+        Chain& ch = get_chain(h, chain);
+        if (!ch.assign_all.p) throw Error(CDL_ERR_STATE, "assign_all was not kept (keep_assign_all = 0)");
+        const size_t n = (size_t)ch.info.n_iter * (size_t)h->donor.M;
+        std::vector<uint8_t> t(n);
+        ch.assign_all.download(t.data(), n, h->st);
+        for (size_t q = 0; q < n; ++q) out[q] = (int32_t)t[q];
+    });
+}
+
+int cdl_fetch_prob_variant(cdl_handle h, int32_t chain, double* out) {
+    return guard(h, [&] {
+        Chain& ch = get_chain(h, chain);
+        const Donor& d = h->donor;
+        const double bytes = (double)d.N * (double)d.M * 8.0;
+        if (bytes > 16e9) throw Error(CDL_ERR_UNSUPPORTED, "dense prob_variant would exceed 16 GB");
+        DevBuf<double> pv((size_t)(d.N * d.M));
+        launch_prob_variant(d, h->gp.wise, ch.theta0_all.p, ch.theta1_all.p, h->n_el, ch.info.n_buin - 1,
+                            ch.info.n_iter, pv.p, h->st);
+        pv.download(out, (size_t)(d.N * d.M), h->st);
+    });
+}
+
+int cdl_fetch_element_index(cdl_handle h, int64_t* out) {
+    return guard(h, [&] {
+        require_data(h);
+        const Donor& d = h->donor;
+        std::vector<int64_t> p((size_t)d.M + 1);
+        std::vector<int32_t> vi((size_t)d.nnz);
+        std::vector<uint16_t> a((size_t)d.nnz), dd((size_t)d.nnz);
+        donor_export(d, p.data(), vi.data(), a.data(), dd.data(), h->st);
+        for (int64_t j = 0; j < d.M; ++j)
+            for (int64_t e = p[(size_t)j]; e < p[(size_t)j + 1]; ++e) out[e] = vi[(size_t)e] + j * d.N;
+    });
+}
+
+int cdl_get_loglik(cdl_handle h, const double* Config, int32_t K, const int32_t* assign, const double* assign_prob,
+                   double theta0, const double* theta1, int64_t n_theta1, double* out) {
+    return guard(h, [&] {
+        require_data(h);
+        const Donor& d = h->donor;
+        if (!Config || !theta1 || !out || K < 1) throw Error(CDL_ERR_INVALID, "bad arguments");
+        if ((assign == nullptr) == (assign_prob == nullptr))
+            throw Error(CDL_ERR_INVALID, "give exactly one of assign / assign_prob");
+        if (n_theta1 != 1 && n_theta1 != d.N) throw Error(CDL_ERR_INVALID, "theta1 must have 1 or N values");
+        DevBuf<double> cfg((size_t)(d.N * K)), th1((size_t)n_theta1), pr;
+        DevBuf<int32_t> as;
+        cfg.upload(Config, (size_t)(d.N * K), h->st);
+        th1.upload(theta1, (size_t)n_theta1, h->st);
+        std::vector<double> t;
+        if (assign) {
+            for (int64_t j = 0; j < d.M; ++j)
+                if (assign[j] < 1 || assign[j] > K) throw Error(CDL_ERR_INVALID, "assignment label out of range");
+            as.alloc((size_t)d.M);
+            as.upload(assign, (size_t)d.M, h->st);
+        } else {
+            t.resize((size_t)(d.M * K));
+            for (int64_t j = 0; j < d.M; ++j)
+                for (int64_t k = 0; k < K; ++k) t[(size_t)(j * K + k)] = assign_prob[j + k * d.M];
+            pr.alloc(t.size());
+            pr.upload(t.data(), t.size(), h->st);
+        }
+        double v = loglik_general(d, cfg.p, K, as.p, pr.p, theta0, th1.p, n_theta1, h->st);
+        if (h->world > 1) v = allreduce_scalar_d(h, v);
+        *out = v;
+    });
+}
+
+int cdl_em_run(cdl_handle h, const double* Config, int32_t K, const double* Psi, int32_t min_iter, int32_t max_iter,
+               double logLik_threshold, const double* theta_init, uint64_t seed, double* theta_out, double* prob_out,
+               double* logLik_out, int32_t* n_iter_out) {
+    return guard(h, [&] {
+        require_data(h);
+        const Donor& d = h->donor;
+        if (!Config || K < 1 || K > KMAX) throw Error(CDL_ERR_UNSUPPORTED, "number of clones must be in 1..32");
+        if (d.max_cell_depth >= (1ull << 32)) throw Error(CDL_ERR_UNSUPPORTED, "a cell's total depth exceeds 2^32");
+        const int64_t M = d.M;
+        std::vector<uint32_t> masks = config_masks(Config, d.N, K, true);
+        DevBuf<uint32_t> cfg((size_t)d.N), S3((size_t)(M * K)), S4((size_t)(M * K)), TA((size_t)M), TB((size_t)M);
+        cfg.upload(masks.data(), (size_t)d.N, h->st);
+        double logPsi[KMAX];
+        fill_logpsi(Psi, K, logPsi);
+        DevBuf<double> lp(KMAX), prob((size_t)(M * K)), sums(5), partials((size_t)(((M + 255) / 256) * 5));
+        lp.upload(logPsi, KMAX, h->st);
+        em_stats(d, cfg.p, K, S3.p, S4.p, TA.p, TB.p, h->sm_count, h->st);
+        const double W_log = allreduce_scalar_d(h, d.W_log);
+        double theta[2];
+        if (theta_init) { theta[0] = theta_init[0]; theta[1] = theta_init[1]; }
+        else {
+            PhiloxKey key{(uint32_t)(seed & 0xffffffffu), (uint32_t)(seed >> 32)};
+            theta[0] = 0.001 + philox_uniform(key, 0, 0, STREAM_EM_INIT, 0) * (0.25 - 0.001);
+            theta[1] = 0.3 + philox_uniform(key, 0, 0, STREAM_EM_INIT, 1) * (0.6 - 0.3);
+        }
+        double logLik = 0.0, logLik_new = logLik + logLik_threshold * 2;
+        int it = 0;
+        for (it = 1; it <= max_iter; ++it) {
+            if (it > min_iter && (logLik_new - logLik) < logLik_threshold) break;
+            logLik = logLik_new;
+            em_iteration(M, K, S3.p, S4.p, TA.p, TB.p, lp.p, theta[0], theta[1], prob.p, sums.p, partials.p, h->st);
+            double s[5];
+            if (h->world > 1)
+                nccl_check(h, h->nccl.AllReduce(sums.p, sums.p, 5, NCCL_F64, NCCL_SUM, h->comm, h->st), "ncclAllReduce");
+            sums.download(s, 5, h->st);
+            logLik_new = s[0] + W_log;
+            theta[0] = (s[2] != s[2] || s[2] == 0.0) ? 0.02 : s[1] / s[2];
+            theta[1] = (s[4] != s[4] || s[4] == 0.0) ? 0.75 : s[3] / s[4];
+        }
+        if (it > max_iter) it = max_iter;   // R's `it` after a completed for loop is the last value
+        if (theta_out) { theta_out[0] = theta[0]; theta_out[1] = theta[1]; }
+        if (logLik_out) *logLik_out = logLik;
+        if (n_iter_out) *n_iter_out = it;
+        if (prob_out) {
+            std::vector<double> t((size_t)(M * K));
+            prob.download(t.data(), t.size(), h->st);
+            for (int64_t j = 0; j < M; ++j)
+                for (int64_t k = 0; k < K; ++k) prob_out[j + k * M] = t[(size_t)(j * K + k)];
+        }
+    });
+}
+
+int cdl_bench_sweeps(cdl_handle h, int32_t warmup, int32_t n, float* ms_total, float* ms_cells, float* ms_stats,
+                     float* ms_table, int64_t* launches) {
+    return guard(h, [&] {
+        if (!h->have_sweep || h->chains.empty()) throw Error(CDL_ERR_STATE, "run cdl_gibbs_run first");
+        Chain& ch = *h->chains[0];
+        SweepArgs a = h->sweep;
+        a.chain = 0;
+        const uint32_t it = (uint32_t)h->T;     // keep overwriting the last trace row
+        ch.dev.prob_acc = nullptr;
+        for (int w = 0; w < warmup; ++w) one_sweep(h, ch, a, it, nullptr, h->n_el);
+        cudaEvent_t e0, e1;
+        CDL_CUDA(cudaEventCreate(&e0));
+        CDL_CUDA(cudaEventCreate(&e1));
+        CDL_CUDA(cudaStreamSynchronize(h->st));
+        const int64_t l0 = h->launches;
+        CDL_CUDA(cudaEventRecord(e0, h->st));
+        for (int q = 0; q < n; ++q) one_sweep(h, ch, a, it, nullptr, h->n_el);
+        CDL_CUDA(cudaEventRecord(e1, h->st));
+        CDL_CUDA(cudaEventSynchronize(e1));
+        float tot = 0;
+        CDL_CUDA(cudaEventElapsedTime(&tot, e0, e1));
+        if (ms_total) *ms_total = tot;
+        if (launches) *launches = h->launches - l0;
+        // per-kernel breakdown (separate pass so the events do not perturb the total)
+        float tc = 0, ts = 0, tt = 0;
+        if (ms_cells || ms_stats || ms_table) {
+            cudaEvent_t ev[4];
+            for (auto& e : ev) CDL_CUDA(cudaEventCreate(&e));
+            for (int q = 0; q < n; ++q) {
+                a.it = it;
+                a.learn_relax_next = (a.relax && !a.relax_fixed_set && ((double)(it + 1) > 0.1 * h->gp.min_iter + 5.0)) ? 1 : 0;
+                CDL_CUDA(cudaEventRecord(ev[0], h->st));
+                launch_cells(h->donor, a, ch.dev, h->sm_count, h->st);
+                CDL_CUDA(cudaEventRecord(ev[1], h->st));
+                launch_stats(h->donor, a, ch.dev, h->sm_count, h->st);
+                allreduce_u64(h, ch.dev.sab, (size_t)(a.N * a.K));
+                CDL_CUDA(cudaEventRecord(ev[2], h->st));
+                launch_table(h->donor, a, ch.dev, h->st);
+                CDL_CUDA(cudaEventRecord(ev[3], h->st));
+                CDL_CUDA(cudaEventSynchronize(ev[3]));
+                float x;
+                CDL_CUDA(cudaEventElapsedTime(&x, ev[0], ev[1])); tc += x;
+                CDL_CUDA(cudaEventElapsedTime(&x, ev[1], ev[2])); ts += x;
+                CDL_CUDA(cudaEventElapsedTime(&x, ev[2], ev[3])); tt += x;
+            }
+            for (auto& e : ev) cudaEventDestroy(e);
+        }
+        if (ms_cells) *ms_cells = tc;
+        if (ms_stats) *ms_stats = ts;
+        if (ms_table) *ms_table = tt;
+        cudaEventDestroy(e0);
+        cudaEventDestroy(e1);
+    });
+}
+
+}  // extern "C"

@@ -1,0 +1,738 @@
+// The Gibbs sweep of clone_id_Gibbs (R/clone_id.R:466-593) as three kernels on sm_100a:
+//
+//   k_cells  one pass over the cell-major layout: logLik thin SpMM (:470-478) -> softmax (:479-481)
+//            -> categorical draw with sample()'s sorted-CDF walk (:492-497).
+//   k_stats  one pass over the variant-major layout: SA[i,k] = sum_{j: z_j = k} A_ij, SB likewise.
+//            These N x K integer tables carry everything the rest of the sweep needs:
+//            they replace the 4K dense S-lists (:394-403,537-542), the two N x M x K products of the
+//            relax step (:525-528) and the weighted sums of the theta step (:546-562).
+//   k_table  N x K work: relax-rate Beta draw (:501-517), Config flips (:528-535), theta0/theta1 Beta
+//            draws (:563-571), logLik trace with the OLD theta (:574-577 -> :734-752).
+//
+// Math is fp64 throughout (the tolerance in BASELINE.json is 1e-6 on probabilities whose logits are
+// sums of ~1e3 terms of magnitude ~10); HBM traffic per sweep is 6 bytes per covered entry per pass.
+#include "internal.h"
+
+namespace cdl {
+
+namespace {
+
+constexpr int CELLS_THREADS = 512;
+constexpr int STATS_THREADS = 256;
+constexpr int STATS_WARPS = STATS_THREADS / 32;
+constexpr int TABLE_THREADS = 256;
+
+template <int KP> struct Log2 {};
+template <> struct Log2<4> { static constexpr int v = 2; };
+template <> struct Log2<8> { static constexpr int v = 3; };
+template <> struct Log2<16> { static constexpr int v = 4; };
+template <> struct Log2<32> { static constexpr int v = 5; };
+
+struct CellsParams {
+    const uint32_t* rowgrp;
+    const void* vidx;
+    const uint16_t* ca;
+    const uint16_t* cb;
+    int64_t M, N, cell_offset;
+    int K;
+    int n_tab;                 // N (variant) or 1 (global)
+    const double* l1;
+    const double* l1c;
+    const double* scal;
+    const uint32_t* mask;
+    double logPsi[KMAX];
+    double* prob_row;          // [M*K] trace row to fill (device layout [cell][clone]) or nullptr
+    double* prob_acc;          // [M*K] accumulator or nullptr
+    uint8_t* z;
+    uint8_t* assign_row;       // [M] 1-based labels or nullptr
+    const double* rp_u;        // replay uniforms for this iteration or nullptr
+    PhiloxKey key;
+    uint32_t chain, it;
+    int tab_in_smem;
+};
+
+// R's revsort (src/main/sort.c) on a tiny array: used only when positive probabilities tie exactly,
+// where sample()'s result depends on the heapsort's tie order.
+__device__ void revsort_dev(double* a, int* ib, int n) {
+    if (n <= 1) return;
+    int l = (n >> 1) + 1, ir = n;
+    double ra;
+    int ii;
+    for (;;) {
+        if (l > 1) {
+            l = l - 1;
+            ra = a[l - 1];
+            ii = ib[l - 1];
+        } else {
+            ra = a[ir - 1];
+            ii = ib[ir - 1];
+            a[ir - 1] = a[0];
+            ib[ir - 1] = ib[0];
+            if (--ir == 1) {
+                a[0] = ra;
+                ib[0] = ii;
+                return;
+            }
+        }
+        int i = l, j = l << 1;
+        while (j <= ir) {
+            if (j < ir && a[j - 1] > a[j]) ++j;
+            if (ra > a[j - 1]) {
+                a[i - 1] = a[j - 1];
+                ib[i - 1] = ib[j - 1];
+                i = j;
+                j += i;
+            } else {
+                j = ir + 1;
+            }
+        }
+        a[i - 1] = ra;
+        ib[i - 1] = ii;
+    }
+}
+
+template <int KP>
+__device__ __forceinline__ void accumulate_entry(double (&acc)[KP], uint32_t a, uint32_t b, double2 t,
+                                                 uint32_t m) {
+    const double del = fma(u16_to_double(a), t.x, u16_to_double(b) * t.y);
+#pragma unroll
+    for (int k = 0; k < KP; ++k) acc[k] += ((m >> k) & 1u) ? del : 0.0;
+}
+
+template <int KP, typename VIdx, bool SMEM>
+__device__ __forceinline__ void accumulate_group(double (&acc)[KP], const uint32_t (&vw)[8], const uint4 a4,
+                                                 const uint4 b4, const double2* __restrict__ tab,
+                                                 const uint32_t* __restrict__ msk) {
+    const uint32_t aw[4] = {a4.x, a4.y, a4.z, a4.w};
+    const uint32_t bw[4] = {b4.x, b4.y, b4.z, b4.w};
+#pragma unroll
+    for (int e = 0; e < 8; ++e) {
+        const uint32_t i = vw[e];
+        const uint32_t a = (e & 1) ? (aw[e >> 1] >> 16) : (aw[e >> 1] & 0xffffu);
+        const uint32_t b = (e & 1) ? (bw[e >> 1] >> 16) : (bw[e >> 1] & 0xffffu);
+        double2 t;
+        uint32_t m;
+        if (SMEM) {
+            t = tab[i];
+            m = msk[i];
+        } else {
+            t = __ldg(tab + i);
+            m = __ldg(msk + i);
+        }
+        accumulate_entry<KP>(acc, a, b, t, m);
+    }
+}
+
+template <typename VIdx>
+__device__ __forceinline__ void load_vidx(const void* base, int64_t g, uint32_t (&vw)[8]);
+template <>
+__device__ __forceinline__ void load_vidx<uint16_t>(const void* base, int64_t g, uint32_t (&vw)[8]) {
+    const uint4 v = ld_stream(reinterpret_cast<const uint4*>(base) + g);
+    vw[0] = v.x & 0xffffu; vw[1] = v.x >> 16; vw[2] = v.y & 0xffffu; vw[3] = v.y >> 16;
+    vw[4] = v.z & 0xffffu; vw[5] = v.z >> 16; vw[6] = v.w & 0xffffu; vw[7] = v.w >> 16;
+}
+template <>
+__device__ __forceinline__ void load_vidx<uint32_t>(const void* base, int64_t g, uint32_t (&vw)[8]) {
+    const uint4 v0 = ld_stream(reinterpret_cast<const uint4*>(base) + 2 * g);
+    const uint4 v1 = ld_stream(reinterpret_cast<const uint4*>(base) + 2 * g + 1);
+    vw[0] = v0.x; vw[1] = v0.y; vw[2] = v0.z; vw[3] = v0.w;
+    vw[4] = v1.x; vw[5] = v1.y; vw[6] = v1.z; vw[7] = v1.w;
+}
+
+template <int KP, typename VIdx, bool SMEM>
+__global__ void __launch_bounds__(CELLS_THREADS) k_cells(const CellsParams P) {
+    constexpr int LOG = Log2<KP>::v;
+    constexpr int SH = 5 - LOG;          // lanes per clone after the transposing reduction
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    double2* s_tab = reinterpret_cast<double2*>(smem_raw);
+    uint32_t* s_msk = reinterpret_cast<uint32_t*>(smem_raw + sizeof(double2) * (size_t)(SMEM ? P.N : 0));
+    const double l0 = P.scal[SC_L0], l0c = P.scal[SC_L0C];
+    const double2* tab;
+    const uint32_t* msk;
+    if (SMEM) {
+        // stage the per-variant weight table: (log th1_i - log th0, log(1-th1_i) - log(1-th0)) and the
+        // Config_new row as a clone bit mask.  logLik[j,k] = base_j + sum_i C_ik * delta_ij; base_j
+        // cancels in the softmax.
+        for (int64_t i = threadIdx.x; i < P.N; i += blockDim.x) {
+            const int64_t t = P.n_tab == 1 ? 0 : i;
+            s_tab[i] = make_double2(P.l1[t] - l0, P.l1c[t] - l0c);
+            s_msk[i] = P.mask[i];
+        }
+        __syncthreads();
+        tab = s_tab;
+        msk = s_msk;
+    } else {
+        tab = reinterpret_cast<const double2*>(P.l1);   // pre-built (du, dv) table in global memory
+        msk = P.mask;
+    }
+    const int lane = threadIdx.x & 31;
+    const int64_t warp = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const int64_t nwarps = ((int64_t)gridDim.x * blockDim.x) >> 5;
+    const int K = P.K;
+    const int k = lane >> SH;
+    const bool rep = (lane & ((1 << SH) - 1)) == 0;
+    const double my_logpsi = (k < K) ? P.logPsi[k] : 0.0;
+    const uint4* a8 = reinterpret_cast<const uint4*>(P.ca);
+    const uint4* b8 = reinterpret_cast<const uint4*>(P.cb);
+
+    for (int64_t j = warp; j < P.M; j += nwarps) {
+        const int64_t g0 = P.rowgrp[j], g1 = P.rowgrp[j + 1];
+        double acc[KP];
+#pragma unroll
+        for (int q = 0; q < KP; ++q) acc[q] = 0.0;
+        for (int64_t g = g0 + lane; g < g1; g += 64) {
+            const bool two = (g + 32) < g1;
+            uint32_t v0[8], v1[8];
+            load_vidx<VIdx>(P.vidx, g, v0);
+            const uint4 a0 = ld_stream(a8 + g), b0 = ld_stream(b8 + g);
+            uint4 a1 = make_uint4(0, 0, 0, 0), b1 = a1;
+            if (two) {
+                load_vidx<VIdx>(P.vidx, g + 32, v1);
+                a1 = ld_stream(a8 + g + 32);
+                b1 = ld_stream(b8 + g + 32);
+            }
+            accumulate_group<KP, VIdx, SMEM>(acc, v0, a0, b0, tab, msk);
+            if (two) accumulate_group<KP, VIdx, SMEM>(acc, v1, a1, b1, tab, msk);
+        }
+        // transposing butterfly: afterwards lane holds the full sum of clone k = lane >> SH
+#pragma unroll
+        for (int s = 0; s < LOG; ++s) {
+            constexpr int dummy = 0; (void)dummy;
+            const int off = 16 >> s;
+            const int n = KP >> (s + 1);
+            const bool up = (lane & off) != 0;
+#pragma unroll
+            for (int q = 0; q < KP / 2; ++q) {
+                if (q < n) {
+                    const double send = up ? acc[q] : acc[q + n];
+                    const double keep = up ? acc[q + n] : acc[q];
+                    acc[q] = keep + shfl_xor_d(send, off);
+                }
+            }
+        }
+        double L = acc[0];
+#pragma unroll
+        for (int off = (1 << SH) >> 1; off >= 1; off >>= 1) L += shfl_xor_d(L, off);
+        L = (k < K) ? L + my_logpsi : -INFINITY;
+        double mx = L;
+#pragma unroll
+        for (int off = 16; off >= 1; off >>= 1) mx = fmax(mx, shfl_xor_d(mx, off));
+        const double ex = exp(L - mx);
+        double sm = ex;
+#pragma unroll
+        for (int off = 16; off >= (1 << SH); off >>= 1) sm += shfl_xor_d(sm, off);
+        const double pr = ex / sm;
+        if (rep && k < K) {
+            if (P.prob_row) P.prob_row[j * K + k] = pr;
+            if (P.prob_acc) P.prob_acc[j * K + k] += pr;
+        }
+        // ---- sample(seq_len(K), 1, prob = pr): walk the DESCENDING-sorted CDF with one uniform ----
+        const uint32_t gcell = (uint32_t)(P.cell_offset + j);
+        const double u = P.rp_u ? P.rp_u[j] : philox_uniform(P.key, P.chain, P.it, STREAM_ASSIGN, gcell);
+        double cum = 0.0;
+        int rank = 0;
+        bool tie = false;
+#pragma unroll
+        for (int l = 0; l < KP; ++l) {
+            const double pl = shfl_d(pr, l << SH);
+            if (l < K) {
+                const bool before = (pl > pr) || (pl == pr && l < k);
+                if (before) { cum += pl; ++rank; }
+                tie |= (pl == pr) && (l != k) && (pr > 0.0);
+            }
+        }
+        unsigned sel;
+        if (__any_sync(0xffffffffu, tie && k < K)) {
+            // exact emulation of revsort's tie order (rare: identical Config columns)
+            double pa[KP];
+            int perm[KP];
+#pragma unroll
+            for (int l = 0; l < KP; ++l) { pa[l] = shfl_d(pr, l << SH); perm[l] = l; }
+            double tot = 0.0;
+            for (int l = 0; l < K; ++l) tot += pa[l];
+            for (int l = 0; l < K; ++l) pa[l] /= tot;
+            revsort_dev(pa, perm, K);
+            for (int l = 1; l < K; ++l) pa[l] += pa[l - 1];
+            int jj = 0;
+            while (jj < K - 1 && !(u <= pa[jj])) ++jj;
+            sel = (unsigned)perm[jj];
+        } else {
+            const bool cand = u <= cum + pr;
+            const unsigned keyv = (k < K && (cand || rank == K - 1)) ? ((unsigned)rank << 8 | (unsigned)k)
+                                                                     : 0xffffffffu;
+            sel = __reduce_min_sync(0xffffffffu, keyv) & 0xffu;
+        }
+        if (lane == 0) {
+            P.z[j] = (uint8_t)sel;
+            if (P.assign_row) P.assign_row[j] = (uint8_t)(sel + 1);
+        }
+    }
+}
+
+// (du, dv) table in global memory for donors whose table does not fit shared memory
+__global__ void k_build_tab(int64_t N, int n_tab, const double* __restrict__ l1, const double* __restrict__ l1c,
+                            const double* __restrict__ scal, double2* __restrict__ out) {
+    int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+    if (i >= N) return;
+    const int64_t t = n_tab == 1 ? 0 : i;
+    out[i] = make_double2(l1[t] - scal[SC_L0], l1c[t] - scal[SC_L0C]);
+}
+
+// ------------------------------------------------------------------------------------------------
+struct StatsParams {
+    const uint32_t* seggrp;
+    const uint16_t* vc;
+    const uint16_t* va;
+    const uint16_t* vb;
+    const uint8_t* z;
+    unsigned long long* sab;
+    int64_t N, M;
+    int K;
+    int chunk;      // variants per CTA
+};
+
+template <int KP>
+__global__ void __launch_bounds__(STATS_THREADS) k_stats(const StatsParams P) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    uint2* s_bins = reinterpret_cast<uint2*>(smem_raw);                    // [WARPS][KP][32]
+    uint8_t* s_z = smem_raw + sizeof(uint2) * STATS_WARPS * KP * 32;       // [cells of this block]
+    const int cb = blockIdx.y;
+    const int64_t c0 = (int64_t)cb * CELL_BLOCK;
+    const int ncell = (int)min((int64_t)CELL_BLOCK, P.M - c0);
+    {
+        const int nvec = ncell >> 4;
+        const uint4* src = reinterpret_cast<const uint4*>(P.z + c0);
+        uint4* dst = reinterpret_cast<uint4*>(s_z);
+        for (int t = threadIdx.x; t < nvec; t += blockDim.x) dst[t] = src[t];
+        for (int t = (nvec << 4) + threadIdx.x; t < ncell; t += blockDim.x) s_z[t] = P.z[c0 + t];
+    }
+    __syncthreads();
+    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+    uint2* bins = s_bins + (size_t)w * KP * 32;
+    const int64_t i_lo = (int64_t)blockIdx.x * P.chunk;
+    const int64_t i_hi = min(P.N, i_lo + P.chunk);
+    const uint4* c8 = reinterpret_cast<const uint4*>(P.vc);
+    const uint4* a8 = reinterpret_cast<const uint4*>(P.va);
+    const uint4* b8 = reinterpret_cast<const uint4*>(P.vb);
+    for (int64_t i = i_lo + w; i < i_hi; i += STATS_WARPS) {
+        const int64_t seg = (int64_t)cb * P.N + i;
+        const int64_t g0 = P.seggrp[seg], g1 = P.seggrp[seg + 1];
+        if (g0 == g1) continue;
+#pragma unroll
+        for (int q = 0; q < KP; ++q) bins[q * 32 + lane] = make_uint2(0u, 0u);
+        for (int64_t g = g0 + lane; g < g1; g += 64) {
+            const bool two = (g + 32) < g1;
+            uint4 cw[2], aw[2], bw[2];
+            cw[0] = ld_stream(c8 + g); aw[0] = ld_stream(a8 + g); bw[0] = ld_stream(b8 + g);
+            if (two) { cw[1] = ld_stream(c8 + g + 32); aw[1] = ld_stream(a8 + g + 32); bw[1] = ld_stream(b8 + g + 32); }
+#pragma unroll
+            for (int h = 0; h < 2; ++h) {
+                if (h == 1 && !two) break;
+                const uint32_t cc[4] = {cw[h].x, cw[h].y, cw[h].z, cw[h].w};
+                const uint32_t aa[4] = {aw[h].x, aw[h].y, aw[h].z, aw[h].w};
+                const uint32_t bb[4] = {bw[h].x, bw[h].y, bw[h].z, bw[h].w};
+#pragma unroll
+                for (int e = 0; e < 8; ++e) {
+                    const uint32_t c = (e & 1) ? (cc[e >> 1] >> 16) : (cc[e >> 1] & 0xffffu);
+                    const uint32_t a = (e & 1) ? (aa[e >> 1] >> 16) : (aa[e >> 1] & 0xffffu);
+                    const uint32_t b = (e & 1) ? (bb[e >> 1] >> 16) : (bb[e >> 1] & 0xffffu);
+                    const uint32_t zz = s_z[c];
+                    uint2* bp = bins + zz * 32 + lane;
+                    uint2 v = *bp;
+                    v.x += a;
+                    v.y += b;
+                    *bp = v;
+                }
+            }
+        }
+        __syncwarp();
+        // column sums of the per-lane private bins: lane handles clone kk = lane % KP over a KP-wide
+        // slice of lanes, rotated so that a half-warp touches 16 distinct banks
+        const int kk = lane & (KP - 1);
+        const int h = lane / KP;                 // 0 .. 32/KP-1
+        unsigned long long sa = 0, sb = 0;
+#pragma unroll
+        for (int s = 0; s < KP; ++s) {
+            const int t = h * KP + ((s + kk) & (KP - 1));
+            const uint2 v = bins[kk * 32 + t];
+            sa += v.x;
+            sb += v.y;
+        }
+#pragma unroll
+        for (int off = KP; off < 32; off <<= 1) {
+            sa += __shfl_xor_sync(0xffffffffu, sa, off);
+            sb += __shfl_xor_sync(0xffffffffu, sb, off);
+        }
+        if (lane < P.K && (sa | sb)) atomicAdd(&P.sab[i * P.K + lane], sa | (sb << 32));
+        __syncwarp();
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+struct TableParams {
+    int64_t N;
+    int K, wise, relax, keep_base, learn_relax_next;
+    double prior0[2], prior1[2], relax_prior[2];
+    const double* prior1_mat;  // [n_el*2] or nullptr
+    int64_t n_el;
+    const uint32_t* cfg0;
+    uint32_t* mask;
+    const unsigned long long* sab;
+    double* scal;
+    double* l1;
+    double* l1c;
+    double W_log;
+    double* theta0_all; double* theta1_all; double* loglik_all; double* relax_all; uint8_t* config_all;
+    int64_t T;
+    uint32_t it;               // 1-based row being filled
+    PhiloxKey key; uint32_t chain;
+    const double* rp_u_config; const double* rp_theta0; const double* rp_theta1; const double* rp_relax_next;
+    double* part_d; unsigned long long* part_u; unsigned int* ticket;
+};
+
+__device__ __forceinline__ unsigned long long block_sum_u64(unsigned long long v, unsigned long long* sm) {
+    v = warp_sum_u64(v);
+    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+    __syncthreads();
+    if (lane == 0) sm[w] = v;
+    __syncthreads();
+    unsigned long long r = 0;
+    for (int q = 0; q < (int)(blockDim.x >> 5); ++q) r += sm[q];
+    return r;
+}
+__device__ __forceinline__ double block_sum_d(double v, double* sm) {
+    v = warp_sum_d(v);
+    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+    __syncthreads();
+    if (lane == 0) sm[w] = v;
+    __syncthreads();
+    double r = 0;
+    for (int q = 0; q < (int)(blockDim.x >> 5); ++q) r += sm[q];
+    return r;
+}
+
+__global__ void __launch_bounds__(TABLE_THREADS) k_table(const TableParams P) {
+    __shared__ unsigned long long sm_u[TABLE_THREADS / 32];
+    __shared__ double sm_d[TABLE_THREADS / 32];
+    __shared__ bool is_last;
+    const int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+    const double l0 = P.scal[SC_L0], l0c = P.scal[SC_L0C], r = P.scal[SC_RELAX];
+    const double odd1 = log(1.0 - r) - log(r);   // Config == 1: log(prior) - log(1 - prior), prior = 1 - r
+    const double odd0 = log(r) - log(1.0 - r);   // Config == 0: prior = r
+    unsigned long long S1 = 0, S2 = 0, S3 = 0, S4 = 0, diff1 = 0;
+    double ll = 0.0;
+    if (i < P.N) {
+        const int64_t t = P.wise == 1 ? i : 0;
+        const double l1 = P.l1[t], l1c = P.l1c[t];
+        const double du = l1 - l0, dv = l1c - l0c;
+        const uint32_t c0 = P.cfg0[i];
+        uint32_t nm = 0;
+        for (int k = 0; k < P.K; ++k) {
+            const unsigned long long pk = P.sab[i * P.K + k];
+            const double SA = (double)(uint32_t)pk, SB = (double)(uint32_t)(pk >> 32);
+            const uint32_t cbit = (c0 >> k) & 1u;
+            uint32_t bit = cbit;
+            if (P.relax) {
+                double prior;
+                if (P.keep_base && k == 0) prior = cbit ? INFINITY : -INFINITY;
+                else prior = cbit ? odd1 : odd0;
+                double x = SA * du + SB * dv + prior;
+                x = x > 50.0 ? 50.0 : (x < -50.0 ? -50.0 : x);
+                const double ex = exp(x);
+                const double p = ex / (ex + 1.0);
+                const uint32_t idx = (uint32_t)(i + (int64_t)k * P.N);
+                const double u = P.rp_u_config ? P.rp_u_config[idx]
+                                               : philox_uniform(P.key, P.chain, P.it, STREAM_CONFIG, idx);
+                bit = (uint32_t)rbinom1(p, u);
+            }
+            // Config_all row (:535); with relax off the row holds Config itself (the reference stops
+            // with "object 'Config_new' not found" there)
+            P.config_all[(int64_t)(P.it - 1) * P.N * P.K + i + (int64_t)k * P.N] = (uint8_t)bit;
+            nm |= bit << k;
+            if (bit) {
+                S3 += (uint32_t)pk; S4 += (uint32_t)(pk >> 32);
+                ll += SA * l1 + SB * l1c;
+            } else {
+                S1 += (uint32_t)pk; S2 += (uint32_t)(pk >> 32);
+                ll += SA * l0 + SB * l0c;
+            }
+            if (k >= 1) diff1 += (bit != cbit);
+        }
+        P.mask[i] = nm;
+        if (P.wise == 1) {
+            double th;
+            if (P.rp_theta1) th = clamp_theta(P.rp_theta1[i]);
+            else {
+                const double pa = P.prior1_mat ? P.prior1_mat[i] : P.prior1[0];
+                const double pb = P.prior1_mat ? P.prior1_mat[P.n_el + i] : P.prior1[1];
+                PhiloxSeq s(P.key, P.chain, P.it, STREAM_THETA1, (uint32_t)i);
+                th = beta_draw(pa + (double)S3, pb + (double)S4, s);
+            }
+            P.theta1_all[(int64_t)(P.it - 1) * P.n_el + i] = th;
+            P.l1[i] = log(th);
+            P.l1c[i] = log(1.0 - th);
+        }
+    }
+    const unsigned long long b1 = block_sum_u64(S1, sm_u), b2 = block_sum_u64(S2, sm_u);
+    const unsigned long long b3 = block_sum_u64(S3, sm_u), b4 = block_sum_u64(S4, sm_u);
+    const unsigned long long bd = block_sum_u64(diff1, sm_u);
+    const double bl = block_sum_d(ll, sm_d);
+    if (threadIdx.x == 0) {
+        unsigned long long* pu = P.part_u + (size_t)blockIdx.x * 8;
+        pu[0] = b1; pu[1] = b2; pu[2] = b3; pu[3] = b4; pu[4] = bd;
+        P.part_d[blockIdx.x] = bl;
+        __threadfence();
+        const unsigned int tk = atomicAdd(P.ticket, 1u);
+        is_last = (tk == gridDim.x - 1);
+    }
+    __syncthreads();
+    if (!is_last) return;
+    __threadfence();
+    // deterministic final reduction in block order
+    unsigned long long t1 = 0, t2 = 0, t3 = 0, t4 = 0, td = 0;
+    double tl = 0.0;
+    for (unsigned b = threadIdx.x; b < gridDim.x; b += blockDim.x) {
+        const volatile unsigned long long* pu = P.part_u + (size_t)b * 8;
+        t1 += pu[0]; t2 += pu[1]; t3 += pu[2]; t4 += pu[3]; td += pu[4];
+        tl += ((const volatile double*)P.part_d)[b];
+    }
+    t1 = block_sum_u64(t1, sm_u); t2 = block_sum_u64(t2, sm_u); t3 = block_sum_u64(t3, sm_u);
+    t4 = block_sum_u64(t4, sm_u); td = block_sum_u64(td, sm_u);
+    tl = block_sum_d(tl, sm_d);
+    if (threadIdx.x == 0) {
+        *P.ticket = 0;
+        const int64_t row = (int64_t)P.it - 1;
+        P.loglik_all[row] = tl + P.W_log;
+        double th0;
+        if (P.rp_theta0) th0 = clamp_theta(P.rp_theta0[0]);
+        else {
+            PhiloxSeq s(P.key, P.chain, P.it, STREAM_THETA0, 0);
+            th0 = beta_draw(P.prior0[0] + (double)t1, P.prior0[1] + (double)t2, s);
+        }
+        P.theta0_all[row] = th0;
+        P.scal[SC_THETA0] = th0;
+        P.scal[SC_L0] = log(th0);
+        P.scal[SC_L0C] = log(1.0 - th0);
+        if (P.wise == 0) {
+            double th;
+            if (P.rp_theta1) th = clamp_theta(P.rp_theta1[0]);
+            else {
+                const double pa = P.prior1_mat ? P.prior1_mat[0] : P.prior1[0];
+                const double pb = P.prior1_mat ? P.prior1_mat[1] : P.prior1[1];
+                PhiloxSeq s(P.key, P.chain, P.it, STREAM_THETA1, 0);
+                th = beta_draw(pa + (double)t3, pb + (double)t4, s);
+            }
+            P.theta1_all[row] = th;
+            P.l1[0] = log(th);
+            P.l1c[0] = log(1.0 - th);
+        }
+        if (P.learn_relax_next && (int64_t)P.it < P.T) {
+            const double d1 = (double)td;
+            const double d0 = (double)P.N * (double)(P.K - 1) - d1;
+            double rr;
+            if (P.rp_relax_next) rr = P.rp_relax_next[0];
+            else {
+                PhiloxSeq s(P.key, P.chain, P.it + 1, STREAM_RELAX, 0);
+                rr = beta_draw(P.relax_prior[0] + d1, P.relax_prior[1] + d0, s);
+            }
+            P.scal[SC_RELAX] = rr;
+            P.relax_all[row + 1] = rr;
+        }
+    }
+}
+
+// initial draws (R/clone_id.R:461-463) and state
+struct InitParams {
+    int64_t N, n_el;
+    int K, wise;
+    double prior0[2], prior1[2];
+    const double* prior1_mat;
+    const uint32_t* cfg0;
+    uint32_t* mask;
+    double* scal; double* l1; double* l1c;
+    double* theta0_all; double* theta1_all; double* relax_all;
+    double relax_init;
+    int learn_relax_first;     // iteration 2 already learns the relax rate (min_iter tiny)
+    double relax_prior[2];
+    PhiloxKey key; uint32_t chain;
+    const double* rp_theta0; const double* rp_theta1; const double* rp_relax_next;
+};
+
+__global__ void k_init(const InitParams P) {
+    const int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+    if (i < P.N) P.mask[i] = P.cfg0[i];
+    if (i < P.n_el) {
+        double th;
+        if (P.rp_theta1) th = clamp_theta(P.rp_theta1[i]);
+        else {
+            const double pa = P.prior1_mat ? P.prior1_mat[i] : P.prior1[0];
+            const double pb = P.prior1_mat ? P.prior1_mat[P.n_el + i] : P.prior1[1];
+            PhiloxSeq s(P.key, P.chain, 1, STREAM_THETA1, (uint32_t)i);
+            th = beta_draw(pa, pb, s);
+        }
+        P.theta1_all[i] = th;
+        P.l1[i] = log(th);
+        P.l1c[i] = log(1.0 - th);
+    }
+    if (i == 0) {
+        double th0;
+        if (P.rp_theta0) th0 = clamp_theta(P.rp_theta0[0]);
+        else {
+            PhiloxSeq s(P.key, P.chain, 1, STREAM_THETA0, 0);
+            th0 = beta_draw(P.prior0[0], P.prior0[1], s);
+        }
+        P.theta0_all[0] = th0;
+        P.scal[SC_THETA0] = th0;
+        P.scal[SC_L0] = log(th0);
+        P.scal[SC_L0C] = log(1.0 - th0);
+        double rr = P.relax_init;
+        if (P.learn_relax_first) {
+            if (P.rp_relax_next) rr = P.rp_relax_next[0];
+            else {
+                PhiloxSeq s(P.key, P.chain, 2, STREAM_RELAX, 0);
+                rr = beta_draw(P.relax_prior[0], P.relax_prior[1] + (double)P.N * (double)(P.K - 1), s);
+            }
+            P.relax_all[1] = rr;
+        }
+        P.scal[SC_RELAX] = rr;
+    }
+}
+
+template <int KP, typename VIdx>
+void launch_cells_t(const CellsParams& P, bool smem_tab, size_t smem, int grid, cudaStream_t st) {
+    if (smem_tab) {
+        auto kern = k_cells<KP, VIdx, true>;
+        CDL_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        kern<<<grid, CELLS_THREADS, smem, st>>>(P);
+    } else {
+        k_cells<KP, VIdx, false><<<grid, CELLS_THREADS, 0, st>>>(P);
+    }
+}
+
+template <int KP>
+void launch_stats_t(const StatsParams& P, dim3 grid, size_t smem, cudaStream_t st) {
+    auto kern = k_stats<KP>;
+    CDL_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    kern<<<grid, STATS_THREADS, smem, st>>>(P);
+}
+
+int pad_k(int K) { return K <= 4 ? 4 : (K <= 8 ? 8 : (K <= 16 ? 16 : 32)); }
+
+}  // namespace
+
+int cells_smem_bytes(int64_t N, int K) {
+    (void)K;
+    const int64_t b = N * (int64_t)(sizeof(double2) + sizeof(uint32_t));
+    return b > (int64_t)0x7fffffff ? 0x7fffffff : (int)b;
+}
+
+void launch_init_chain(const SweepArgs& a, ChainDev& c, cudaStream_t st) {
+    InitParams P{};
+    P.N = a.N; P.n_el = a.wise == 1 ? a.N : 1; P.K = a.K; P.wise = a.wise;
+    P.prior0[0] = a.prior0[0]; P.prior0[1] = a.prior0[1];
+    P.prior1[0] = a.prior1[0]; P.prior1[1] = a.prior1[1];
+    P.prior1_mat = a.prior1_mat; P.cfg0 = a.cfg0; P.mask = c.mask;
+    P.scal = c.scal; P.l1 = c.l1; P.l1c = c.l1c;
+    P.theta0_all = c.theta0_all; P.theta1_all = c.theta1_all; P.relax_all = c.relax_all;
+    P.relax_init = a.relax_fixed_set ? a.relax_fixed : a.relax_prior[0] / (a.relax_prior[0] + a.relax_prior[1]);
+    P.learn_relax_first = a.learn_relax_next;
+    P.relax_prior[0] = a.relax_prior[0]; P.relax_prior[1] = a.relax_prior[1];
+    P.key = a.key; P.chain = a.chain;
+    P.rp_theta0 = a.rp_theta0; P.rp_theta1 = a.rp_theta1; P.rp_relax_next = a.rp_relax_next;
+    const int64_t n = std::max<int64_t>(a.N, 1);
+    k_init<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(P);
+    CDL_CUDA(cudaGetLastError());
+}
+
+void launch_cells(const Donor& d, const SweepArgs& a, ChainDev& c, int sm_count, cudaStream_t st) {
+    CellsParams P{};
+    P.rowgrp = d.c_rowgrp; P.vidx = d.c_vidx; P.ca = d.c_a; P.cb = d.c_b;
+    P.M = d.M; P.N = d.N; P.cell_offset = d.cell_offset; P.K = a.K;
+    P.n_tab = a.wise == 1 ? (int)a.N : 1;
+    P.l1 = c.l1; P.l1c = c.l1c; P.scal = c.scal; P.mask = c.mask;
+    for (int k = 0; k < KMAX; ++k) P.logPsi[k] = a.logPsi[k];
+    const int64_t row = (int64_t)a.it - 1;
+    P.prob_row = c.prob_all ? c.prob_all + row * d.M * a.K : nullptr;
+    P.prob_acc = c.prob_acc;
+    P.z = c.z;
+    P.assign_row = c.assign_all ? c.assign_all + row * d.M : nullptr;
+    P.rp_u = a.rp_u_assign;
+    P.key = a.key; P.chain = a.chain; P.it = a.it;
+    const size_t smem = (size_t)cells_smem_bytes(d.N, a.K);
+    const bool smem_tab = smem <= 200 * 1024;
+    P.tab_in_smem = smem_tab;
+    int ctas_per_sm = 1;
+    if (smem_tab) {
+        ctas_per_sm = (int)std::min<size_t>(4, (220 * 1024) / std::max<size_t>(smem + 1024, 1));
+        if (ctas_per_sm < 1) ctas_per_sm = 1;
+    } else {
+        ctas_per_sm = 4;
+        if (!c.tab_g) throw Error(4, "global weight table not allocated");
+        k_build_tab<<<(unsigned)((d.N + 255) / 256), 256, 0, st>>>(d.N, P.n_tab, c.l1, c.l1c, c.scal, c.tab_g);
+        P.l1 = reinterpret_cast<const double*>(c.tab_g);
+    }
+    const int64_t warps_needed = d.M;
+    int64_t grid = (int64_t)sm_count * ctas_per_sm;
+    const int64_t max_useful = (warps_needed + CELLS_THREADS / 32 - 1) / (CELLS_THREADS / 32);
+    if (grid > max_useful) grid = std::max<int64_t>(max_useful, 1);
+    const int KP = pad_k(a.K);
+#define CDL_CELLS(KPV)                                                                       \
+    if (d.vidx32) launch_cells_t<KPV, uint32_t>(P, smem_tab, smem, (int)grid, st);           \
+    else launch_cells_t<KPV, uint16_t>(P, smem_tab, smem, (int)grid, st);
+    switch (KP) {
+        case 4: CDL_CELLS(4) break;
+        case 8: CDL_CELLS(8) break;
+        case 16: CDL_CELLS(16) break;
+        default: CDL_CELLS(32) break;
+    }
+#undef CDL_CELLS
+    CDL_CUDA(cudaGetLastError());
+}
+
+void launch_stats(const Donor& d, const SweepArgs& a, ChainDev& c, int sm_count, cudaStream_t st) {
+    CDL_CUDA(cudaMemsetAsync(c.sab, 0, sizeof(unsigned long long) * (size_t)(d.N * a.K), st));
+    StatsParams P{};
+    P.seggrp = d.v_seggrp; P.vc = d.v_cell; P.va = d.v_a; P.vb = d.v_b; P.z = c.z; P.sab = c.sab;
+    P.N = d.N; P.M = d.M; P.K = a.K;
+    const int KP = pad_k(a.K);
+    const int target_ctas = sm_count * 2;
+    int chunks = std::max(1, (target_ctas + d.n_cb - 1) / d.n_cb);
+    int64_t chunk = (d.N + chunks - 1) / chunks;
+    if (chunk < STATS_WARPS) chunk = STATS_WARPS;
+    chunks = (int)((d.N + chunk - 1) / chunk);
+    P.chunk = (int)chunk;
+    const int ncell_max = (int)std::min<int64_t>(CELL_BLOCK, d.M);
+    const size_t smem = sizeof(uint2) * STATS_WARPS * KP * 32 + (size_t)((ncell_max + 15) / 16 * 16);
+    dim3 grid((unsigned)chunks, (unsigned)d.n_cb);
+    switch (KP) {
+        case 4: launch_stats_t<4>(P, grid, smem, st); break;
+        case 8: launch_stats_t<8>(P, grid, smem, st); break;
+        case 16: launch_stats_t<16>(P, grid, smem, st); break;
+        default: launch_stats_t<32>(P, grid, smem, st); break;
+    }
+    CDL_CUDA(cudaGetLastError());
+}
+
+void launch_table(const Donor& d, const SweepArgs& a, ChainDev& c, cudaStream_t st) {
+    TableParams P{};
+    P.N = d.N; P.K = a.K; P.wise = a.wise; P.relax = a.relax; P.keep_base = a.keep_base;
+    P.learn_relax_next = a.learn_relax_next;
+    for (int q = 0; q < 2; ++q) {
+        P.prior0[q] = a.prior0[q]; P.prior1[q] = a.prior1[q]; P.relax_prior[q] = a.relax_prior[q];
+    }
+    P.prior1_mat = a.prior1_mat;
+    P.n_el = a.wise == 1 ? d.N : 1;
+    P.cfg0 = a.cfg0; P.mask = c.mask; P.sab = c.sab; P.scal = c.scal; P.l1 = c.l1; P.l1c = c.l1c;
+    P.W_log = a.W_log;
+    P.theta0_all = c.theta0_all; P.theta1_all = c.theta1_all; P.loglik_all = c.loglik_all;
+    P.relax_all = c.relax_all; P.config_all = c.config_all;
+    P.T = a.T; P.it = a.it; P.key = a.key; P.chain = a.chain;
+    P.rp_u_config = a.rp_u_config; P.rp_theta0 = a.rp_theta0; P.rp_theta1 = a.rp_theta1;
+    P.rp_relax_next = a.rp_relax_next;
+    P.part_d = c.part_d; P.part_u = c.part_u; P.ticket = c.ticket;
+    const unsigned grid = (unsigned)((d.N + TABLE_THREADS - 1) / TABLE_THREADS);
+    k_table<<<grid, TABLE_THREADS, 0, st>>>(P);
+    CDL_CUDA(cudaGetLastError());
+}
+
+}  // namespace cdl

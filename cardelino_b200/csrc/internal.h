@@ -1,0 +1,140 @@
+// Internal host-side declarations shared by the translation units of libcardelino_b200.so.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <string>
+#include <stdexcept>
+#include "common.cuh"
+
+namespace cdl {
+
+constexpr int GROUP = 8;           // entries per 128-bit load of uint16 payload
+constexpr int CELL_BLOCK = 65536;  // cells per variant-major block (local cell id fits uint16)
+constexpr int KMAX = 32;
+
+struct Error : std::runtime_error {
+    int code;
+    Error(int c, const std::string& m) : std::runtime_error(m), code(c) {}
+};
+
+#define CDL_CUDA(expr)                                                                              \
+    do {                                                                                            \
+        cudaError_t _e = (expr);                                                                    \
+        if (_e != cudaSuccess)                                                                      \
+            throw ::cdl::Error(2, std::string(#expr) + ": " + cudaGetErrorString(_e) + " (" +       \
+                                      __FILE__ + ":" + std::to_string(__LINE__) + ")");             \
+    } while (0)
+
+// Device-resident donor: the same counts in two layouts.
+//  (A) cell-major, each cell's entries padded to a multiple of GROUP with (variant 0, a 0, b 0):
+//      c_rowgrp[M+1] group offsets; c_vidx (uint16 if N <= 65536 else uint32), c_a, c_b.
+//      One pass over (A) gives the thin SpMM logLik  (R/clone_id.R:470-478).
+//  (B) variant-major inside blocks of CELL_BLOCK cells, segments padded likewise:
+//      v_seggrp[n_cb*N+1]; v_cell (uint16 local cell id), v_a, v_b.
+//      One pass over (B) gives the per-variant x clone read sums that replace the S-lists
+//      (R/clone_id.R:394-403,537-562).
+struct Donor {
+    int64_t N = 0, M = 0, nnz = 0;      // M = local cells of this rank
+    int64_t M_total = 0, cell_offset = 0;
+    bool vidx32 = false;
+    uint32_t* c_rowgrp = nullptr;
+    void* c_vidx = nullptr;
+    uint16_t* c_a = nullptr;
+    uint16_t* c_b = nullptr;
+    int64_t c_groups = 0;
+    int n_cb = 0;
+    uint32_t* v_seggrp = nullptr;
+    uint16_t* v_cell = nullptr;
+    uint16_t* v_a = nullptr;
+    uint16_t* v_b = nullptr;
+    int64_t v_groups = 0;
+    double W_log = 0.0;                 // local shard's sum(lchoose(D, A))
+    int32_t* labels = nullptr;          // synthetic ground truth (1-based), optional
+    uint64_t max_variant_depth = 0;     // max_i sum_j D_ij (must stay < 2^32 for packed statistics)
+    uint64_t max_cell_depth = 0;
+};
+
+void donor_free(Donor& d);
+// raw CSC (cells = columns) already on the device -> both layouts.  Frees nothing of the input.
+void donor_build(Donor& d, int64_t N, int64_t M, int64_t nnz, const int64_t* p_dev, const int32_t* i_dev,
+                 const uint16_t* a_dev, const uint16_t* d_dev, cudaStream_t st);
+void donor_export(const Donor& d, int64_t* p, int32_t* i, uint16_t* a, uint16_t* dd, cudaStream_t st);
+void synth_generate(Donor& d, int64_t N, int64_t M_total, int64_t cell_offset, int64_t M_local, int K,
+                    const double* Config_host, double coverage, uint64_t seed, cudaStream_t st);
+
+// Per-chain sampler state (device pointers).
+struct ChainDev {
+    // current state
+    double* scal;        // [16] device scalars, see SC_* below
+    double* l1;          // [n_tab] log(theta1), n_tab = N (variant) or 1 (global)
+    double* l1c;         // [n_tab] log(1 - theta1)
+    uint32_t* mask;      // [N] Config_new as clone bit masks
+    uint8_t* z;          // [M] current labels (0-based)
+    unsigned long long* sab;  // [N*K] packed statistics: low 32 bits sum A, high 32 bits sum B
+    // traces (row t = iteration t+1)
+    double* theta0_all;  // [T]
+    double* theta1_all;  // [T * n_el]
+    double* loglik_all;  // [T]
+    double* relax_all;   // [T]
+    uint8_t* config_all; // [T * N*K], element i + k*N like R's column-major flattening
+    double* prob_all;    // [T * M*K] device layout [t][cell][clone]  (exact mode) or nullptr
+    uint8_t* assign_all; // [T * M] 1-based labels or nullptr
+    double* prob_acc;    // [M*K] streaming accumulator (compact mode) or nullptr
+    // reduction scratch
+    double* part_d;      // [grid * 4]
+    unsigned long long* part_u; // [grid * 8]
+    unsigned int* ticket;
+    double2* tab_g;      // (du, dv) table in global memory when it does not fit shared memory, else nullptr
+};
+
+enum {
+    SC_THETA0 = 0, SC_L0 = 1, SC_L0C = 2, SC_RELAX = 3,   // relax rate used by the NEXT flip step
+    SC_N
+};
+
+struct SweepArgs {
+    int64_t N, M, M_total, cell_offset;
+    int K, KP;
+    int wise;            // 0 global, 1 variant
+    int relax;           // Config flips enabled
+    int learn_relax_next;// draw relax rate for iteration it+1 at the end of this sweep
+    int keep_base;
+    double prior0[2], prior1[2], relax_prior[2];
+    const double* prior1_mat;   // device [n_el*2] column-major or nullptr
+    double relax_fixed;  int relax_fixed_set;
+    double logPsi[KMAX];
+    const uint32_t* cfg0;       // [N] input Config bit masks
+    double W_log;
+    PhiloxKey key; uint32_t chain; uint32_t it;   // it = 1-based trace row being filled
+    int64_t T;                                    // trace rows allocated
+    // replay (device pointers to row `it-1`), nullptr = own draws
+    const double* rp_u_assign; const double* rp_u_config;
+    const double* rp_theta0; const double* rp_theta1; const double* rp_relax_next;
+};
+
+struct KernelTimes { float cells = 0, stats = 0, table = 0; };
+
+int cells_smem_bytes(int64_t N, int K);
+void launch_init_chain(const SweepArgs& a, ChainDev& c, cudaStream_t st);
+void launch_cells(const Donor& d, const SweepArgs& a, ChainDev& c, int sm_count, cudaStream_t st);
+void launch_stats(const Donor& d, const SweepArgs& a, ChainDev& c, int sm_count, cudaStream_t st);
+void launch_table(const Donor& d, const SweepArgs& a, ChainDev& c, cudaStream_t st);
+
+// post-processing
+void launch_geweke(const double* prob_all, int64_t cols, int64_t n_rows, unsigned long long* counts2,
+                   cudaStream_t st);  // counts2[0] = #non-NaN, counts2[1] = #|Z|<=2
+void launch_col_means_d(const double* X, int64_t cols, int64_t r0, int64_t r1, double* out, cudaStream_t st);
+void launch_col_means_u8(const uint8_t* X, int64_t cols, int64_t r0, int64_t r1, double* out, cudaStream_t st);
+void launch_prob_variant(const Donor& d, int wise, const double* theta0_all, const double* theta1_all,
+                         int64_t n_el, int64_t r0, int64_t r1, double* out_dense, cudaStream_t st);
+double loglik_general(const Donor& d, const double* Config_dev, int K, const int32_t* assign_dev,
+                      const double* prob_dev /* [M][K] device layout, or null */, double theta0,
+                      const double* theta1_dev, int64_t n_theta1, cudaStream_t st);
+// EM
+void em_stats(const Donor& d, const uint32_t* cfg_mask, int K, uint32_t* S3, uint32_t* S4, uint32_t* TA,
+              uint32_t* TB, int sm_count, cudaStream_t st);
+void em_iteration(int64_t M, int K, const uint32_t* S3, const uint32_t* S4, const uint32_t* TA,
+                  const uint32_t* TB, const double* logPsi_dev, double theta0, double theta1,
+                  double* prob_out /* [M][K] */, double* sums5_dev, double* partials, cudaStream_t st);
+
+}  // namespace cdl

@@ -1,0 +1,317 @@
+// Post-sweep kernels: Geweke_Z stop rule (R/clone_id.R:688-715), posterior means (:645-653),
+// prob_variant (:606-622), the general get_logLik (:734-752) and clone_id_EM (:240-326).
+#include "internal.h"
+
+namespace cdl {
+
+namespace {
+
+// One thread per trace column.  X is [n_rows][cols]; windows A = rows [0, floor(.1 n)),
+// B = rows [ceil(.5 n) - 1, n); both variances divide by nrow(A) - 1 as the reference does.
+__global__ void k_geweke(const double* __restrict__ X, int64_t cols, int64_t n, unsigned long long* counts) {
+    const int64_t c = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+    unsigned ok = 0, conv = 0;
+    if (c < cols) {
+        const int64_t nA = (int64_t)floor(0.1 * (double)n);
+        const int64_t bs = (int64_t)ceil(0.5 * (double)n) - 1;
+        const int64_t nB = n - bs;
+        double sA = 0.0, sB = 0.0;
+        for (int64_t r = 0; r < nA; ++r) sA += X[r * cols + c];
+        for (int64_t r = bs; r < n; ++r) sB += X[r * cols + c];
+        const double mA = sA / (double)nA, mB = sB / (double)nB;
+        double vA = 0.0, vB = 0.0;
+        for (int64_t r = 0; r < nA; ++r) { const double d = X[r * cols + c] - mA; vA += d * d; }
+        for (int64_t r = bs; r < n; ++r) { const double d = X[r * cols + c] - mB; vB += d * d; }
+        vA /= (double)(nA - 1);
+        vB /= (double)(nA - 1);
+        const double Z = (mA - mB) / sqrt(vA + vB + 1e-50);
+        if (!isnan(Z)) { ok = 1; conv = fabs(Z) <= 2.0; }
+    }
+    const unsigned okw = __popc(__ballot_sync(0xffffffffu, ok));
+    const unsigned cvw = __popc(__ballot_sync(0xffffffffu, conv));
+    if ((threadIdx.x & 31) == 0) {
+        if (okw) atomicAdd(&counts[0], (unsigned long long)okw);
+        if (cvw) atomicAdd(&counts[1], (unsigned long long)cvw);
+    }
+}
+
+template <typename T>
+__global__ void k_col_means(const T* __restrict__ X, int64_t cols, int64_t r0, int64_t r1, double* __restrict__ out) {
+    const int64_t c = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+    if (c >= cols) return;
+    double s = 0.0;
+    for (int64_t r = r0; r < r1; ++r) s += (double)X[r * cols + c];
+    out[c] = s / (double)(r1 - r0);
+}
+
+// prob_variant for wise in {global, variant}: per covered entry
+//   sum_t dbinom(a, d, th1_t) / (sum_t dbinom(a, d, th1_t) + sum_t dbinom(a, d, th0_t)); the choose(d, a)
+// factor is common and cancels.  Uncovered entries are 0.5 (dbinom(0, 0, .) = 1), filled by the caller.
+template <typename VIdx>
+__global__ void k_prob_variant(const uint32_t* __restrict__ rowgrp, const VIdx* __restrict__ vidx,
+                               const uint16_t* __restrict__ ca, const uint16_t* __restrict__ cb, int64_t M,
+                               int64_t N, int wise, const double* __restrict__ th0, const double* __restrict__ th1,
+                               int64_t n_el, int64_t r0, int64_t r1, double* __restrict__ out) {
+    const int lane = threadIdx.x & 31;
+    const int64_t warp = (blockIdx.x * (int64_t)blockDim.x + threadIdx.x) >> 5;
+    const int64_t nwarps = ((int64_t)gridDim.x * blockDim.x) >> 5;
+    for (int64_t j = warp; j < M; j += nwarps) {
+        const int64_t e0 = (int64_t)rowgrp[j] * GROUP, e1 = (int64_t)rowgrp[j + 1] * GROUP;
+        for (int64_t e = e0 + lane; e < e1; e += 32) {
+            const uint32_t a = ca[e], b = cb[e];
+            if (a + b == 0) continue;
+            const int64_t i = vidx[e];
+            double p1 = 0.0, p0 = 0.0;
+            for (int64_t r = r0; r < r1; ++r) {
+                const double t1 = th1[r * n_el + (wise == 1 ? i : 0)];
+                const double t0 = th0[r];
+                p1 += exp((double)a * log(t1) + (double)b * log(1.0 - t1));
+                p0 += exp((double)a * log(t0) + (double)b * log(1.0 - t0));
+            }
+            out[i + j * N] = p1 / (p1 + p0);
+        }
+    }
+}
+
+__global__ void k_fill(double* p, int64_t n, double v) {
+    int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+    if (i < n) p[i] = v;
+}
+
+// get_logLik with arbitrary (fractional) Config and either labels or an assignment-probability matrix.
+// Dense definition per covered entry: log( exp(l1 a + l1c b) * q + exp(l0 a + l0c b) * (1 - q) ),
+// q = sum_k Config[i,k] * P[j,k]; uncovered entries contribute log(1) = 0.  One warp per cell, partial
+// sums per cell then a fixed-order reduction (deterministic).
+template <typename VIdx>
+__global__ void k_loglik(const uint32_t* __restrict__ rowgrp, const VIdx* __restrict__ vidx,
+                         const uint16_t* __restrict__ ca, const uint16_t* __restrict__ cb, int64_t M, int64_t N,
+                         int K, const double* __restrict__ Config /* N x K col-major */,
+                         const int32_t* __restrict__ assign, const double* __restrict__ prob /* [M][K] */,
+                         double l0, double l0c, const double* __restrict__ theta1, int64_t n_th1,
+                         double* __restrict__ cell_out) {
+    const int lane = threadIdx.x & 31;
+    const int64_t warp = (blockIdx.x * (int64_t)blockDim.x + threadIdx.x) >> 5;
+    const int64_t nwarps = ((int64_t)gridDim.x * blockDim.x) >> 5;
+    for (int64_t j = warp; j < M; j += nwarps) {
+        const int64_t e0 = (int64_t)rowgrp[j] * GROUP, e1 = (int64_t)rowgrp[j + 1] * GROUP;
+        const int zlab = assign ? assign[j] - 1 : -1;
+        double s = 0.0;
+        for (int64_t e = e0 + lane; e < e1; e += 32) {
+            const uint32_t a = ca[e], b = cb[e];
+            if (a + b == 0) continue;
+            const int64_t i = vidx[e];
+            double q = 0.0;
+            if (assign) q = Config[i + (int64_t)zlab * N];
+            else
+                for (int k = 0; k < K; ++k) q += Config[i + (int64_t)k * N] * prob[j * K + k];
+            const double t1 = theta1[n_th1 == 1 ? 0 : i];
+            const double w1 = exp(log(t1) * (double)a + log(1.0 - t1) * (double)b);
+            const double w0 = exp(l0 * (double)a + l0c * (double)b);
+            s += log(w1 * q + w0 * (1.0 - q));
+        }
+        s = warp_sum_d(s);
+        if (lane == 0) cell_out[j] = s;
+    }
+}
+
+// fixed-order sum of n doubles by one block (deterministic)
+__global__ void k_sum_fixed(const double* __restrict__ x, int64_t n, double* out) {
+    __shared__ double sm[256];
+    double s = 0.0;
+    for (int64_t i = threadIdx.x; i < n; i += blockDim.x) s += x[i];
+    sm[threadIdx.x] = s;
+    __syncthreads();
+    for (int o = 128; o > 0; o >>= 1) {
+        if ((int)threadIdx.x < o) sm[threadIdx.x] += sm[threadIdx.x + o];
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) out[0] = sm[0];
+}
+
+// ---- EM ----
+// S3[j,k] = sum_i A_ij C_ik, S4 likewise with B (R/clone_id.R:274-275); S1 = TA - S3, S2 = TB - S4.
+template <typename VIdx>
+__global__ void k_em_stats(const uint32_t* __restrict__ rowgrp, const VIdx* __restrict__ vidx,
+                           const uint16_t* __restrict__ ca, const uint16_t* __restrict__ cb, int64_t M, int K,
+                           const uint32_t* __restrict__ cfg, uint32_t* __restrict__ S3, uint32_t* __restrict__ S4,
+                           uint32_t* __restrict__ TA, uint32_t* __restrict__ TB) {
+    const int lane = threadIdx.x & 31;
+    const int64_t warp = (blockIdx.x * (int64_t)blockDim.x + threadIdx.x) >> 5;
+    const int64_t nwarps = ((int64_t)gridDim.x * blockDim.x) >> 5;
+    for (int64_t j = warp; j < M; j += nwarps) {
+        const int64_t e0 = (int64_t)rowgrp[j] * GROUP, e1 = (int64_t)rowgrp[j + 1] * GROUP;
+        uint32_t s3[KMAX], s4[KMAX];
+#pragma unroll
+        for (int k = 0; k < KMAX; ++k) { s3[k] = 0; s4[k] = 0; }
+        uint32_t ta = 0, tb = 0;
+        for (int64_t e = e0 + lane; e < e1; e += 32) {
+            const uint32_t a = ca[e], b = cb[e];
+            const uint32_t m = cfg[vidx[e]];
+            ta += a; tb += b;
+#pragma unroll
+            for (int k = 0; k < KMAX; ++k) {
+                const uint32_t on = 0u - ((m >> k) & 1u);
+                s3[k] += a & on;
+                s4[k] += b & on;
+            }
+        }
+        ta = __reduce_add_sync(0xffffffffu, ta);
+        tb = __reduce_add_sync(0xffffffffu, tb);
+#pragma unroll
+        for (int k = 0; k < KMAX; ++k) {
+            if (k < K) {
+                const uint32_t x = __reduce_add_sync(0xffffffffu, s3[k]);
+                const uint32_t y = __reduce_add_sync(0xffffffffu, s4[k]);
+                if (lane == 0) { S3[j * K + k] = x; S4[j * K + k] = y; }
+            }
+        }
+        if (lane == 0) { TA[j] = ta; TB[j] = tb; }
+    }
+}
+
+// One EM iteration over the M x K statistics (R/clone_id.R:291-317).  Per-block partial sums of
+// (logSumExp, prob*S1, prob*(S1+S2), prob*S3, prob*(S3+S4)) go to `partials`; k_em_final adds them in
+// block order.
+__global__ void k_em_iter(int64_t M, int K, const uint32_t* __restrict__ S3, const uint32_t* __restrict__ S4,
+                          const uint32_t* __restrict__ TA, const uint32_t* __restrict__ TB,
+                          const double* __restrict__ logPsi, double l0, double l0c, double l1, double l1c,
+                          double* __restrict__ prob, double* __restrict__ partials) {
+    __shared__ double sm[5][8];
+    const int64_t j = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+    double v[5] = {0, 0, 0, 0, 0};
+    if (j < M) {
+        double L[KMAX];
+        double mx = -INFINITY;
+        const double ta = TA[j], tb = TB[j];
+        for (int k = 0; k < K; ++k) {
+            const double s3 = S3[j * K + k], s4 = S4[j * K + k];
+            L[k] = (ta - s3) * l0 + (tb - s4) * l0c + s3 * l1 + s4 * l1c + logPsi[k];
+            mx = fmax(mx, L[k]);
+        }
+        double se = 0.0;
+        for (int k = 0; k < K; ++k) { L[k] = exp(L[k] - mx); se += L[k]; }
+        v[0] = mx + log(se);
+        for (int k = 0; k < K; ++k) {
+            const double p = L[k] / se;
+            prob[j * K + k] = p;
+            const double s3 = S3[j * K + k], s4 = S4[j * K + k];
+            const double s1 = ta - s3, s2 = tb - s4;
+            v[1] += p * s1; v[2] += p * (s1 + s2); v[3] += p * s3; v[4] += p * (s3 + s4);
+        }
+    }
+    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+#pragma unroll
+    for (int q = 0; q < 5; ++q) {
+        const double r = warp_sum_d(v[q]);
+        if (lane == 0) sm[q][w] = r;
+    }
+    __syncthreads();
+    if (threadIdx.x < 5) {
+        double r = 0.0;
+        for (int ww = 0; ww < (int)(blockDim.x >> 5); ++ww) r += sm[threadIdx.x][ww];
+        partials[(size_t)blockIdx.x * 5 + threadIdx.x] = r;
+    }
+}
+
+__global__ void k_em_final(const double* __restrict__ partials, int64_t nblocks, double* __restrict__ out5) {
+    __shared__ double sm[256];
+    for (int q = 0; q < 5; ++q) {
+        double s = 0.0;
+        for (int64_t b = threadIdx.x; b < nblocks; b += blockDim.x) s += partials[b * 5 + q];
+        sm[threadIdx.x] = s;
+        __syncthreads();
+        for (int o = 128; o > 0; o >>= 1) {
+            if ((int)threadIdx.x < o) sm[threadIdx.x] += sm[threadIdx.x + o];
+            __syncthreads();
+        }
+        if (threadIdx.x == 0) out5[q] = sm[0];
+        __syncthreads();
+    }
+}
+
+inline unsigned warp_grid(int64_t M, int threads) {
+    return (unsigned)std::max<int64_t>(1, std::min<int64_t>((M * 32 + threads - 1) / threads, 148 * 16));
+}
+
+}  // namespace
+
+void launch_geweke(const double* prob_all, int64_t cols, int64_t n_rows, unsigned long long* counts2,
+                   cudaStream_t st) {
+    CDL_CUDA(cudaMemsetAsync(counts2, 0, 2 * sizeof(unsigned long long), st));
+    k_geweke<<<(unsigned)((cols + 255) / 256), 256, 0, st>>>(prob_all, cols, n_rows, counts2);
+    CDL_CUDA(cudaGetLastError());
+}
+
+void launch_col_means_d(const double* X, int64_t cols, int64_t r0, int64_t r1, double* out, cudaStream_t st) {
+    k_col_means<double><<<(unsigned)((cols + 255) / 256), 256, 0, st>>>(X, cols, r0, r1, out);
+    CDL_CUDA(cudaGetLastError());
+}
+void launch_col_means_u8(const uint8_t* X, int64_t cols, int64_t r0, int64_t r1, double* out, cudaStream_t st) {
+    k_col_means<uint8_t><<<(unsigned)((cols + 255) / 256), 256, 0, st>>>(X, cols, r0, r1, out);
+    CDL_CUDA(cudaGetLastError());
+}
+
+void launch_prob_variant(const Donor& d, int wise, const double* theta0_all, const double* theta1_all,
+                         int64_t n_el, int64_t r0, int64_t r1, double* out_dense, cudaStream_t st) {
+    const int64_t n = d.N * d.M;
+    k_fill<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(out_dense, n, 0.5);
+    const unsigned grid = warp_grid(d.M, 256);
+    if (d.vidx32)
+        k_prob_variant<uint32_t><<<grid, 256, 0, st>>>(d.c_rowgrp, (const uint32_t*)d.c_vidx, d.c_a, d.c_b, d.M, d.N,
+                                                       wise, theta0_all, theta1_all, n_el, r0, r1, out_dense);
+    else
+        k_prob_variant<uint16_t><<<grid, 256, 0, st>>>(d.c_rowgrp, (const uint16_t*)d.c_vidx, d.c_a, d.c_b, d.M, d.N,
+                                                       wise, theta0_all, theta1_all, n_el, r0, r1, out_dense);
+    CDL_CUDA(cudaGetLastError());
+}
+
+double loglik_general(const Donor& d, const double* Config_dev, int K, const int32_t* assign_dev,
+                      const double* prob_dev, double theta0, const double* theta1_dev, int64_t n_theta1,
+                      cudaStream_t st) {
+    double* cell = nullptr;
+    double* out = nullptr;
+    CDL_CUDA(cudaMalloc(&cell, sizeof(double) * (size_t)d.M));
+    CDL_CUDA(cudaMalloc(&out, sizeof(double)));
+    const unsigned grid = warp_grid(d.M, 256);
+    const double l0 = log(theta0), l0c = log(1.0 - theta0);
+    if (d.vidx32)
+        k_loglik<uint32_t><<<grid, 256, 0, st>>>(d.c_rowgrp, (const uint32_t*)d.c_vidx, d.c_a, d.c_b, d.M, d.N, K,
+                                                 Config_dev, assign_dev, prob_dev, l0, l0c, theta1_dev, n_theta1, cell);
+    else
+        k_loglik<uint16_t><<<grid, 256, 0, st>>>(d.c_rowgrp, (const uint16_t*)d.c_vidx, d.c_a, d.c_b, d.M, d.N, K,
+                                                 Config_dev, assign_dev, prob_dev, l0, l0c, theta1_dev, n_theta1, cell);
+    k_sum_fixed<<<1, 256, 0, st>>>(cell, d.M, out);
+    double h = 0.0;
+    cudaError_t e = cudaMemcpyAsync(&h, out, sizeof(double), cudaMemcpyDeviceToHost, st);
+    cudaStreamSynchronize(st);
+    cudaFree(cell);
+    cudaFree(out);
+    CDL_CUDA(e);
+    CDL_CUDA(cudaGetLastError());
+    return h + d.W_log;
+}
+
+void em_stats(const Donor& d, const uint32_t* cfg_mask, int K, uint32_t* S3, uint32_t* S4, uint32_t* TA,
+              uint32_t* TB, int sm_count, cudaStream_t st) {
+    (void)sm_count;
+    const unsigned grid = warp_grid(d.M, 256);
+    if (d.vidx32)
+        k_em_stats<uint32_t><<<grid, 256, 0, st>>>(d.c_rowgrp, (const uint32_t*)d.c_vidx, d.c_a, d.c_b, d.M, K,
+                                                   cfg_mask, S3, S4, TA, TB);
+    else
+        k_em_stats<uint16_t><<<grid, 256, 0, st>>>(d.c_rowgrp, (const uint16_t*)d.c_vidx, d.c_a, d.c_b, d.M, K,
+                                                   cfg_mask, S3, S4, TA, TB);
+    CDL_CUDA(cudaGetLastError());
+}
+
+void em_iteration(int64_t M, int K, const uint32_t* S3, const uint32_t* S4, const uint32_t* TA,
+                  const uint32_t* TB, const double* logPsi_dev, double theta0, double theta1, double* prob_out,
+                  double* sums5_dev, double* partials, cudaStream_t st) {
+    const int64_t nblocks = (M + 255) / 256;
+    k_em_iter<<<(unsigned)nblocks, 256, 0, st>>>(M, K, S3, S4, TA, TB, logPsi_dev, log(theta0), log(1.0 - theta0),
+                                                 log(theta1), log(1.0 - theta1), prob_out, partials);
+    k_em_final<<<1, 256, 0, st>>>(partials, nblocks, sums5_dev);
+    CDL_CUDA(cudaGetLastError());
+}
+
+}  // namespace cdl
