@@ -6,7 +6,7 @@ of include/cardelino_b200.h); this package is the host-side mirror of the R inte
 """
 from ._lib import CdlError, Handle, load_library, LIB_PATH, EXPORTS  # noqa: F401
 from .clone_id import (clone_id, clone_id_Gibbs, clone_id_EM, get_logLik, colMatch, devianceIC,  # noqa: F401
-                       Geweke_Z, assign_cells_to_clones)
+                       Geweke_Z, assign_cells_to_clones, SparseCounts)
 
 __all__ = ["clone_id", "clone_id_Gibbs", "clone_id_EM", "get_logLik", "colMatch", "devianceIC", "Geweke_Z",
            "assign_cells_to_clones", "Handle", "CdlError", "load_library"]

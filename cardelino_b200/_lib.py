@@ -13,7 +13,7 @@ LIB_PATH = os.path.join(_HERE, "libcardelino_b200.so")
 
 EXPORTS = [
     "cdl_version", "cdl_last_error", "cdl_create", "cdl_destroy", "cdl_load_dense", "cdl_load_csc",
-    "cdl_load_csc_u16", "cdl_synth_generate", "cdl_synth_labels", "cdl_export_csc_u16", "cdl_data_info",
+    "cdl_load_csc_u16", "cdl_synth_generate", "cdl_synth_labels", "cdl_export_csc_u16", "cdl_data_info", "cdl_set_shard",
     "cdl_comm_unique_id", "cdl_comm_init", "cdl_gibbs_defaults", "cdl_gibbs_run", "cdl_gibbs_info_get",
     "cdl_fetch_prob", "cdl_fetch_config_prob", "cdl_fetch_theta", "cdl_fetch_theta_traces",
     "cdl_fetch_loglik_trace", "cdl_fetch_relax_rate", "cdl_fetch_prob_all", "cdl_fetch_config_all",
@@ -138,6 +138,9 @@ class Handle:
                 np.ascontiguousarray(a, np.uint16), np.ascontiguousarray(d, np.uint16)]
         self._check(self.lib.cdl_load_csc_u16(self.h, C.c_int64(N), C.c_int64(M),
                                               *[C.c_void_p(x.ctypes.data) for x in arrs]))
+
+    def set_shard(self, cell_offset, M_total):
+        self._check(self.lib.cdl_set_shard(self.h, C.c_int64(cell_offset), C.c_int64(M_total)))
 
     def synth_generate(self, N, M_total, K, Config, coverage, seed, cell_offset=0, M_local=None):
         Config = _f64(Config)

@@ -39,6 +39,17 @@ def _handle(device=0):
     return _default_handle
 
 
+class SparseCounts:
+    """Compact host form of (A, D): one CSC pattern over cells (D > 0 everywhere), uint16 counts --
+    what load_cellSNP_vcf's two dgCMatrix objects (R/read_data.R:293-294) reduce to.  Pass it as `A`
+    (with D=None).  cell_offset / M_total mark a cell shard of a larger donor."""
+
+    def __init__(self, N, M, indptr, indices, a, d, cell_offset=0, M_total=None):
+        self.shape = (int(N), int(M))
+        self.indptr, self.indices, self.a, self.d = indptr, indices, a, d
+        self.cell_offset, self.M_total = int(cell_offset), int(M if M_total is None else M_total)
+
+
 def _names(x):
     if _pd is not None and isinstance(x, _pd.DataFrame):
         return list(x.index), list(x.columns)
@@ -48,14 +59,18 @@ def _names(x):
 def _values(x):
     if _pd is not None and isinstance(x, _pd.DataFrame):
         return x.to_numpy(dtype=np.float64)
-    if _sp is not None and _sp.issparse(x):
+    if x is None or isinstance(x, SparseCounts) or (_sp is not None and _sp.issparse(x)):
         return x
     return np.asarray(x, dtype=np.float64)
 
 
 def _load(h, A, D):
     """Replaces as.matrix() + NA normalisation (R/clone_id.R:121-122,380-391)."""
-    if _sp is not None and _sp.issparse(D):
+    if isinstance(A, SparseCounts):
+        h.load_csc_u16(A.shape[0], A.shape[1], A.indptr, A.indices, A.a, A.d)
+        if A.cell_offset or A.M_total != A.shape[1]:
+            h.set_shard(A.cell_offset, A.M_total)
+    elif _sp is not None and _sp.issparse(D):
         Dc = _sp.csc_matrix(D)
         Ac = _sp.csc_matrix(A)
         Dc.sort_indices()
@@ -138,6 +153,8 @@ def Geweke_Z(X, first=0.1, last=0.5):
 
 
 def _check_shapes(A, D, Config, Psi, gibbs):
+    if D is None and isinstance(A, SparseCounts):
+        D = A
     if A.shape != D.shape or A.shape[0] != Config.shape[0] or Config.shape[1] != len(Psi):
         raise ValueError("A and D must have the same size;\n" + (" " if gibbs else "") +
                          "A and Config must have the same number of variants;\n"
@@ -172,7 +189,7 @@ def clone_id_Gibbs(A, D, Config, Psi=None, relax_Config=True, relax_rate_fixed=N
                    keep_base_clone=True, prior0=(0.2, 99.8), prior1=(0.45, 0.55), min_iter=5000,
                    max_iter=20000, buin_frac=0.5, wise="variant", relabel=False, verbose=True,
                    seed=1, n_chain=1, replay=None, keep_assign_all=False, keep_prob_all=-1,
-                   handle=None, _loaded=False, _all_chains=False):
+                   handle=None, light=False, _loaded=False, _all_chains=False):
     """R/clone_id.R:351-675.  Returns the reference's list (:662-673) as a dict.  Extra arguments: `seed`
     (Philox key; the reference uses R's global RNG), `n_chain` (chains run inside the library), `replay`
     (dict of injected draws, see cdl_replay)."""
@@ -207,12 +224,24 @@ def clone_id_Gibbs(A, D, Config, Psi=None, relax_Config=True, relax_rate_fixed=N
                 buin_frac=float(buin_frac), wise=wise, n_chain=int(n_chain), seed=int(seed),
                 keep_assign_all=int(bool(keep_assign_all)),
                 keep_prob_all=1 if relabel else int(keep_prob_all), verbose=0)
-    outs = [_collect(h, c, Av, Config, wise, relabel, verbose, keep_assign_all) for c in range(n_chain)]
+    outs = [_collect(h, c, Av, Config, wise, relabel, verbose, keep_assign_all, light) for c in range(n_chain)]
     return outs if _all_chains else outs[0]
 
 
-def _collect(h, chain, Av, Config, wise, relabel, verbose, keep_assign_all):
+def _collect(h, chain, Av, Config, wise, relabel, verbose, keep_assign_all, light=False):
     N, M = Av.shape
+    if light:   # large donors: only the fields that stay small (no dense N x M, no big traces)
+        info = h.gibbs_info(chain)
+        theta0, theta1_el = h.fetch("theta", chain)
+        theta0_all, theta1_all = h.fetch("theta_traces", chain)
+        relax_rate, relax_rate_all = h.fetch("relax_rate", chain)
+        return {"theta0": theta0, "theta1_elements": theta1_el, "theta0_all": theta0_all.reshape(-1, 1),
+                "theta1_all": theta1_all, "logLik": h.fetch("logLik", chain), "prob": h.fetch("prob", chain),
+                "relax_rate": relax_rate, "relax_rate_all": relax_rate_all,
+                "Config_prob": h.fetch("Config_prob", chain), "n_iter": info.n_iter, "n_buin": info.n_buin,
+                "percent_converged": info.percent_converged, "logLik_post": info.logLik_post,
+                "DIC": dict(zip(("DIC", "logLik_var", "D_mean", "D_post", "DIC_Gelman", "DIC_Spiegelhalter"),
+                                list(info.dic)))}
     K = Config.shape[1]
     info = h.gibbs_info(chain)
     it, n_buin = info.n_iter, info.n_buin

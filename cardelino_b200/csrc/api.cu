@@ -274,7 +274,7 @@ void one_sweep(cdl_handle h, Chain& ch, SweepArgs& a, uint32_t it, const cdl_rep
     launch_stats(h->donor, a, ch.dev, h->sm_count, h->st);
     allreduce_u64(h, ch.dev.sab, (size_t)(a.N * a.K));
     launch_table(h->donor, a, ch.dev, h->st);
-    h->launches += 4;
+    h->launches += 3;   // k_cells, k_stats, k_table (+ one memset node)
 }
 
 double geweke_fraction(cdl_handle h, Chain& ch, int64_t n_rows, DevBuf<unsigned long long>& counts) {
@@ -466,6 +466,16 @@ int cdl_data_info(cdl_handle h, int64_t* N, int64_t* M, int64_t* nnz, double* W_
         if (M) *M = h->donor.M;
         if (nnz) *nnz = h->donor.nnz;
         if (W_log) *W_log = h->donor.W_log;
+    });
+}
+
+int cdl_set_shard(cdl_handle h, int64_t cell_offset, int64_t M_total) {
+    return guard(h, [&] {
+        require_data(h);
+        if (cell_offset < 0 || cell_offset + h->donor.M > M_total || M_total >= (int64_t)0xFFFFFFFFll)
+            throw Error(CDL_ERR_INVALID, "bad shard bounds");
+        h->donor.cell_offset = cell_offset;
+        h->donor.M_total = M_total;
     });
 }
 

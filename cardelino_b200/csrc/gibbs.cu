@@ -91,35 +91,54 @@ __device__ void revsort_dev(double* a, int* ib, int n) {
     }
 }
 
+// acc[k] += bit_k(m) ? del : 0 for all clones.  ptxas turns a predicated fp64 add into two FSELs plus an
+// unconditional DADD; masking only the HIGH word (the low word alone is a denormal < 2^-1022, absorbed by
+// any normal accumulator and irrelevant next to logPsi) costs one SEL + one DADD per clone, with the
+// predicates produced seven at a time by R2P.
 template <int KP>
-__device__ __forceinline__ void accumulate_entry(double (&acc)[KP], uint32_t a, uint32_t b, double2 t,
-                                                 uint32_t m) {
-    const double del = fma(u16_to_double(a), t.x, u16_to_double(b) * t.y);
+__device__ __forceinline__ void accumulate_entry(double (&acc)[KP], double del, uint32_t m) {
+    const int hi = __double2hiint(del), lo = __double2loint(del);
 #pragma unroll
-    for (int k = 0; k < KP; ++k) acc[k] += ((m >> k) & 1u) ? del : 0.0;
+    for (int k = 0; k < KP; ++k) {
+        asm("{\n\t.reg .pred p;\n\t.reg .b32 t, h;\n\t.reg .f64 w;\n\t"
+            "and.b32 t, %3, %4;\n\tsetp.ne.u32 p, t, 0;\n\tselp.b32 h, %2, 0, p;\n\t"
+            "mov.b64 w, {%1, h};\n\tadd.f64 %0, %0, w;\n\t}"
+            : "+d"(acc[k])
+            : "r"(lo), "r"(hi), "r"(m), "r"(1u << k));
+    }
 }
 
-template <int KP, typename VIdx, bool SMEM>
+// weight table access: shared memory through 32-bit shared addresses, or global memory through L1
+template <bool SMEM>
+__device__ __forceinline__ void load_tab(uint32_t tab_sa, uint32_t msk_sa, const double2* __restrict__ tab_g,
+                                         const uint32_t* __restrict__ msk_g, uint32_t i, double& du, double& dv,
+                                         uint32_t& m) {
+    if (SMEM) {
+        asm volatile("ld.shared.v2.f64 {%0, %1}, [%2];" : "=d"(du), "=d"(dv) : "r"(tab_sa + (i << 4)));
+        asm volatile("ld.shared.u32 %0, [%1];" : "=r"(m) : "r"(msk_sa + (i << 2)));
+    } else {
+        const double2 t = __ldg(tab_g + i);
+        du = t.x; dv = t.y;
+        m = __ldg(msk_g + i);
+    }
+}
+
+template <int KP, bool SMEM>
 __device__ __forceinline__ void accumulate_group(double (&acc)[KP], const uint32_t (&vw)[8], const uint4 a4,
-                                                 const uint4 b4, const double2* __restrict__ tab,
-                                                 const uint32_t* __restrict__ msk) {
+                                                 const uint4 b4, uint32_t tab_sa, uint32_t msk_sa,
+                                                 const double2* __restrict__ tab_g,
+                                                 const uint32_t* __restrict__ msk_g) {
     const uint32_t aw[4] = {a4.x, a4.y, a4.z, a4.w};
     const uint32_t bw[4] = {b4.x, b4.y, b4.z, b4.w};
 #pragma unroll
     for (int e = 0; e < 8; ++e) {
-        const uint32_t i = vw[e];
         const uint32_t a = (e & 1) ? (aw[e >> 1] >> 16) : (aw[e >> 1] & 0xffffu);
         const uint32_t b = (e & 1) ? (bw[e >> 1] >> 16) : (bw[e >> 1] & 0xffffu);
-        double2 t;
+        double du, dv;
         uint32_t m;
-        if (SMEM) {
-            t = tab[i];
-            m = msk[i];
-        } else {
-            t = __ldg(tab + i);
-            m = __ldg(msk + i);
-        }
-        accumulate_entry<KP>(acc, a, b, t, m);
+        load_tab<SMEM>(tab_sa, msk_sa, tab_g, msk_g, vw[e], du, dv, m);
+        const double del = fma(u16_to_double(a), du, u16_to_double(b) * dv);
+        accumulate_entry<KP>(acc, del, m);
     }
 }
 
@@ -139,68 +158,77 @@ __device__ __forceinline__ void load_vidx<uint32_t>(const void* base, int64_t g,
     vw[4] = v1.x; vw[5] = v1.y; vw[6] = v1.z; vw[7] = v1.w;
 }
 
-template <int KP, typename VIdx, bool SMEM>
-__global__ void __launch_bounds__(CELLS_THREADS) k_cells(const CellsParams P) {
+// One group of G lanes per cell (G >= KP); 32/G cells per warp at a time.
+template <int KP, int G, typename VIdx, bool SMEM>
+__global__ void __launch_bounds__(CELLS_THREADS, (KP <= 8 ? 2 : 1)) k_cells(const CellsParams P) {
     constexpr int LOG = Log2<KP>::v;
-    constexpr int SH = 5 - LOG;          // lanes per clone after the transposing reduction
+    constexpr int LOGG = Log2<G>::v;
+    constexpr int SH = LOGG - LOG;       // log2(lanes per clone) after the transposing reduction
+    constexpr int CPW = 32 / G;          // cells per warp pass
     extern __shared__ __align__(16) unsigned char smem_raw[];
-    double2* s_tab = reinterpret_cast<double2*>(smem_raw);
-    uint32_t* s_msk = reinterpret_cast<uint32_t*>(smem_raw + sizeof(double2) * (size_t)(SMEM ? P.N : 0));
     const double l0 = P.scal[SC_L0], l0c = P.scal[SC_L0C];
-    const double2* tab;
-    const uint32_t* msk;
+    uint32_t tab_sa = 0, msk_sa = 0;
+    const double2* tab_g = nullptr;
+    const uint32_t* msk_g = P.mask;
     if (SMEM) {
         // stage the per-variant weight table: (log th1_i - log th0, log(1-th1_i) - log(1-th0)) and the
         // Config_new row as a clone bit mask.  logLik[j,k] = base_j + sum_i C_ik * delta_ij; base_j
         // cancels in the softmax.
+        double2* s_tab = reinterpret_cast<double2*>(smem_raw);
+        uint32_t* s_msk = reinterpret_cast<uint32_t*>(smem_raw + sizeof(double2) * (size_t)P.N);
         for (int64_t i = threadIdx.x; i < P.N; i += blockDim.x) {
             const int64_t t = P.n_tab == 1 ? 0 : i;
             s_tab[i] = make_double2(P.l1[t] - l0, P.l1c[t] - l0c);
             s_msk[i] = P.mask[i];
         }
         __syncthreads();
-        tab = s_tab;
-        msk = s_msk;
+        tab_sa = (uint32_t)__cvta_generic_to_shared(s_tab);
+        msk_sa = (uint32_t)__cvta_generic_to_shared(s_msk);
     } else {
-        tab = reinterpret_cast<const double2*>(P.l1);   // pre-built (du, dv) table in global memory
-        msk = P.mask;
+        tab_g = reinterpret_cast<const double2*>(P.l1);   // pre-built (du, dv) table in global memory
     }
     const int lane = threadIdx.x & 31;
+    const int lig = lane & (G - 1);               // lane in group
+    const int grp = lane >> LOGG;                 // group in warp
+    const int gbase = lane & ~(G - 1);            // first lane of my group
+    const unsigned gmask = (G == 32) ? 0xffffffffu : (((1u << G) - 1u) << gbase);
     const int64_t warp = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
     const int64_t nwarps = ((int64_t)gridDim.x * blockDim.x) >> 5;
     const int K = P.K;
-    const int k = lane >> SH;
-    const bool rep = (lane & ((1 << SH) - 1)) == 0;
+    const int k = lig >> SH;
+    const bool rep = (lig & ((1 << SH) - 1)) == 0;
     const double my_logpsi = (k < K) ? P.logPsi[k] : 0.0;
     const uint4* a8 = reinterpret_cast<const uint4*>(P.ca);
     const uint4* b8 = reinterpret_cast<const uint4*>(P.cb);
 
-    for (int64_t j = warp; j < P.M; j += nwarps) {
-        const int64_t g0 = P.rowgrp[j], g1 = P.rowgrp[j + 1];
+    for (int64_t jb = warp * CPW; jb < P.M; jb += nwarps * CPW) {
+        const int64_t j = jb + grp;
+        const bool valid = j < P.M;
+        int64_t g0 = 0, g1 = 0;
+        if (valid) { g0 = P.rowgrp[j]; g1 = P.rowgrp[j + 1]; }
         double acc[KP];
 #pragma unroll
         for (int q = 0; q < KP; ++q) acc[q] = 0.0;
-        for (int64_t g = g0 + lane; g < g1; g += 64) {
-            const bool two = (g + 32) < g1;
+        for (int64_t g = g0 + lig; g < g1; g += 2 * G) {
+            const bool two = (g + G) < g1;
             uint32_t v0[8], v1[8];
             load_vidx<VIdx>(P.vidx, g, v0);
             const uint4 a0 = ld_stream(a8 + g), b0 = ld_stream(b8 + g);
             uint4 a1 = make_uint4(0, 0, 0, 0), b1 = a1;
             if (two) {
-                load_vidx<VIdx>(P.vidx, g + 32, v1);
-                a1 = ld_stream(a8 + g + 32);
-                b1 = ld_stream(b8 + g + 32);
+                load_vidx<VIdx>(P.vidx, g + G, v1);
+                a1 = ld_stream(a8 + g + G);
+                b1 = ld_stream(b8 + g + G);
             }
-            accumulate_group<KP, VIdx, SMEM>(acc, v0, a0, b0, tab, msk);
-            if (two) accumulate_group<KP, VIdx, SMEM>(acc, v1, a1, b1, tab, msk);
+            accumulate_group<KP, SMEM>(acc, v0, a0, b0, tab_sa, msk_sa, tab_g, msk_g);
+            if (two) accumulate_group<KP, SMEM>(acc, v1, a1, b1, tab_sa, msk_sa, tab_g, msk_g);
         }
-        // transposing butterfly: afterwards lane holds the full sum of clone k = lane >> SH
+        // transposing butterfly inside the group: afterwards a lane holds the full sum of clone k
 #pragma unroll
         for (int s = 0; s < LOG; ++s) {
-            constexpr int dummy = 0; (void)dummy;
-            const int off = 16 >> s;
+            const int off = (G / 2) >> s;
             const int n = KP >> (s + 1);
-            const bool up = (lane & off) != 0;
+            const bool up = (lig & off) != 0;
 #pragma unroll
             for (int q = 0; q < KP / 2; ++q) {
                 if (q < n) {
@@ -216,38 +244,43 @@ __global__ void __launch_bounds__(CELLS_THREADS) k_cells(const CellsParams P) {
         L = (k < K) ? L + my_logpsi : -INFINITY;
         double mx = L;
 #pragma unroll
-        for (int off = 16; off >= 1; off >>= 1) mx = fmax(mx, shfl_xor_d(mx, off));
+        for (int off = G / 2; off >= 1; off >>= 1) mx = fmax(mx, shfl_xor_d(mx, off));
         const double ex = exp(L - mx);
         double sm = ex;
 #pragma unroll
-        for (int off = 16; off >= (1 << SH); off >>= 1) sm += shfl_xor_d(sm, off);
+        for (int off = G / 2; off >= (1 << SH); off >>= 1) sm += shfl_xor_d(sm, off);
         const double pr = ex / sm;
-        if (rep && k < K) {
+        if (valid && rep && k < K) {
             if (P.prob_row) P.prob_row[j * K + k] = pr;
             if (P.prob_acc) P.prob_acc[j * K + k] += pr;
         }
         // ---- sample(seq_len(K), 1, prob = pr): walk the DESCENDING-sorted CDF with one uniform ----
         const uint32_t gcell = (uint32_t)(P.cell_offset + j);
-        const double u = P.rp_u ? P.rp_u[j] : philox_uniform(P.key, P.chain, P.it, STREAM_ASSIGN, gcell);
+        double u = 0.5;
+        if (valid) u = P.rp_u ? P.rp_u[j] : philox_uniform(P.key, P.chain, P.it, STREAM_ASSIGN, gcell);
         double cum = 0.0;
         int rank = 0;
         bool tie = false;
 #pragma unroll
         for (int l = 0; l < KP; ++l) {
-            const double pl = shfl_d(pr, l << SH);
+            const double pl = shfl_d(pr, gbase + (l << SH));
             if (l < K) {
                 const bool before = (pl > pr) || (pl == pr && l < k);
                 if (before) { cum += pl; ++rank; }
                 tie |= (pl == pr) && (l != k) && (pr > 0.0);
             }
         }
+        const unsigned tie_lanes = __ballot_sync(0xffffffffu, tie && k < K);
         unsigned sel;
-        if (__any_sync(0xffffffffu, tie && k < K)) {
-            // exact emulation of revsort's tie order (rare: identical Config columns)
+        if (tie_lanes & gmask) {
+            // exact emulation of revsort's tie order (identical Config columns, uncovered cells)
             double pa[KP];
             int perm[KP];
 #pragma unroll
-            for (int l = 0; l < KP; ++l) { pa[l] = shfl_d(pr, l << SH); perm[l] = l; }
+            for (int l = 0; l < KP; ++l) {
+                pa[l] = __shfl_sync(gmask, pr, gbase + (l << SH));
+                perm[l] = l;
+            }
             double tot = 0.0;
             for (int l = 0; l < K; ++l) tot += pa[l];
             for (int l = 0; l < K; ++l) pa[l] /= tot;
@@ -260,9 +293,9 @@ __global__ void __launch_bounds__(CELLS_THREADS) k_cells(const CellsParams P) {
             const bool cand = u <= cum + pr;
             const unsigned keyv = (k < K && (cand || rank == K - 1)) ? ((unsigned)rank << 8 | (unsigned)k)
                                                                      : 0xffffffffu;
-            sel = __reduce_min_sync(0xffffffffu, keyv) & 0xffu;
+            sel = __reduce_min_sync(gmask, keyv) & 0xffu;
         }
-        if (lane == 0) {
+        if (valid && lig == 0) {
             P.z[j] = (uint8_t)sel;
             if (P.assign_row) P.assign_row[j] = (uint8_t)(sel + 1);
         }
@@ -551,6 +584,7 @@ struct InitParams {
     uint32_t* mask;
     double* scal; double* l1; double* l1c;
     double* theta0_all; double* theta1_all; double* relax_all;
+    uint8_t* config_all; int relax;
     double relax_init;
     int learn_relax_first;     // iteration 2 already learns the relax rate (min_iter tiny)
     double relax_prior[2];
@@ -560,7 +594,11 @@ struct InitParams {
 
 __global__ void k_init(const InitParams P) {
     const int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
-    if (i < P.N) P.mask[i] = P.cfg0[i];
+    if (i < P.N) {
+        P.mask[i] = P.cfg0[i];
+        if (!P.relax)   // Config_new == Config when the relax step is off: trace row 1 holds it too
+            for (int k = 0; k < P.K; ++k) P.config_all[i + (int64_t)k * P.N] = (uint8_t)((P.cfg0[i] >> k) & 1u);
+    }
     if (i < P.n_el) {
         double th;
         if (P.rp_theta1) th = clamp_theta(P.rp_theta1[i]);
@@ -598,15 +636,21 @@ __global__ void k_init(const InitParams P) {
     }
 }
 
-template <int KP, typename VIdx>
+template <int KP, int G, typename VIdx>
 void launch_cells_t(const CellsParams& P, bool smem_tab, size_t smem, int grid, cudaStream_t st) {
     if (smem_tab) {
-        auto kern = k_cells<KP, VIdx, true>;
+        auto kern = k_cells<KP, G, VIdx, true>;
         CDL_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         kern<<<grid, CELLS_THREADS, smem, st>>>(P);
     } else {
-        k_cells<KP, VIdx, false><<<grid, CELLS_THREADS, 0, st>>>(P);
+        k_cells<KP, G, VIdx, false><<<grid, CELLS_THREADS, 0, st>>>(P);
     }
+}
+
+template <int KP, int G>
+void launch_cells_v(const Donor& d, const CellsParams& P, bool smem_tab, size_t smem, int grid, cudaStream_t st) {
+    if (d.vidx32) launch_cells_t<KP, G, uint32_t>(P, smem_tab, smem, grid, st);
+    else launch_cells_t<KP, G, uint16_t>(P, smem_tab, smem, grid, st);
 }
 
 template <int KP>
@@ -634,6 +678,7 @@ void launch_init_chain(const SweepArgs& a, ChainDev& c, cudaStream_t st) {
     P.prior1_mat = a.prior1_mat; P.cfg0 = a.cfg0; P.mask = c.mask;
     P.scal = c.scal; P.l1 = c.l1; P.l1c = c.l1c;
     P.theta0_all = c.theta0_all; P.theta1_all = c.theta1_all; P.relax_all = c.relax_all;
+    P.config_all = c.config_all; P.relax = a.relax;
     P.relax_init = a.relax_fixed_set ? a.relax_fixed : a.relax_prior[0] / (a.relax_prior[0] + a.relax_prior[1]);
     P.learn_relax_first = a.learn_relax_next;
     P.relax_prior[0] = a.relax_prior[0]; P.relax_prior[1] = a.relax_prior[1];
@@ -671,21 +716,28 @@ void launch_cells(const Donor& d, const SweepArgs& a, ChainDev& c, int sm_count,
         k_build_tab<<<(unsigned)((d.N + 255) / 256), 256, 0, st>>>(d.N, P.n_tab, c.l1, c.l1c, c.scal, c.tab_g);
         P.l1 = reinterpret_cast<const double*>(c.tab_g);
     }
-    const int64_t warps_needed = d.M;
+    // lanes per cell: enough that a lane sees ~2 groups of 8 entries, never fewer than the padded clones
+    const int KP = pad_k(a.K);
+    const double groups_per_cell = (double)d.c_groups / (double)std::max<int64_t>(d.M, 1);
+    int G = groups_per_cell >= 40.0 ? 32 : (groups_per_cell >= 12.0 ? 16 : 8);
+    if (G < KP) G = KP;
+    const int cpw = 32 / G;
+    const int64_t warps_needed = (d.M + cpw - 1) / cpw;
     int64_t grid = (int64_t)sm_count * ctas_per_sm;
     const int64_t max_useful = (warps_needed + CELLS_THREADS / 32 - 1) / (CELLS_THREADS / 32);
     if (grid > max_useful) grid = std::max<int64_t>(max_useful, 1);
-    const int KP = pad_k(a.K);
-#define CDL_CELLS(KPV)                                                                       \
-    if (d.vidx32) launch_cells_t<KPV, uint32_t>(P, smem_tab, smem, (int)grid, st);           \
-    else launch_cells_t<KPV, uint16_t>(P, smem_tab, smem, (int)grid, st);
-    switch (KP) {
-        case 4: CDL_CELLS(4) break;
-        case 8: CDL_CELLS(8) break;
-        case 16: CDL_CELLS(16) break;
-        default: CDL_CELLS(32) break;
+    const int code = KP * 100 + G;
+    switch (code) {
+        case 408: launch_cells_v<4, 8>(d, P, smem_tab, smem, (int)grid, st); break;
+        case 416: launch_cells_v<4, 16>(d, P, smem_tab, smem, (int)grid, st); break;
+        case 432: launch_cells_v<4, 32>(d, P, smem_tab, smem, (int)grid, st); break;
+        case 808: launch_cells_v<8, 8>(d, P, smem_tab, smem, (int)grid, st); break;
+        case 816: launch_cells_v<8, 16>(d, P, smem_tab, smem, (int)grid, st); break;
+        case 832: launch_cells_v<8, 32>(d, P, smem_tab, smem, (int)grid, st); break;
+        case 1616: launch_cells_v<16, 16>(d, P, smem_tab, smem, (int)grid, st); break;
+        case 1632: launch_cells_v<16, 32>(d, P, smem_tab, smem, (int)grid, st); break;
+        default: launch_cells_v<32, 32>(d, P, smem_tab, smem, (int)grid, st); break;
     }
-#undef CDL_CELLS
     CDL_CUDA(cudaGetLastError());
 }
 

@@ -121,6 +121,10 @@ int cdl_synth_labels(cdl_handle h, int32_t* labels_out /* M_local, 1-based */);
 /* Export the resident counts in the cdl_load_csc_u16 layout (sizes from cdl_data_info). */
 int cdl_export_csc_u16(cdl_handle h, int64_t* p, int32_t* i, uint16_t* a, uint16_t* d);
 int cdl_data_info(cdl_handle h, int64_t* N, int64_t* M, int64_t* nnz, double* W_log);
+/* Declare the loaded cells to be cells [cell_offset, cell_offset + M) of an M_total-cell donor (cell-sharded
+ * multi-GPU runs): the Philox stream of a cell is keyed by its GLOBAL id, so draws do not depend on the
+ * number of ranks.  Call after cdl_load_*. */
+int cdl_set_shard(cdl_handle h, int64_t cell_offset, int64_t M_total);
 
 /* ---- multi-GPU (cells sharded over ranks; one all-reduce of the N x K statistic table per sweep) ----
  * nccl_lib_path: libnccl.so.2 to dlopen (the host passes torch's bundled copy); unique_id: the 128-byte

@@ -133,7 +133,8 @@ def preprocess(A, D):
         A[zero] = np.nan
         D[zero] = np.nan
         A[(D > 0) & np.isnan(A)] = 0.0     # NA in a logical subscript is skipped on assignment
-    B = D - A
+    with np.errstate(invalid="ignore"):
+        B = D - A
     ok = ~np.isnan(D) & ~np.isnan(A)
     W_log = float(np.sum(lchoose(D[ok], A[ok])))
     A1 = np.nan_to_num(A, nan=0.0)
@@ -183,6 +184,8 @@ def geweke_z(X, first=0.1, last=0.5):
     n = X.shape[0]
     Aw = X[: int(math.floor(first * n))]
     Bw = X[int(math.ceil(last * n)) - 1:]
+    if Aw.shape[0] == 0:                       # mean of an empty window is NaN in R as well
+        return np.full(X.shape[1], np.nan)
     with np.errstate(invalid="ignore", divide="ignore"):
         mA = Aw.mean(axis=0)
         mB = Bw.mean(axis=0)
@@ -668,3 +671,112 @@ def sweep_tables(A1, B1, Config_cur, theta0, theta1_vec, Psi, u_assign):
     prob = E / E.sum(axis=1, keepdims=True)
     labels = np.array([r_sample_one(prob[j], u_assign[j]) for j in range(prob.shape[0])])
     return prob, labels
+
+
+# --------------------------------------------------------------------------------------------
+# step-wise (teacher-forced) verification of a recorded chain
+# --------------------------------------------------------------------------------------------
+
+
+def verify_gibbs_trace(A, D, Config, rec, Psi=None, relax_Config=True, relax_rate_fixed=None,
+                       relax_rate_prior=(1, 9), keep_base_clone=True, min_iter=5000, wise="variant",
+                       seed=0, chain=0, u_assign=None, u_config=None, tie_rtol=1e-12, cdf_tol=1e-6,
+                       dense_loglik=True):
+    """Check every sweep of a recorded chain `rec` (dict with theta0_all, theta1_all, relax_rate_all,
+    prob_all, assign_all, Config_all, logLik in the reference's layouts) against the reference
+    formulas, each sweep teacher-forced from the RECORDED state of the previous one (SURVEY.md
+    section 8c protocol 2/3):
+
+      prob_all[t]   is a pure function of theta[t-1], Config_all[t-1]            (R/clone_id.R:468-481)
+      assign_all[t] follows from prob_all[t] and the uniform of cell j          (:492-497)
+      Config_all[t] follows from assign_all[t], theta[t-1], relax rate and u     (:501-535)
+      logLik[t]     from Config_all[t], assign_all[t], theta[t-1]                (:574-577)
+
+    Label disagreements are classified: `boundary` = the uniform lies within cdf_tol of a CDF
+    boundary; `near_tie` = two probabilities agree to tie_rtol so their order in sample()'s sort is
+    decided by rounding; anything else is `hard` (a real bug)."""
+    Config = np.asarray(Config, dtype=np.float64)
+    N, K = Config.shape
+    A1, B1, W_log = preprocess(A, D)
+    M = A1.shape[1]
+    Psi = np.full(K, 1.0 / K) if Psi is None else np.asarray(Psi, float)
+    theta0_all = np.asarray(rec["theta0_all"], float).reshape(-1)
+    theta1_all = np.asarray(rec["theta1_all"], float)
+    if theta1_all.ndim == 1:
+        theta1_all = theta1_all.reshape(-1, 1)
+    T = len(theta0_all)
+    relax = relax_Config is not None and relax_Config is not False
+    out = {"max_dprob": 0.0, "boundary": 0, "near_tie": 0, "hard": 0, "config_boundary": 0,
+           "config_hard": 0, "max_dloglik_rel": 0.0, "first_hard": None, "n_sweeps": T - 1}
+    Config_prev = Config.copy()
+    if relax:
+        relax_rate = relax_rate_fixed if relax_rate_fixed is not None else \
+            relax_rate_prior[0] / (relax_rate_prior[0] + relax_rate_prior[1])
+    for it in range(2, T + 1):
+        theta0 = theta0_all[it - 2]
+        th1 = theta1_all[it - 2]
+        th1v = np.full(N, th1[0]) if wise == "global" else th1
+        ua = u_assign[it - 1] if u_assign is not None else \
+            philox.uniforms(seed, chain, it, philox.STREAM_ASSIGN, np.arange(M))
+        # (a) prob
+        l0, l0c = math.log(theta0), math.log(1 - theta0)
+        l1, l1c = np.log(th1v).reshape(-1, 1), np.log(1 - th1v).reshape(-1, 1)
+        WA = Config_prev * l1 + (1 - Config_prev) * l0
+        WB = Config_prev * l1c + (1 - Config_prev) * l0c
+        L = A1.T @ WA + B1.T @ WB + np.log(Psi)[None, :]
+        E = np.exp(L - L.max(axis=1, keepdims=True))
+        prob = E / E.sum(axis=1, keepdims=True)
+        rec_prob = np.asarray(rec["prob_all"][it - 1]).reshape(K, M).T
+        out["max_dprob"] = max(out["max_dprob"], float(np.abs(prob - rec_prob).max()))
+        # (b) labels
+        rec_lab = np.asarray(rec["assign_all"][it - 1]).astype(int)
+        for j in range(M):
+            lab, cdf, perm = r_sample_one(prob[j], ua[j], return_cdf=True)
+            if lab != rec_lab[j]:
+                ps = sorted(prob[j], reverse=True)
+                gaps = [abs(ps[q] - ps[q + 1]) <= tie_rtol * max(ps[q], 1e-300) for q in range(K - 1)
+                        if ps[q] > 0]
+                if min(abs(ua[j] - c) for c in cdf) <= cdf_tol:
+                    out["boundary"] += 1
+                elif any(gaps):
+                    out["near_tie"] += 1
+                else:
+                    out["hard"] += 1
+                    if out["first_hard"] is None:
+                        out["first_hard"] = {"it": it, "cell": j, "oracle": lab, "recorded": int(rec_lab[j]),
+                                             "u": float(ua[j]), "prob": prob[j].tolist(),
+                                             "rec_prob": rec_prob[j].tolist()}
+        z = rec_lab - 1
+        # (c) Config flips
+        rec_cfg = np.asarray(rec["Config_all"][it - 1]).reshape(K, N).T
+        Zm = np.zeros((M, K))
+        Zm[np.arange(M), z] = 1.0
+        SA, SB = A1 @ Zm, B1 @ Zm
+        if relax:
+            if it > (0.1 * min_iter + 5) and relax_rate_fixed is None:
+                relax_rate = float(np.asarray(rec["relax_rate_all"]).reshape(-1)[it - 1])
+            oddlog = _config_prior_oddlog(Config, relax_rate, keep_base_clone)
+            odd = SA * (l1 - l0) + SB * (l1c - l0c) + oddlog
+            odd = np.clip(odd, -50, 50)
+            p = np.exp(odd) / (np.exp(odd) + 1)
+            uc = u_config[it - 1] if u_config is not None else \
+                philox.uniforms(seed, chain, it, philox.STREAM_CONFIG, np.arange(N * K))
+            new = r_rbinom1(p.T.ravel(), uc).reshape(K, N).T
+            bad = new != rec_cfg
+            if bad.any():
+                ucm = np.asarray(uc).reshape(K, N).T
+                thr = np.where(p > 0.5, p, 1 - np.minimum(p, 1 - p))
+                near = np.abs(ucm - thr) <= cdf_tol
+                out["config_boundary"] += int((bad & near).sum())
+                out["config_hard"] += int((bad & ~near).sum())
+        else:
+            out["config_hard"] += int((rec_cfg != Config).sum())
+        # (d) logLik trace with the OLD theta and the RECORDED new Config
+        if dense_loglik:
+            ll = get_logLik(A1, B1, rec_cfg, rec_lab, theta0, np.broadcast_to(th1v.reshape(-1, 1), A1.shape))
+        else:
+            ll = get_logLik_tables(A1, B1, rec_cfg, rec_lab, theta0, th1v)
+        rl = float(np.asarray(rec["logLik"]).reshape(-1)[it - 1])
+        out["max_dloglik_rel"] = max(out["max_dloglik_rel"], abs(ll - rl) / max(abs(ll), 1e-300))
+        Config_prev = rec_cfg
+    return out

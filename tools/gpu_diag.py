@@ -69,6 +69,8 @@ def t_gibbs(**kw):
     print("  relax_rate", res["relax_rate"], o["relax_rate"], "DIC", res["DIC"]["DIC"], o["DIC"]["DIC"])
     print("  max|dprob_variant|", np.nanmax(np.abs(res["prob_variant"] - o["prob_variant"])))
     print("  pc", res["percent_converged"], o["percent_converged"], "logLik_post", res["logLik_post"], o["logLik_post"])
+    v = O.verify_gibbs_trace(A, D, cfg, res, min_iter=T, seed=11, **{k_: v_ for k_, v_ in kw.items() if k_ in ("relax_Config", "relax_rate_fixed", "wise")})
+    print("  VERIFY", v)
 
 step("load", t_load)
 step("em", t_em)
@@ -94,3 +96,15 @@ def t_synth():
     print("  bench", h.bench_sweeps(3, 20))
     lab = h.synth_labels(); pr = h.fetch("prob"); print("  acc", (pr.argmax(1) + 1 == lab).mean())
 step("synth C3", t_synth)
+
+def t_synth4():
+    rng = np.random.default_rng(2)
+    N, M, K = 10000, 1000000, 16
+    cfg = (rng.random((N, K)) < 0.3).astype(float); cfg[:, 0] = 0
+    t = time.time(); h.synth_generate(N, M, K, cfg, 0.05, 7); print("  synth", time.time() - t, h.data_info())
+    t = time.time()
+    h.gibbs_run(cfg, None, min_iter=12, max_iter=12, seed=1, keep_prob_all=1)
+    print("  run 12 its", time.time() - t)
+    print("  bench", h.bench_sweeps(3, 10))
+    lab = h.synth_labels(); pr = h.fetch("prob"); print("  acc", (pr.argmax(1) + 1 == lab).mean())
+step("synth C4", t_synth4)
