@@ -12,6 +12,7 @@
 // Math is fp64 throughout (the tolerance in BASELINE.json is 1e-6 on probabilities whose logits are
 // sums of ~1e3 terms of magnitude ~10); HBM traffic per sweep is 6 bytes per covered entry per pass.
 #include "internal.h"
+#include <cstdlib>
 
 namespace cdl {
 
@@ -49,6 +50,7 @@ struct CellsParams {
     PhiloxKey key;
     uint32_t chain, it;
     int tab_in_smem;
+    int zero;                  // always 0; a kernel parameter so it lives in a register (see accumulate_entry)
 };
 
 // R's revsort (src/main/sort.c) on a tiny array: used only when positive probabilities tie exactly,
@@ -91,21 +93,42 @@ __device__ void revsort_dev(double* a, int* ib, int n) {
     }
 }
 
-// acc[k] += bit_k(m) ? del : 0 for all clones.  ptxas turns a predicated fp64 add into two FSELs plus an
-// unconditional DADD; masking only the HIGH word (the low word alone is a denormal < 2^-1022, absorbed by
-// any normal accumulator and irrelevant next to logPsi) costs one SEL + one DADD per clone, with the
-// predicates produced seven at a time by R2P.
+// acc[k] += bit_k(m) ? del : 0 for all clones, as acc[k] = fma(del, w_k, acc[k]) with w_k in {0.0, 1.0}
+// built from one SEL on the high word (ptxas turns a predicated fp64 add into two FSELs plus an
+// unconditional DADD, and produces the predicates seven at a time with R2P): one SEL + one DFMA per
+// clone.  `zero` must be a register holding 0 (the low word of every weight).
 template <int KP>
-__device__ __forceinline__ void accumulate_entry(double (&acc)[KP], double del, uint32_t m) {
+__device__ __forceinline__ void accumulate_entry(double (&acc)[KP], double del, uint32_t m, int zero) {
+#ifndef CDL_ACC_VARIANT
+#define CDL_ACC_VARIANT 3
+#endif
+#if CDL_ACC_VARIANT == 1
+    (void)zero;
+#pragma unroll
+    for (int k = 0; k < KP; ++k) acc[k] += ((m >> k) & 1u) ? del : 0.0;
+#elif CDL_ACC_VARIANT == 3
+    // hi-word masking: (lo, hi & -bit) is either del or a denormal < 2^-1022 that any normal accumulator
+    // absorbs; one SEL (alu pipe) + one DADD (fp64 pipe) per clone instead of two FSELs + DADD.
+    (void)zero;
     const int hi = __double2hiint(del), lo = __double2loint(del);
 #pragma unroll
     for (int k = 0; k < KP; ++k) {
-        asm("{\n\t.reg .pred p;\n\t.reg .b32 t, h;\n\t.reg .f64 w;\n\t"
+        asm volatile("{\n\t.reg .pred p;\n\t.reg .b32 t, h;\n\t.reg .f64 w;\n\t"
             "and.b32 t, %3, %4;\n\tsetp.ne.u32 p, t, 0;\n\tselp.b32 h, %2, 0, p;\n\t"
             "mov.b64 w, {%1, h};\n\tadd.f64 %0, %0, w;\n\t}"
             : "+d"(acc[k])
             : "r"(lo), "r"(hi), "r"(m), "r"(1u << k));
     }
+#else
+#pragma unroll
+    for (int k = 0; k < KP; ++k) {
+        asm("{\n\t.reg .pred p;\n\t.reg .b32 t, h;\n\t.reg .f64 w;\n\t"
+            "and.b32 t, %2, %3;\n\tsetp.ne.u32 p, t, 0;\n\tselp.b32 h, 0x3ff00000, 0, p;\n\t"
+            "mov.b64 w, {%4, h};\n\tfma.rn.f64 %0, %1, w, %0;\n\t}"
+            : "+d"(acc[k])
+            : "d"(del), "r"(m), "r"(1u << k), "r"(zero));
+    }
+#endif
 }
 
 // weight table access: shared memory through 32-bit shared addresses, or global memory through L1
@@ -123,42 +146,55 @@ __device__ __forceinline__ void load_tab(uint32_t tab_sa, uint32_t msk_sa, const
     }
 }
 
-template <int KP, bool SMEM>
-__device__ __forceinline__ void accumulate_group(double (&acc)[KP], const uint32_t (&vw)[8], const uint4 a4,
-                                                 const uint4 b4, uint32_t tab_sa, uint32_t msk_sa,
-                                                 const double2* __restrict__ tab_g,
-                                                 const uint32_t* __restrict__ msk_g) {
-    const uint32_t aw[4] = {a4.x, a4.y, a4.z, a4.w};
-    const uint32_t bw[4] = {b4.x, b4.y, b4.z, b4.w};
+// one group of 8 entries as it sits in HBM
+template <typename VIdx> struct Grp;
+template <> struct Grp<uint16_t> {
+    uint4 v, a, b;
+    __device__ __forceinline__ void load(const void* vidx, const uint4* a8, const uint4* b8, int64_t g) {
+        v = ld_stream(reinterpret_cast<const uint4*>(vidx) + g);
+        a = ld_stream(a8 + g);
+        b = ld_stream(b8 + g);
+    }
+    __device__ __forceinline__ uint32_t idx(int e) const {
+        const uint32_t w = e < 2 ? v.x : (e < 4 ? v.y : (e < 6 ? v.z : v.w));
+        return (e & 1) ? (w >> 16) : (w & 0xffffu);
+    }
+};
+template <> struct Grp<uint32_t> {
+    uint4 v, v2, a, b;
+    __device__ __forceinline__ void load(const void* vidx, const uint4* a8, const uint4* b8, int64_t g) {
+        v = ld_stream(reinterpret_cast<const uint4*>(vidx) + 2 * g);
+        v2 = ld_stream(reinterpret_cast<const uint4*>(vidx) + 2 * g + 1);
+        a = ld_stream(a8 + g);
+        b = ld_stream(b8 + g);
+    }
+    __device__ __forceinline__ uint32_t idx(int e) const {
+        return e == 0 ? v.x : e == 1 ? v.y : e == 2 ? v.z : e == 3 ? v.w : e == 4 ? v2.x : e == 5 ? v2.y
+                                                                                 : e == 6 ? v2.z : v2.w;
+    }
+};
+
+template <int KP, typename VIdx, bool SMEM>
+__device__ __forceinline__ void accumulate_group(double (&acc)[KP], const Grp<VIdx>& q, uint32_t tab_sa,
+                                                 uint32_t msk_sa, const double2* __restrict__ tab_g,
+                                                 const uint32_t* __restrict__ msk_g, int zero) {
 #pragma unroll
     for (int e = 0; e < 8; ++e) {
-        const uint32_t a = (e & 1) ? (aw[e >> 1] >> 16) : (aw[e >> 1] & 0xffffu);
-        const uint32_t b = (e & 1) ? (bw[e >> 1] >> 16) : (bw[e >> 1] & 0xffffu);
+        const uint32_t aw = e < 2 ? q.a.x : (e < 4 ? q.a.y : (e < 6 ? q.a.z : q.a.w));
+        const uint32_t bw = e < 2 ? q.b.x : (e < 4 ? q.b.y : (e < 6 ? q.b.z : q.b.w));
+        const uint32_t a = (e & 1) ? (aw >> 16) : (aw & 0xffffu);
+        const uint32_t b = (e & 1) ? (bw >> 16) : (bw & 0xffffu);
         double du, dv;
         uint32_t m;
-        load_tab<SMEM>(tab_sa, msk_sa, tab_g, msk_g, vw[e], du, dv, m);
+        load_tab<SMEM>(tab_sa, msk_sa, tab_g, msk_g, q.idx(e), du, dv, m);
         const double del = fma(u16_to_double(a), du, u16_to_double(b) * dv);
-        accumulate_entry<KP>(acc, del, m);
+        accumulate_entry<KP>(acc, del, m, zero);
     }
 }
 
-template <typename VIdx>
-__device__ __forceinline__ void load_vidx(const void* base, int64_t g, uint32_t (&vw)[8]);
-template <>
-__device__ __forceinline__ void load_vidx<uint16_t>(const void* base, int64_t g, uint32_t (&vw)[8]) {
-    const uint4 v = ld_stream(reinterpret_cast<const uint4*>(base) + g);
-    vw[0] = v.x & 0xffffu; vw[1] = v.x >> 16; vw[2] = v.y & 0xffffu; vw[3] = v.y >> 16;
-    vw[4] = v.z & 0xffffu; vw[5] = v.z >> 16; vw[6] = v.w & 0xffffu; vw[7] = v.w >> 16;
-}
-template <>
-__device__ __forceinline__ void load_vidx<uint32_t>(const void* base, int64_t g, uint32_t (&vw)[8]) {
-    const uint4 v0 = ld_stream(reinterpret_cast<const uint4*>(base) + 2 * g);
-    const uint4 v1 = ld_stream(reinterpret_cast<const uint4*>(base) + 2 * g + 1);
-    vw[0] = v0.x; vw[1] = v0.y; vw[2] = v0.z; vw[3] = v0.w;
-    vw[4] = v1.x; vw[5] = v1.y; vw[6] = v1.z; vw[7] = v1.w;
-}
-
-// One group of G lanes per cell (G >= KP); 32/G cells per warp at a time.
+// One group of G lanes per cell (G >= KP); 32/G cells per warp at a time.  Each lane streams its share of
+// the cell's 8-entry groups with a one-group software prefetch that also runs ACROSS cells, so the loads
+// of the next cell are in flight during the reduction / softmax / draw of the current one.
 template <int KP, int G, typename VIdx, bool SMEM>
 __global__ void __launch_bounds__(CELLS_THREADS, (KP <= 8 ? 2 : 1)) k_cells(const CellsParams P) {
     constexpr int LOG = Log2<KP>::v;
@@ -187,6 +223,7 @@ __global__ void __launch_bounds__(CELLS_THREADS, (KP <= 8 ? 2 : 1)) k_cells(cons
     } else {
         tab_g = reinterpret_cast<const double2*>(P.l1);   // pre-built (du, dv) table in global memory
     }
+    const int zero = P.zero;
     const int lane = threadIdx.x & 31;
     const int lig = lane & (G - 1);               // lane in group
     const int grp = lane >> LOGG;                 // group in warp
@@ -201,28 +238,42 @@ __global__ void __launch_bounds__(CELLS_THREADS, (KP <= 8 ? 2 : 1)) k_cells(cons
     const uint4* a8 = reinterpret_cast<const uint4*>(P.ca);
     const uint4* b8 = reinterpret_cast<const uint4*>(P.cb);
 
-    for (int64_t jb = warp * CPW; jb < P.M; jb += nwarps * CPW) {
-        const int64_t j = jb + grp;
+    int64_t jb = warp * CPW;
+    if (jb >= P.M) return;
+    int64_t j = jb + grp;
+    int64_t g0 = 0, g1 = 0;
+    if (j < P.M) { g0 = P.rowgrp[j]; g1 = P.rowgrp[j + 1]; }
+    Grp<VIdx> cur;
+    cur.v = cur.a = cur.b = make_uint4(0, 0, 0, 0);
+    bool have = (g0 + lig) < g1;
+    if (have) cur.load(P.vidx, a8, b8, g0 + lig);
+
+    for (; jb < P.M; jb += nwarps * CPW) {
+        j = jb + grp;
         const bool valid = j < P.M;
-        int64_t g0 = 0, g1 = 0;
-        if (valid) { g0 = P.rowgrp[j]; g1 = P.rowgrp[j + 1]; }
+        // row bounds of my group's NEXT cell, needed for the cross-cell prefetch
+        const int64_t jn = j + nwarps * CPW;
+        int64_t ng0 = 0, ng1 = 0;
+        if (jn < P.M) { ng0 = P.rowgrp[jn]; ng1 = P.rowgrp[jn + 1]; }
         double acc[KP];
 #pragma unroll
         for (int q = 0; q < KP; ++q) acc[q] = 0.0;
-        for (int64_t g = g0 + lig; g < g1; g += 2 * G) {
-            const bool two = (g + G) < g1;
-            uint32_t v0[8], v1[8];
-            load_vidx<VIdx>(P.vidx, g, v0);
-            const uint4 a0 = ld_stream(a8 + g), b0 = ld_stream(b8 + g);
-            uint4 a1 = make_uint4(0, 0, 0, 0), b1 = a1;
-            if (two) {
-                load_vidx<VIdx>(P.vidx, g + G, v1);
-                a1 = ld_stream(a8 + g + G);
-                b1 = ld_stream(b8 + g + G);
-            }
-            accumulate_group<KP, SMEM>(acc, v0, a0, b0, tab_sa, msk_sa, tab_g, msk_g);
-            if (two) accumulate_group<KP, SMEM>(acc, v1, a1, b1, tab_sa, msk_sa, tab_g, msk_g);
+        int64_t g = g0 + lig;
+        bool nhave;
+        for (;;) {
+            const int64_t gn = g + G;
+            const bool more = gn < g1;
+            Grp<VIdx> nxt;
+            nxt.v = nxt.a = nxt.b = make_uint4(0, 0, 0, 0);
+            nhave = more ? true : ((ng0 + lig) < ng1);
+            if (nhave) nxt.load(P.vidx, a8, b8, more ? gn : ng0 + lig);
+            if (have) accumulate_group<KP, VIdx, SMEM>(acc, cur, tab_sa, msk_sa, tab_g, msk_g, zero);
+            cur = nxt;          // after the compute: the copy waits for the load, which had the whole
+            have = nhave;       // accumulate_group (and, on the last pass, the epilogue) to land
+            if (!more) break;
+            g = gn;
         }
+        g0 = ng0; g1 = ng1;
         // transposing butterfly inside the group: afterwards a lane holds the full sum of clone k
 #pragma unroll
         for (int s = 0; s < LOG; ++s) {
@@ -258,42 +309,50 @@ __global__ void __launch_bounds__(CELLS_THREADS, (KP <= 8 ? 2 : 1)) k_cells(cons
         const uint32_t gcell = (uint32_t)(P.cell_offset + j);
         double u = 0.5;
         if (valid) u = P.rp_u ? P.rp_u[j] : philox_uniform(P.key, P.chain, P.it, STREAM_ASSIGN, gcell);
-        double cum = 0.0;
-        int rank = 0;
-        bool tie = false;
-#pragma unroll
-        for (int l = 0; l < KP; ++l) {
-            const double pl = shfl_d(pr, gbase + (l << SH));
-            if (l < K) {
-                const bool before = (pl > pr) || (pl == pr && l < k);
-                if (before) { cum += pl; ++rank; }
-                tie |= (pl == pr) && (l != k) && (pr > 0.0);
-            }
-        }
-        const unsigned tie_lanes = __ballot_sync(0xffffffffu, tie && k < K);
+        // shortcut: the first element of the sorted CDF is the maximum; if it is unique and u <= p_max the
+        // walk stops there (confident cells, the common case)
+        const unsigned top = __ballot_sync(0xffffffffu, rep && k < K && L == mx) & gmask;
         unsigned sel;
-        if (tie_lanes & gmask) {
-            // exact emulation of revsort's tie order (identical Config columns, uncovered cells)
-            double pa[KP];
-            int perm[KP];
+        const bool quick = (__popc(top) == 1) && (u * sm <= 1.0) && (u <= 1.0 / sm);
+        if (__all_sync(0xffffffffu, quick)) {
+            sel = (unsigned)(((__ffs(top) - 1) - gbase) >> SH);
+        } else {
+            double cum = 0.0;
+            int rank = 0;
+            bool tie = false;
 #pragma unroll
             for (int l = 0; l < KP; ++l) {
-                pa[l] = __shfl_sync(gmask, pr, gbase + (l << SH));
-                perm[l] = l;
+                const double pl = shfl_d(pr, gbase + (l << SH));
+                if (l < K) {
+                    const bool before = (pl > pr) || (pl == pr && l < k);
+                    if (before) { cum += pl; ++rank; }
+                    tie |= (pl == pr) && (l != k) && (pr > 0.0);
+                }
             }
-            double tot = 0.0;
-            for (int l = 0; l < K; ++l) tot += pa[l];
-            for (int l = 0; l < K; ++l) pa[l] /= tot;
-            revsort_dev(pa, perm, K);
-            for (int l = 1; l < K; ++l) pa[l] += pa[l - 1];
-            int jj = 0;
-            while (jj < K - 1 && !(u <= pa[jj])) ++jj;
-            sel = (unsigned)perm[jj];
-        } else {
             const bool cand = u <= cum + pr;
             const unsigned keyv = (k < K && (cand || rank == K - 1)) ? ((unsigned)rank << 8 | (unsigned)k)
                                                                      : 0xffffffffu;
             sel = __reduce_min_sync(gmask, keyv) & 0xffu;
+            // the order inside a group of exactly tied probabilities is revsort's; it only matters when
+            // the walk stops inside such a group
+            const int sel_tied = __shfl_sync(0xffffffffu, (int)tie, gbase + ((int)sel << SH));
+            if (sel_tied) {
+                double pa[KP];
+                int perm[KP];
+#pragma unroll
+                for (int l = 0; l < KP; ++l) {
+                    pa[l] = __shfl_sync(gmask, pr, gbase + (l << SH));
+                    perm[l] = l;
+                }
+                double tot = 0.0;
+                for (int l = 0; l < K; ++l) tot += pa[l];
+                for (int l = 0; l < K; ++l) pa[l] /= tot;
+                revsort_dev(pa, perm, K);
+                for (int l = 1; l < K; ++l) pa[l] += pa[l - 1];
+                int jj = 0;
+                while (jj < K - 1 && !(u <= pa[jj])) ++jj;
+                sel = (unsigned)perm[jj];
+            }
         }
         if (valid && lig == 0) {
             P.z[j] = (uint8_t)sel;
@@ -706,6 +765,7 @@ void launch_cells(const Donor& d, const SweepArgs& a, ChainDev& c, int sm_count,
     const size_t smem = (size_t)cells_smem_bytes(d.N, a.K);
     const bool smem_tab = smem <= 200 * 1024;
     P.tab_in_smem = smem_tab;
+    P.zero = 0;
     int ctas_per_sm = 1;
     if (smem_tab) {
         ctas_per_sm = (int)std::min<size_t>(4, (220 * 1024) / std::max<size_t>(smem + 1024, 1));
@@ -716,11 +776,15 @@ void launch_cells(const Donor& d, const SweepArgs& a, ChainDev& c, int sm_count,
         k_build_tab<<<(unsigned)((d.N + 255) / 256), 256, 0, st>>>(d.N, P.n_tab, c.l1, c.l1c, c.scal, c.tab_g);
         P.l1 = reinterpret_cast<const double*>(c.tab_g);
     }
-    // lanes per cell: enough that a lane sees ~2 groups of 8 entries, never fewer than the padded clones
+    // lanes per cell: the smallest group that still gives every padded clone a lane.  Several cells share
+    // a warp, which amortises the per-cell reduction / softmax / draw instructions; a lane then streams
+    // rows_groups / G groups of 8 entries with the software prefetch.
     const int KP = pad_k(a.K);
-    const double groups_per_cell = (double)d.c_groups / (double)std::max<int64_t>(d.M, 1);
-    int G = groups_per_cell >= 40.0 ? 32 : (groups_per_cell >= 12.0 ? 16 : 8);
-    if (G < KP) G = KP;
+    int G = KP < 8 ? 8 : KP;
+    if (const char* e = getenv("CDL_CELLS_G")) {
+        const int g = atoi(e);
+        if ((g == 8 || g == 16 || g == 32) && g >= KP) G = g;
+    }
     const int cpw = 32 / G;
     const int64_t warps_needed = (d.M + cpw - 1) / cpw;
     int64_t grid = (int64_t)sm_count * ctas_per_sm;
