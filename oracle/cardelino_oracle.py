@@ -780,3 +780,23 @@ def verify_gibbs_trace(A, D, Config, rec, Psi=None, relax_Config=True, relax_rat
         out["max_dloglik_rel"] = max(out["max_dloglik_rel"], abs(ll - rl) / max(abs(ll), 1e-300))
         Config_prev = rec_cfg
     return out
+
+
+class RecordingDraws(NumpyDraws):
+    """NumpyDraws that also records every uniform it hands out, so a chain can be replayed elsewhere
+    (what tools/record_reference.R does for a genuine R run)."""
+
+    def __init__(self, seed, T, M, NK):
+        super().__init__(seed)
+        self.ua = np.full((T, M), 0.5)
+        self.uc = np.full((T, NK), 0.5)
+
+    def u_assign(self, it, M):
+        u = self.rng.random(M)
+        self.ua[it - 1] = u
+        return u
+
+    def u_config(self, it, NK):
+        u = self.rng.random(NK)
+        self.uc[it - 1] = u
+        return u

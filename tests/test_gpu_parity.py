@@ -1,0 +1,310 @@
+"""GPU parity tests (run with -m gpu on a B200).  Every test calls the CUDA path through the C ABI
+(ctypes -> libcardelino_b200.so) and checks it against the NumPy oracle on the same inputs.
+
+Tolerances (BASELINE.json north_star): get_logLik / EM <= 1e-6 relative; replayed chains reproduce
+assignments exactly except draws within 1e-6 of a CDF boundary (or whose order in sample()'s sort is
+decided by rounding between two probabilities equal to 1e-12); converged prob within Monte-Carlo error
+(max |dprob| <= 0.02 on decided cells, identical argmax where prob > 0.9)."""
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+
+from oracle import cardelino_oracle as O  # noqa: E402
+
+REL = 1e-6
+
+
+def _cb():
+    import cardelino_b200 as cb
+    return cb
+
+
+def _verify(cb, h, A, D, cfg, T=40, seed=11, **kw):
+    res = cb.clone_id_Gibbs(A, D, cfg, min_iter=T, max_iter=T, seed=seed, keep_assign_all=True, handle=h,
+                            verbose=False, **kw)
+    okw = {k: v for k, v in kw.items() if k in ("relax_Config", "relax_rate_fixed", "wise", "Psi",
+                                                "keep_base_clone", "relax_rate_prior")}
+    v = O.verify_gibbs_trace(A, D, cfg, res, min_iter=T, seed=seed, **okw)
+    assert v["max_dprob"] <= 1e-9, v
+    assert v["hard"] == 0 and v["config_hard"] == 0, v
+    assert v["max_dloglik_rel"] <= REL, v
+    n_lab = (T - 1) * np.asarray(A).shape[1]
+    assert v["boundary"] + v["near_tie"] <= max(2, 0.02 * n_lab), v
+    return res, v
+
+
+def test_em_example_donor(gpu_handle, example_donor):
+    cb = _cb()
+    A, D, Z = example_donor
+    for init in [(0.1, 0.5), (0.2, 0.35)]:
+        g = cb.clone_id_EM(A, D, Z, theta_init=init, handle=gpu_handle, verbose=False)
+        o = O.clone_id_EM(A, D, Z, theta_init=init)
+        assert g["n_iter"] == o["n_iter"]
+        assert np.allclose(g["theta"], o["theta"], rtol=REL, atol=0)
+        assert abs(g["logLik"] - o["logLik"]) <= REL * abs(o["logLik"])
+        assert np.abs(g["prob"] - o["prob"]).max() <= 1e-9
+    assert g["logLik"] == pytest.approx(-1854.0001, abs=2e-4)      # survey known answer
+
+
+def test_em_c2(gpu_handle, c2_donor):
+    cb = _cb()
+    A, D, Z, _ = c2_donor
+    psi = np.array([0.4, 0.3, 0.2, 0.1])
+    g = cb.clone_id_EM(A, D, Z, Psi=psi, theta_init=(0.05, 0.4), handle=gpu_handle, verbose=False)
+    o = O.clone_id_EM(A, D, Z, Psi=psi, theta_init=(0.05, 0.4))
+    assert g["n_iter"] == o["n_iter"]
+    assert np.allclose(g["theta"], o["theta"], rtol=REL)
+    assert abs(g["logLik"] - o["logLik"]) <= REL * abs(o["logLik"])
+    assert np.abs(g["prob"] - o["prob"]).max() <= 1e-9
+
+
+def test_get_loglik(gpu_handle, example_donor, c2_donor):
+    cb = _cb()
+    rng = np.random.default_rng(0)
+    for A, D, Z in (example_donor, c2_donor[:3]):
+        A1, B1, _ = O.preprocess(A, D)
+        N, M = A.shape
+        K = Z.shape[1]
+        gpu_handle.load_dense(A, D)
+        lab = rng.integers(1, K + 1, M)
+        th1 = rng.uniform(0.2, 0.8, N)
+        g = gpu_handle.get_loglik(Z, lab, 0.03, th1)
+        o = O.get_logLik(A1, B1, Z, lab, 0.03, np.repeat(th1[:, None], M, 1))
+        assert abs(g - o) <= REL * abs(o)
+        P = rng.dirichlet(np.ones(K), M)
+        C = rng.uniform(0, 1, Z.shape)
+        g = gpu_handle.get_loglik(C, P, 0.03, th1)
+        o = O.get_logLik(A1, B1, C, P, 0.03, np.repeat(th1[:, None], M, 1))
+        assert abs(g - o) <= REL * abs(o)
+        g = gpu_handle.get_loglik(C, P, 0.03, 0.41)                  # scalar theta1 (wise = global)
+        o = O.get_logLik(A1, B1, C, P, 0.03, np.full((N, M), 0.41))
+        assert abs(g - o) <= REL * abs(o)
+
+
+@pytest.mark.parametrize("kw", [
+    dict(),                                                   # the reference test's configuration
+    dict(wise="global", relax_rate_fixed=0.3),
+    dict(relax_Config=False),
+    dict(keep_base_clone=False, relax_rate_prior=(2, 5)),
+    dict(Psi=np.array([0.1, 0.2, 0.3, 0.4])),
+])
+def test_gibbs_stepwise_example_donor(gpu_handle, example_donor, kw):
+    A, D, Z = example_donor
+    res, v = _verify(_cb(), gpu_handle, A, D, Z, T=60, **kw)
+    assert res["prob_all"].shape == (60, 428 * 4) and np.all(res["prob_all"][0] == 0)
+    assert res["Config_all"].shape == (60, 34 * 4)
+    assert res["prob"].shape == (428, 4) and res["prob_variant"].shape == (34, 428)
+
+
+@pytest.mark.parametrize("K", [2, 3, 6, 12, 20])
+def test_gibbs_denovo_clone_counts(gpu_handle, example_donor, K):
+    """De-novo mode (Config = 0, relax rate fixed at 0.5, R/clone_id.R:98-105): exercises every padded
+    clone width (4, 8, 16, 32) and the exact-tie path of the categorical draw."""
+    A, D, _ = example_donor
+    _verify(_cb(), gpu_handle, A, D, np.zeros((34, K)), T=30, relax_rate_fixed=0.5)
+
+
+def test_gibbs_c2_four_chains(gpu_handle, c2_donor):
+    """BASELINE config 2: sim_read_count donor, 4 clones, relax_Config = TRUE, n_chain = 4."""
+    cb = _cb()
+    A, D, Z, lab = c2_donor
+    T = 40
+    outs = cb.clone_id_Gibbs(A, D, Z, min_iter=T, max_iter=T, seed=5, n_chain=4, keep_assign_all=True,
+                             handle=gpu_handle, verbose=False, _all_chains=True)
+    assert len(outs) == 4
+    for c, res in enumerate(outs):
+        v = O.verify_gibbs_trace(A, D, Z, res, min_iter=T, seed=5, chain=c)
+        assert v["max_dprob"] <= 1e-9 and v["hard"] == 0 and v["config_hard"] == 0, v
+        assert v["max_dloglik_rel"] <= REL
+    assert not np.array_equal(outs[0]["assign_all"], outs[1]["assign_all"])     # chains are independent
+    merged = cb.clone_id(A, D, Z, min_iter=T, max_iter=T, seed=5, n_chain=4, handle=gpu_handle, verbose=False)
+    assert merged["n_chain"] == 4 and np.allclose(merged["prob"].sum(1), 1)
+    assert (merged["prob"].argmax(1) + 1 == lab).mean() > 0.8
+
+
+def test_replay_mode(gpu_handle, example_donor):
+    """Correctness check 2 of the north star: inject a recorded run's uniforms and theta draws; the
+    assignments and Config flips must be reproduced."""
+    cb = _cb()
+    A, D, Z = example_donor
+    T, M, NK = 50, 428, 34 * 4
+    rec = O.RecordingDraws(21, T, M, NK)
+    o = O.clone_id_Gibbs(A, D, Z, min_iter=T, max_iter=T, draws=rec)
+    replay = {"n_rows": T, "u_assign": rec.ua, "u_config": rec.uc, "theta0": o["theta0_all"].ravel(),
+              "theta1": o["theta1_all"], "relax_rate": o["relax_rate_all"]}
+    g = cb.clone_id_Gibbs(A, D, Z, min_iter=T, max_iter=T, replay=replay, keep_assign_all=True,
+                          handle=gpu_handle, verbose=False)
+    v = O.verify_gibbs_trace(A, D, Z, g, min_iter=T, u_assign=rec.ua, u_config=rec.uc)
+    assert v["hard"] == 0 and v["config_hard"] == 0 and v["max_dprob"] <= 1e-9, v
+    assert np.allclose(g["theta0_all"].ravel(), o["theta0_all"].ravel())
+    # the free-running oracle chain itself is reproduced unless a rounding-order tie intervened
+    if v["boundary"] + v["near_tie"] == 0:
+        assert np.array_equal(g["assign_all"], o["assign_all"])
+        assert np.array_equal(g["Config_all"], o["Config_all"])
+        assert np.abs(g["prob"] - o["prob"]).max() <= 1e-9
+        assert abs(g["DIC"]["DIC"] - o["DIC"]["DIC"]) <= 1e-6 * abs(o["DIC"]["DIC"])
+
+
+def test_stop_rule_and_summaries(gpu_handle, example_donor):
+    """Geweke stop rule (every 100 sweeps from min_iter), burn-in, posterior means, prob_variant, DIC."""
+    cb = _cb()
+    A, D, Z = example_donor
+    g = cb.clone_id_Gibbs(A, D, Z, min_iter=100, max_iter=600, seed=3, handle=gpu_handle, verbose=False)
+    it = g["n_iter"]
+    assert it % 100 == 0 or it == 600
+    for chk in range(100, it + 1, 100):
+        frac = O.converged_fraction(g["prob_all"][:chk])
+        if chk < it:
+            assert not frac > 0.995          # the chain did not stop earlier
+        elif it < 600:
+            assert frac > 0.995              # and it stopped because the rule fired
+    assert g["percent_converged"] == pytest.approx(O.r_round(O.converged_fraction(g["prob_all"][:it]), 3) * 100)
+    nb = int(np.ceil(it * 0.5))
+    assert g["n_buin"] == nb
+    assert np.abs(g["prob"] - g["prob_all"][nb - 1:it].mean(0).reshape(4, 428).T).max() <= 1e-12
+    assert np.abs(g["Config_prob"] - g["Config_all"][nb - 1:it].mean(0).reshape(4, 34).T).max() <= 1e-12
+    assert g["theta0"] == pytest.approx(g["theta0_all"][nb - 1:it].mean())
+    assert g["relax_rate"] == pytest.approx(g["relax_rate_all"][nb - 1:it].mean())
+    # prob_variant (R/clone_id.R:606-622)
+    from scipy.stats import binom
+    A1, B1, _ = O.preprocess(A, D)
+    p1 = sum(binom.pmf(A1, A1 + B1, g["theta1_all"][i][:, None]) for i in range(nb - 1, it))
+    p0 = sum(binom.pmf(A1, A1 + B1, g["theta0_all"][i, 0]) for i in range(nb - 1, it))
+    assert np.abs(g["prob_variant"] - p1 / (p1 + p0)).max() <= 1e-9
+    th1m = np.repeat(g["theta1_all"][nb - 1:it].mean(0)[:, None], 428, 1)
+    llp = O.get_logLik(A1, B1, g["Config_prob"], g["prob"], g["theta0"], th1m)
+    assert abs(g["logLik_post"] - llp) <= REL * abs(llp)
+    d = O.devianceIC(g["logLik"][nb - 1:it], llp)
+    assert abs(g["DIC"]["DIC"] - d["DIC"]) <= 1e-6 * abs(d["DIC"])
+
+
+def test_relabel(gpu_handle, example_donor):
+    cb = _cb()
+    A, D, Z = example_donor
+    g = cb.clone_id_Gibbs(A, D, Z, min_iter=60, max_iter=60, seed=9, relabel=True, handle=gpu_handle,
+                          verbose=False)
+    assert g["prob"].shape == (428, 4) and np.allclose(g["prob"].sum(1), 1)
+
+
+def test_converged_posterior_matches_oracle_chains(gpu_handle, example_donor):
+    """Correctness check 3: converged prob agrees with independent CPU chains within Monte-Carlo error."""
+    cb = _cb()
+    A, D, Z = example_donor
+    T = 3000
+    g = cb.clone_id(A, D, Z, min_iter=T, max_iter=T, n_chain=4, seed=17, handle=gpu_handle, verbose=False,
+                    keep_prob_all=1)
+    os_ = [O.clone_id_Gibbs(A, D, Z, min_iter=1500, max_iter=1500, draws=O.NumpyDraws(100 + c)) for c in range(2)]
+    po = sum(o["prob"] for o in os_) / len(os_)
+    covered = (np.nan_to_num(D) > 0).sum(0) > 0
+    assert np.abs(g["prob"] - po)[covered].max() <= 0.06
+    assert np.abs(g["prob"] - po).mean() <= 0.01
+    sure = po.max(1) > 0.9
+    assert sure.sum() > 20 and np.array_equal(g["prob"][sure].argmax(1), po[sure].argmax(1))
+    assert abs(g["theta0"] - np.mean([o["theta0"] for o in os_])) < 0.004
+    assert np.abs(g["Config_prob"] - sum(o["Config_prob"] for o in os_) / len(os_)).max() < 0.25
+
+
+def test_sparse_input_equals_dense(gpu_handle, c2_donor):
+    import scipy.sparse as sp
+    cb = _cb()
+    A, D, Z, _ = c2_donor
+    Dn, An = np.nan_to_num(D), np.nan_to_num(A)
+    An[Dn == 0] = 0
+    kw = dict(min_iter=15, max_iter=15, seed=2, handle=gpu_handle, verbose=False)
+    a = cb.clone_id_Gibbs(A, D, Z, **kw)
+    b = cb.clone_id_Gibbs(sp.csc_matrix(An), sp.csc_matrix(Dn), Z, **kw)
+    assert np.array_equal(a["prob_all"], b["prob_all"]) and np.array_equal(a["Config_all"], b["Config_all"])
+    gpu_handle.load_dense(A, D)
+    p, i, av, dv = gpu_handle.export_csc_u16()
+    c = cb.clone_id_Gibbs(cb.SparseCounts(A.shape[0], A.shape[1], p, i, av, dv), None, Z, **kw)
+    assert np.array_equal(a["prob_all"], c["prob_all"]) and np.array_equal(a["logLik"], c["logLik"])
+
+
+def test_many_variants_uint32_index_and_global_table(gpu_handle):
+    """N > 65536: uint32 variant ids in the cell-major layout and the weight table read from global
+    memory instead of shared memory."""
+    cb = _cb()
+    rng = np.random.default_rng(8)
+    N, M, K = 70000, 60, 5
+    cfg = (rng.random((N, K)) < 0.3).astype(float)
+    cfg[:, 0] = 0
+    nnz_per = 300
+    rows = np.concatenate([np.sort(rng.choice(N, nnz_per, replace=False)) for _ in range(M)]).astype(np.int32)
+    p = np.arange(M + 1, dtype=np.int64) * nnz_per
+    d = rng.integers(1, 12, rows.size).astype(np.uint16)
+    a = rng.binomial(d, 0.3).astype(np.uint16)
+    counts = cb.SparseCounts(N, M, p, rows, a, d)
+    T = 12
+    res = cb.clone_id_Gibbs(counts, None, cfg, min_iter=T, max_iter=T, seed=4, keep_assign_all=True,
+                            handle=gpu_handle, verbose=False, light=False, keep_prob_all=1)
+    import scipy.sparse as sp
+    Dm = sp.csc_matrix((d.astype(float), rows, p), shape=(N, M)).toarray()
+    Am = sp.csc_matrix((a.astype(float), rows, p), shape=(N, M)).toarray()
+    Dm[Dm == 0] = np.nan
+    Am[np.isnan(Dm)] = np.nan
+    v = O.verify_gibbs_trace(Am, Dm, cfg, res, min_iter=T, seed=4, dense_loglik=False)
+    assert v["max_dprob"] <= 1e-9 and v["hard"] == 0 and v["config_hard"] == 0 and v["max_dloglik_rel"] <= REL, v
+
+
+def test_full_size_properties(gpu_handle):
+    """At BASELINE's single-GPU sizes (C3 shape) through size-independent properties: probabilities sum to
+    one, the sufficient statistics conserve the read totals (via the logLik identity), the run is
+    bit-reproducible, an export -> reload round trip reproduces it, and labels are recovered."""
+    cb = _cb()
+    import bench
+    N, M, K, cov = bench.WORKLOADS["C3"]
+    cfg = bench.make_config(N, K)
+    h = gpu_handle
+    h.synth_generate(N, M, K, cfg, cov, 77)
+    _, _, nnz, W = h.data_info()
+    assert abs(nnz / (N * M) - cov) < 0.01
+    kw = dict(min_iter=12, max_iter=12, seed=6, keep_prob_all=1)
+    h.gibbs_run(cfg, None, **kw)
+    prob_all = h.fetch("prob_all")
+    ll = h.fetch("logLik")
+    assert np.allclose(prob_all[1:].reshape(11, K, M).sum(1), 1, atol=1e-12)
+    assert np.all(np.isfinite(ll[1:])) and np.all(ll[1:] < W)
+    t0, t1 = h.fetch("theta_traces")
+    assert np.all((t0 > 0) & (t0 < 1)) and np.all((t1 > 0) & (t1 < 1))
+    lab = h.synth_labels()
+    assert (h.fetch("prob").argmax(1) + 1 == lab).mean() > 0.98
+    h.gibbs_run(cfg, None, **kw)
+    assert np.array_equal(prob_all, h.fetch("prob_all")) and np.array_equal(ll, h.fetch("logLik"))
+    p, i, a, d = h.export_csc_u16()
+    assert p[-1] == nnz and np.all(d > 0) and np.all(a <= d)
+    h.load_csc_u16(N, M, p, i, a, d)
+    h.gibbs_run(cfg, None, **kw)
+    assert np.array_equal(prob_all, h.fetch("prob_all")) and np.array_equal(ll, h.fetch("logLik"))
+    # get_logLik on labels through the general kernel equals the sweep's table-identity trace
+    t0, t1 = h.fetch("theta_traces")
+    h.gibbs_run(cfg, None, keep_assign_all=1, **kw)
+    z = h.fetch("assign_all")
+    C = h.fetch("Config_all")
+    it = 7
+    g = h.get_loglik(C[it - 1].reshape(K, N).T, z[it - 1], t0[it - 2], t1[it - 2])
+    assert abs(g - ll[it - 1]) <= 1e-9 * abs(g)
+
+
+def test_error_paths(gpu_handle, example_donor):
+    cb = _cb()
+    A, D, Z = example_donor
+    with pytest.raises(cb.CdlError, match="non-integer"):
+        B = A.copy(); B[np.isfinite(B)] += 0.5
+        gpu_handle.load_dense(B, D)
+    with pytest.raises(cb.CdlError, match="exceeds"):
+        B = np.where(np.isfinite(D), D + 1, np.nan)
+        gpu_handle.load_dense(B, D)
+    with pytest.raises(cb.CdlError, match="65535"):
+        gpu_handle.load_dense(np.zeros((2, 2)), np.full((2, 2), 70000.0))
+    gpu_handle.load_dense(A, D)
+    with pytest.raises(cb.CdlError, match="1..32"):
+        gpu_handle.gibbs_run(np.zeros((34, 40)), None, min_iter=5, max_iter=5)
+    with pytest.raises(cb.CdlError, match="binary"):
+        gpu_handle.gibbs_run(np.full((34, 3), 0.5), None, min_iter=5, max_iter=5)
+    with pytest.raises(ValueError, match="relax_rate_fixed"):
+        cb.clone_id_Gibbs(A, D, Z, relax_rate_fixed=1.5, handle=gpu_handle)
+    with pytest.raises(ValueError, match="wise"):
+        cb.clone_id_Gibbs(A, D, Z, wise="cell", handle=gpu_handle)
+    with pytest.raises(ValueError, match="same size"):
+        cb.clone_id_Gibbs(A, D[:, :-1], Z, handle=gpu_handle)

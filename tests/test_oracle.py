@@ -1,0 +1,150 @@
+"""CPU tests of the oracle itself: known-answer vectors, base-R semantics, fixture integrity.
+The reference's own tests pin no numbers for this path (tests/testthat/test-clone_id.R:7-49 are type
+checks), so these pin the restatement against (a) Random123's published Philox vectors, (b) the fixtures
+decoded from the reference's .RData files, (c) algebraic identities of the model."""
+import math
+
+import numpy as np
+import pytest
+
+from oracle import cardelino_oracle as O
+from oracle import philox
+
+
+def test_philox_known_answers():
+    # Random123 kat_vectors, philox4x32-10
+    assert [hex(int(x)) for x in philox.philox4x32(0, 0, 0, 0, 0, 0)] == \
+        ["0x6627e8d5", "0xe169c58d", "0xbc57ac4c", "0x9b00dbd8"]
+    f = 0xFFFFFFFF
+    assert [hex(int(x)) for x in philox.philox4x32(f, f, f, f, f, f)] == \
+        ["0x408f276d", "0x41c83b0e", "0xa20bc7c6", "0x6d5451fd"]
+    assert [hex(int(x)) for x in philox.philox4x32(0x243f6a88, 0x85a308d3, 0x13198a2e, 0x03707344,
+                                                    0xa4093822, 0x299f31d0)] == \
+        ["0xd16cfe09", "0x94fdcceb", "0x5001e420", "0x24126ea1"]
+    u = philox.uniforms(3, 1, 7, philox.STREAM_ASSIGN, np.arange(1000))
+    assert u.min() > 0 and u.max() < 1 and abs(u.mean() - 0.5) < 0.05
+
+
+def test_fixture_shapes(example_donor, simulation_input):
+    A, D, Z = example_donor
+    assert A.shape == (34, 428) and D.shape == (34, 428) and Z.shape == (34, 4)
+    assert int(np.sum(np.nan_to_num(D) > 0)) == 1874
+    assert np.nanmax(D) == 55 and np.nanmax(A) == 18 and np.nanmin(D) == 1
+    assert np.all(Z[:, 0] == 0)
+    D_input, Z4 = simulation_input
+    assert D_input.shape == (439, 151) and Z4.shape == (403, 4)
+
+
+def test_revsort_descending_and_sample_semantics():
+    rng = np.random.default_rng(0)
+    for _ in range(200):
+        n = int(rng.integers(1, 9))
+        a = list(rng.random(n).round(1))           # coarse values -> many ties
+        ib = list(range(1, n + 1))
+        a0 = list(a)
+        O.revsort(a, ib)
+        assert all(a[i] >= a[i + 1] for i in range(n - 1))
+        assert sorted(ib) == list(range(1, n + 1))
+        assert all(a0[ib[i] - 1] == a[i] for i in range(n))
+    # sample(): first element of the descending CDF whose cumulative mass reaches u
+    assert O.r_sample_one([0.1, 0.7, 0.2], 0.65) == 2
+    assert O.r_sample_one([0.1, 0.7, 0.2], 0.75) == 3
+    assert O.r_sample_one([0.1, 0.7, 0.2], 0.95) == 1
+    assert O.r_sample_one([1.0], 0.3) == 1
+    # frequencies
+    u = np.random.default_rng(1).random(20000)
+    lab = np.array([O.r_sample_one([0.2, 0.5, 0.3], x) for x in u])
+    assert np.allclose(np.bincount(lab)[1:] / len(u), [0.2, 0.5, 0.3], atol=0.015)
+
+
+def test_rbinom1_semantics():
+    assert O.r_rbinom1(0.0, 0.999) == 0 and O.r_rbinom1(1.0, 0.001) == 1
+    # p <= 0.5: 1 iff u >= 1 - p ; p > 0.5: 1 iff u < p
+    assert O.r_rbinom1(0.3, 0.69) == 0 and O.r_rbinom1(0.3, 0.71) == 1
+    assert O.r_rbinom1(0.8, 0.79) == 1 and O.r_rbinom1(0.8, 0.81) == 0
+    u = np.random.default_rng(2).random(50000)
+    assert abs(O.r_rbinom1(np.full_like(u, 0.37), u).mean() - 0.37) < 0.01
+
+
+def test_preprocess_na_rules():
+    A = np.array([[1.0, np.nan, 3.0], [np.nan, 2.0, 0.0]])
+    D = np.array([[2.0, 4.0, 0.0], [np.nan, 2.0, 5.0]])
+    A1, B1, W = O.preprocess(A, D)
+    assert np.array_equal(A1, [[1, 0, 0], [0, 2, 0]])      # A NA & D>0 -> 0; D==0 -> missing
+    assert np.array_equal(B1, [[1, 4, 0], [0, 0, 5]])
+    assert W == pytest.approx(math.log(2) + 0 + 0 + 0)     # lchoose(2,1) + lchoose(4,0) + lchoose(2,2) + lchoose(5,0)
+
+
+def test_em_known_answer(example_donor):
+    """EM on example_donor converges from any start to the same optimum."""
+    A, D, Z = example_donor
+    for init in [(0.1, 0.5), (0.2, 0.35), (0.01, 0.59)]:
+        r = O.clone_id_EM(A, D, Z, theta_init=init)
+        assert r["theta"] == pytest.approx([0.03442, 0.66522], abs=2e-5)
+        assert r["logLik"] == pytest.approx(-1854.0001, abs=2e-4)
+        assert r["n_iter"] == 11
+        assert list(np.bincount(r["prob"].argmax(1))) == [186, 197, 38, 7]
+        assert np.allclose(r["prob"].sum(1), 1)
+
+
+def test_loglik_dense_equals_table_identity(example_donor):
+    A, D, Z = example_donor
+    A1, B1, _ = O.preprocess(A, D)
+    rng = np.random.default_rng(3)
+    for _ in range(5):
+        lab = rng.integers(1, 5, A.shape[1])
+        cfg = (rng.random(Z.shape) < 0.4).astype(float)
+        th1 = rng.uniform(0.05, 0.95, A.shape[0])
+        dense = O.get_logLik(A1, B1, cfg, lab, 0.02, np.repeat(th1[:, None], A.shape[1], 1))
+        table = O.get_logLik_tables(A1, B1, cfg, lab, 0.02, th1)
+        assert dense == pytest.approx(table, rel=1e-12)
+
+
+def test_geweke_matches_definition():
+    rng = np.random.default_rng(4)
+    X = rng.random((200, 7))
+    Z = O.geweke_z(X)
+    a, b = X[:20], X[99:]
+    ref = (a.mean(0) - b.mean(0)) / np.sqrt(a.var(0, ddof=1) + ((b - b.mean(0)) ** 2).sum(0) / 19 + 1e-50)
+    assert np.allclose(Z, ref)
+    assert np.all(np.isnan(O.geweke_z(X[:5])))            # first window empty -> NaN like R
+
+
+def test_deviance_ic():
+    d = O.devianceIC(np.array([-10.0, -12.0, -11.0]), -9.0)
+    assert d["DIC_Gelman"] == pytest.approx(18 + 4 * 1.0)
+    assert d["DIC_Spiegelhalter"] == pytest.approx(18 + 2 * (22 - 18))
+
+
+def test_colmatch():
+    rng = np.random.default_rng(5)
+    A = rng.random((30, 4))
+    perm = np.array([2, 0, 3, 1])
+    B = A[:, perm] + 0.01 * rng.random((30, 4))
+    for force in (True, False):
+        idx = O.colMatch(A, B, force=force)
+        assert np.array_equal(perm[idx], np.arange(4))
+
+
+def test_gibbs_dense_matches_stepwise_verifier(example_donor):
+    """The free-running dense chain and the step-wise formulas agree (self-consistency of the oracle)."""
+    A, D, Z = example_donor
+    T = 25
+    g = O.clone_id_Gibbs(A, D, Z, min_iter=T, max_iter=T, draws=O.NumpyDraws(11))
+    assert g["prob_all"].shape == (T, 428 * 4) and np.all(g["prob_all"][0] == 0)
+    assert np.allclose(g["prob_all"][1:].reshape(T - 1, 4, 428).sum(1), 1)
+    # replay its own recorded draws through the verifier (uniforms are not recorded -> only prob/logLik)
+    rec = dict(g)
+    v = O.verify_gibbs_trace(A, D, Z, rec, min_iter=T, u_assign=np.full((T, 428), 2.0),
+                             u_config=None, seed=0)
+    assert v["max_dprob"] < 1e-12 and v["max_dloglik_rel"] < 1e-12
+
+
+def test_gibbs_statistical_sanity(example_donor):
+    """Order-of-magnitude expectations from the survey's probe (appendix A)."""
+    A, D, Z = example_donor
+    g = O.clone_id_Gibbs(A, D, Z, min_iter=300, max_iter=300, draws=O.NumpyDraws(7))
+    assert 0.005 < g["theta0"] < 0.05
+    assert 0.3 < np.nanmean(g["theta1"]) < 0.6
+    assert -1350 < g["logLik"][-1] < -1100
+    assert 0.5 < (g["prob"].max(1) > 0.5).mean() < 0.85

@@ -70,6 +70,7 @@ class _Reader:
         elif typ == 14:  # REALSXP
             n = self.i32()
             v = np.frombuffer(self.b, dtype=">f8", count=n, offset=self.p).astype(np.float64)
+            v[np.isnan(v)] = np.nan      # R's NA_real_ is a SIGNALLING NaN (payload 1954): canonicalise
             self.p += 8 * n
             obj = v
         elif typ == 16:  # STRSXP
