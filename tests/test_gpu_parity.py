@@ -187,22 +187,60 @@ def test_relabel(gpu_handle, example_donor):
     assert g["prob"].shape == (428, 4) and np.allclose(g["prob"].sum(1), 1)
 
 
-def test_converged_posterior_matches_oracle_chains(gpu_handle, example_donor):
-    """Correctness check 3: converged prob agrees with independent CPU chains within Monte-Carlo error."""
+def test_converged_posterior_matches_oracle_chains(gpu_handle, c2_donor, example_donor):
+    """Correctness check 3: converged prob agrees with independent CPU chains within Monte-Carlo error
+    (max |dprob| <= 0.02, identical argmax where prob > 0.9) on an identified posterior: the
+    sim_read_count donor with relax_Config = TRUE, and example_donor with the tree held fixed.
+    (example_donor WITH relaxation is multimodal -- clone columns can swap -- so independent chains of the
+    reference itself disagree there; it is covered step-wise above.)"""
     cb = _cb()
-    A, D, Z = example_donor
-    T = 3000
-    g = cb.clone_id(A, D, Z, min_iter=T, max_iter=T, n_chain=4, seed=17, handle=gpu_handle, verbose=False,
-                    keep_prob_all=1)
-    os_ = [O.clone_id_Gibbs(A, D, Z, min_iter=1500, max_iter=1500, draws=O.NumpyDraws(100 + c)) for c in range(2)]
+    A, D, Z, lab = c2_donor
+    g = cb.clone_id(A, D, Z, min_iter=1000, max_iter=1000, n_chain=4, seed=17, handle=gpu_handle,
+                    verbose=False, keep_prob_all=0)
+    os_ = [O.clone_id_Gibbs(A, D, Z, min_iter=500, max_iter=500, draws=O.NumpyDraws(100 + c)) for c in range(2)]
     po = sum(o["prob"] for o in os_) / len(os_)
-    covered = (np.nan_to_num(D) > 0).sum(0) > 0
-    assert np.abs(g["prob"] - po)[covered].max() <= 0.06
-    assert np.abs(g["prob"] - po).mean() <= 0.01
+    assert np.abs(g["prob"] - po).max() <= 0.02
     sure = po.max(1) > 0.9
-    assert sure.sum() > 20 and np.array_equal(g["prob"][sure].argmax(1), po[sure].argmax(1))
-    assert abs(g["theta0"] - np.mean([o["theta0"] for o in os_])) < 0.004
-    assert np.abs(g["Config_prob"] - sum(o["Config_prob"] for o in os_) / len(os_)).max() < 0.25
+    assert sure.sum() > 300 and np.array_equal(g["prob"][sure].argmax(1), po[sure].argmax(1))
+    assert abs(g["theta0"] - np.mean([o["theta0"] for o in os_])) < 5e-4
+    assert np.abs(g["Config_prob"] - sum(o["Config_prob"] for o in os_) / len(os_)).max() < 0.1
+    assert abs(g["relax_rate"] - np.mean([o["relax_rate"] for o in os_])) < 0.01
+    # fixed tree on the real donor
+    A, D, Z = example_donor
+    g = cb.clone_id(A, D, Z, min_iter=4000, max_iter=4000, n_chain=4, seed=3, relax_Config=False,
+                    handle=gpu_handle, verbose=False, keep_prob_all=0)
+    os_ = [O.clone_id_Gibbs(A, D, Z, min_iter=2000, max_iter=2000, relax_Config=False,
+                            draws=O.NumpyDraws(200 + c)) for c in range(2)]
+    po = sum(o["prob"] for o in os_) / len(os_)
+    assert np.abs(g["prob"] - po).max() <= 0.03
+    sure = po.max(1) > 0.9
+    assert np.array_equal(g["prob"][sure].argmax(1), po[sure].argmax(1))
+    assert abs(g["theta0"] - np.mean([o["theta0"] for o in os_])) < 2e-3
+
+
+def test_device_beta_sampler_distribution(gpu_handle):
+    """The on-device Beta draws (Marsaglia-Tsang gammas on Philox streams) replace R's rbeta (Cheng BB/BC):
+    same distribution, different stream.  Kolmogorov-Smirnov against scipy for small, moderate and large
+    shapes, using the initial theta1 draws (one per variant, R/clone_id.R:462)."""
+    from scipy import stats
+    cb = _cb()
+    N, M = 40000, 4
+    rng = np.random.default_rng(0)
+    p = np.arange(M + 1, dtype=np.int64) * 3
+    rows = np.tile(np.array([0, 1, 2], np.int32), M)
+    counts = cb.SparseCounts(N, M, p, rows, np.ones(rows.size, np.uint16), np.full(rows.size, 2, np.uint16))
+    cfg = np.zeros((N, 2))
+    for a, b in [(0.45, 0.55), (0.2, 99.8), (5.3, 2.1), (3000.0, 9000.0)]:
+        res = cb.clone_id_Gibbs(counts, None, cfg, min_iter=3, max_iter=3, seed=int(a * 100), prior1=(a, b),
+                                handle=gpu_handle, verbose=False, light=True)
+        draws = res["theta1_all"][0]
+        assert draws.shape == (N,)
+        ks = stats.kstest(draws, stats.beta(a, b).cdf)
+        assert ks.pvalue > 1e-3, (a, b, ks)
+        assert abs(draws.mean() - a / (a + b)) < 5 * np.sqrt(a * b / ((a + b) ** 2 * (a + b + 1)) / N) + 1e-12
+        # sweep 2 draws are posterior draws: for untouched variants (3..N-1) still Beta(a, b)
+        ks2 = stats.kstest(res["theta1_all"][1][3:], stats.beta(a, b).cdf)
+        assert ks2.pvalue > 1e-3, (a, b, ks2)
 
 
 def test_sparse_input_equals_dense(gpu_handle, c2_donor):
