@@ -206,7 +206,7 @@ def run_ours(args):
                                    "table per sweep" % (world, N, K),
                        "l2": "inputs (%.1f GB per rank per pass) exceed the 126 MB L2" % (nnz_local * 6 / 1e9)},
             "nnz_clone_updates_per_s": value * nnz * K,
-            "roofline": {"bound": "hbm", "kernel": "k_cells (logLik + softmax + draw)",
+            "roofline": {"bound": "hbm", "kernel": "%s (logLik + softmax + draw)" % ("k_cells_sell" if M >= 16384 else "k_cells"),
                          "achieved": cells_b / (cells_ms * 1e-3) / 1e9, "peak": peak, "unit": "GB/s",
                          "frac": cells_b / (cells_ms * 1e-3) / 1e9 / peak, "traffic": None,
                          "peak_source": peak_src, "algorithmic_bytes_per_launch": cells_b,

@@ -18,10 +18,11 @@ EXPORTS = [
     "cdl_fetch_prob", "cdl_fetch_config_prob", "cdl_fetch_theta", "cdl_fetch_theta_traces",
     "cdl_fetch_loglik_trace", "cdl_fetch_relax_rate", "cdl_fetch_prob_all", "cdl_fetch_config_all",
     "cdl_fetch_assign_all", "cdl_fetch_prob_variant", "cdl_fetch_element_index", "cdl_get_loglik",
-    "cdl_em_run", "cdl_bench_sweeps",
+    "cdl_em_run", "cdl_bench_sweeps", "cdl_set_cells_layout",
 ]
 
 WISE = {"global": 0, "variant": 1, "element": 2}
+CELLS_LAYOUT = {"auto": 0, "rows": 1, "slices": 2}
 
 
 class CdlError(RuntimeError):
@@ -138,6 +139,10 @@ class Handle:
                 np.ascontiguousarray(a, np.uint16), np.ascontiguousarray(d, np.uint16)]
         self._check(self.lib.cdl_load_csc_u16(self.h, C.c_int64(N), C.c_int64(M),
                                               *[C.c_void_p(x.ctypes.data) for x in arrs]))
+
+    def set_cells_layout(self, layout):
+        """'auto' | 'rows' | 'slices': which cell kernel the Gibbs sweep uses (include/cardelino_b200.h)."""
+        self._check(self.lib.cdl_set_cells_layout(self.h, C.c_int32(CELLS_LAYOUT[layout])))
 
     def set_shard(self, cell_offset, M_total):
         self._check(self.lib.cdl_set_shard(self.h, C.c_int64(cell_offset), C.c_int64(M_total)))

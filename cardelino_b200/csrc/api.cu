@@ -71,7 +71,7 @@ struct Chain {
     DevBuf<uint32_t> mask;
     DevBuf<uint8_t> z, config_all, assign_all;
     DevBuf<unsigned long long> sab, part_u;
-    DevBuf<unsigned int> ticket;
+    DevBuf<unsigned int> ticket, work;
     DevBuf<double2> tab_g;
     // summaries
     DevBuf<double> prob_mean, config_prob, theta1_mean;
@@ -103,6 +103,8 @@ struct cdl_handle_s {
     void* comm = nullptr;
     int rank = 0, world = 1;
     int64_t launches = 0;
+    int cells_layout = CDL_CELLS_AUTO;   // cdl_set_cells_layout
+    bool use_sell = false;               // decided per run
 };
 
 namespace {
@@ -270,11 +272,12 @@ void one_sweep(cdl_handle h, Chain& ch, SweepArgs& a, uint32_t it, const cdl_rep
         a.rp_theta1 = rp_dev->theta1 ? rp_dev->theta1 + row * n_el : nullptr;
         a.rp_relax_next = (rp_dev->relax_rate && (int64_t)it < a.T) ? rp_dev->relax_rate + row + 1 : nullptr;
     }
-    launch_cells(h->donor, a, ch.dev, h->sm_count, h->st);
+    if (h->use_sell) launch_cells_sell(h->donor, a, ch.dev, h->sm_count, h->st);
+    else launch_cells(h->donor, a, ch.dev, h->sm_count, h->st);
     launch_stats(h->donor, a, ch.dev, h->sm_count, h->st);
     allreduce_u64(h, ch.dev.sab, (size_t)(a.N * a.K));
     launch_table(h->donor, a, ch.dev, h->st);
-    h->launches += 3;   // k_cells, k_stats, k_table (+ one memset node)
+    h->launches += 3;   // k_cells / k_cells_sell, k_stats, k_table (+ memset nodes)
 }
 
 double geweke_fraction(cdl_handle h, Chain& ch, int64_t n_rows, DevBuf<unsigned long long>& counts) {
@@ -479,6 +482,14 @@ int cdl_set_shard(cdl_handle h, int64_t cell_offset, int64_t M_total) {
     });
 }
 
+int cdl_set_cells_layout(cdl_handle h, int32_t layout) {
+    return guard(h, [&] {
+        if (layout != CDL_CELLS_AUTO && layout != CDL_CELLS_ROWS && layout != CDL_CELLS_SLICES)
+            throw Error(CDL_ERR_INVALID, "unknown cells layout");
+        h->cells_layout = layout;
+    });
+}
+
 int cdl_comm_unique_id(cdl_handle h, const char* nccl_lib_path, uint8_t* id128) {
     return guard(h, [&] {
         nccl_load(h, nccl_lib_path);
@@ -543,6 +554,11 @@ int cdl_gibbs_run(cdl_handle h, const double* Config, int32_t K, const double* P
         h->chains.clear();
         h->gp = gp;
         h->K = K;
+        // cell kernel: one lane per cell on the slice-major layout for large donors, row-split otherwise.
+        // The choice depends on the WHOLE donor's cell count so that it is the same on every rank.
+        h->use_sell = h->cells_layout == CDL_CELLS_SLICES ||
+                      (h->cells_layout == CDL_CELLS_AUTO && d.M_total >= 16384);
+        if (h->use_sell) donor_build_sell(h->donor, h->st);
         const int64_t N = d.N, M = d.M, T = gp.max_iter;
         const int64_t n_el = gp.wise == CDL_WISE_VARIANT ? N : 1;
         h->T = T;
@@ -623,7 +639,8 @@ int cdl_gibbs_run(cdl_handle h, const double* Config, int32_t K, const double* P
             const size_t tgrid = (size_t)((N + 255) / 256) + 1;
             ch.part_d.alloc(tgrid * 4); ch.part_u.alloc(tgrid * 8);
             ch.ticket.alloc(1); ch.ticket.zero(h->st);
-            if (cells_smem_bytes(N, K) > 200 * 1024) ch.tab_g.alloc((size_t)N);
+            ch.work.alloc(1); ch.work.zero(h->st);
+            ch.tab_g.alloc((size_t)N);
             ch.dev.scal = ch.scal.p; ch.dev.l1 = ch.l1.p; ch.dev.l1c = ch.l1c.p; ch.dev.mask = ch.mask.p;
             ch.dev.z = ch.z.p; ch.dev.sab = ch.sab.p;
             ch.dev.theta0_all = ch.theta0_all.p; ch.dev.theta1_all = ch.theta1_all.p;
@@ -634,6 +651,7 @@ int cdl_gibbs_run(cdl_handle h, const double* Config, int32_t K, const double* P
             ch.dev.prob_acc = nullptr;
             ch.dev.part_d = ch.part_d.p; ch.dev.part_u = ch.part_u.p; ch.dev.ticket = ch.ticket.p;
             ch.dev.tab_g = ch.tab_g.p;
+            ch.dev.work = ch.work.p;
 
             a.chain = (uint32_t)c;
             // initial draws (row 1)
@@ -945,7 +963,8 @@ int cdl_bench_sweeps(cdl_handle h, int32_t warmup, int32_t n, float* ms_total, f
                 a.it = it;
                 a.learn_relax_next = (a.relax && !a.relax_fixed_set && ((double)(it + 1) > 0.1 * h->gp.min_iter + 5.0)) ? 1 : 0;
                 CDL_CUDA(cudaEventRecord(ev[0], h->st));
-                launch_cells(h->donor, a, ch.dev, h->sm_count, h->st);
+                if (h->use_sell) launch_cells_sell(h->donor, a, ch.dev, h->sm_count, h->st);
+                else launch_cells(h->donor, a, ch.dev, h->sm_count, h->st);
                 CDL_CUDA(cudaEventRecord(ev[1], h->st));
                 launch_stats(h->donor, a, ch.dev, h->sm_count, h->st);
                 allreduce_u64(h, ch.dev.sab, (size_t)(a.N * a.K));

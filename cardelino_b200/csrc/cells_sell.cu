@@ -1,0 +1,422 @@
+// Slice-major cell kernel for large donors (the BASELINE C3/C4 shapes): logLik thin SpMM -> softmax ->
+// categorical draw (R/clone_id.R:470-497) with ONE LANE PER CELL.
+//
+// Layout (built once per donor from the row layout by donor_build_sell): cells are sorted by row length
+// inside windows of SELL_SIGMA cells and cut into slices of 32; slice s owns group slots
+// [slice_off[s], slice_off[s+1]) and slot g stores, for each of the 32 cells, one 8-entry group
+// (variant index, A, B as uint16) at [(g * 32 + lane)] -- so one warp-wide 128-bit load per array reads
+// 512 contiguous bytes, each lane walks its own cell, and nothing is reduced across lanes: the per-cell
+// softmax / draw epilogue costs a few warp instructions per cell instead of hundreds.
+//
+// The per-variant weights (log th1_i - log th0, log(1-th1_i) - log(1-th0)) sit in shared memory as one
+// double2 per variant.  For K <= 16 the Config_new row of the variant rides in the lowest mantissa byte
+// of each of the two doubles (clones 0-7 in the first, 8-15 in the second): one 128-bit shared load per
+// entry instead of two loads, and R2P reads the predicate bits straight from those registers.  The
+// perturbation is <= 2^-44 relative per weight (~1e-10 absolute on a logit of 500 entries), four orders
+// below the 1e-6 parity bar; the Config flips, theta draws and the logLik trace (k_table) use the exact
+// weights.
+#include "internal.h"
+#include "cells.cuh"
+#include <cub/cub.cuh>
+#include <cstdlib>
+
+namespace cdl {
+
+namespace {
+
+constexpr int SELL_THREADS = 512;
+constexpr int SELL_SIGMA = 4096;   // sorting window in cells (multiple of 32)
+
+struct SellParams {
+    CellsParams c;
+    const uint32_t* slice_off;   // [n_slices + 1] group-slot offsets
+    const uint32_t* perm;        // [n_slices * 32] local cell id of each lane, 0xffffffff = empty lane
+    const uint4* v8;
+    const uint4* a8;
+    const uint4* b8;
+    int64_t n_slices;
+    unsigned int* work;          // dynamic slice counter (zeroed before the launch)
+};
+
+// acc[k] += bit_q(bits) ? del : 0 for NK clones starting at K0.  Written as a branch around the add in
+// volatile PTX: ptxas if-converts that into a PREDICATED DADD (@P DADD) with the predicates produced seven at
+// a time by R2P -- about 1.2 instructions per clone.  (A predicated add written directly, or a ?: in C, is
+// turned into two FSELs + an unconditional DADD, and the high-word-select form needs a SEL and a register
+// move per clone.)
+template <int K0, int NK, int KP>
+__device__ __forceinline__ void masked_add8(double (&acc)[KP], double del, uint32_t bits) {
+#pragma unroll
+    for (int q = 0; q < NK; ++q) {
+        asm volatile("{\n\t.reg .pred p;\n\t.reg .b32 t;\n\t"
+                     "and.b32 t, %2, %3;\n\tsetp.eq.u32 p, t, 0;\n\t@p bra SKIP%=;\n\t"
+                     "add.f64 %0, %0, %1;\n\tSKIP%=:\n\t}"
+                     : "+d"(acc[K0 + q])
+                     : "d"(del), "r"(bits), "r"(1u << q));
+    }
+}
+
+template <int KP, typename VIdx, bool SMEM, bool PACKED>
+__device__ __forceinline__ void sell_group(double (&acc)[KP], const Grp<VIdx>& q, uint32_t tab_sa, uint32_t msk_sa,
+                                           const double2* __restrict__ tab_g, const uint32_t* __restrict__ msk_g) {
+#pragma unroll
+    for (int e = 0; e < 8; ++e) {
+        const uint32_t aw = e < 2 ? q.a.x : (e < 4 ? q.a.y : (e < 6 ? q.a.z : q.a.w));
+        const uint32_t bw = e < 2 ? q.b.x : (e < 4 ? q.b.y : (e < 6 ? q.b.z : q.b.w));
+        const uint32_t a = (e & 1) ? (aw >> 16) : (aw & 0xffffu);
+        const uint32_t b = (e & 1) ? (bw >> 16) : (bw & 0xffffu);
+        double du, dv;
+        if (PACKED) {
+            const uint32_t i = q.idx(e);
+            if (SMEM) {
+                asm volatile("ld.shared.v2.f64 {%0, %1}, [%2];" : "=d"(du), "=d"(dv) : "r"(tab_sa + (i << 4)));
+            } else {
+                const double2 t = __ldg(tab_g + i);
+                du = t.x; dv = t.y;
+            }
+            const double del = fma(u16_to_double(a), du, u16_to_double(b) * dv);
+            masked_add8<0, (KP < 8 ? KP : 8), KP>(acc, del, (uint32_t)__double2loint(du));
+            if (KP > 8) masked_add8<8, KP - 8, KP>(acc, del, (uint32_t)__double2loint(dv));
+        } else {
+            uint32_t m;
+            load_tab<SMEM>(tab_sa, msk_sa, tab_g, msk_g, q.idx(e), du, dv, m);
+            const double del = fma(u16_to_double(a), du, u16_to_double(b) * dv);
+            masked_add8<0, 8, KP>(acc, del, m);
+            masked_add8<8, 8, KP>(acc, del, m >> 8);
+            if (KP > 16) {
+                masked_add8<16, 8, KP>(acc, del, m >> 16);
+                masked_add8<24, 8, KP>(acc, del, m >> 24);
+            }
+        }
+    }
+}
+
+template <int KP, typename VIdx, bool SMEM>
+__global__ void __launch_bounds__(SELL_THREADS, 1) k_cells_sell(const SellParams P) {
+    constexpr bool PACKED = KP <= 16;
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    const CellsParams& C = P.c;
+    uint32_t tab_sa = 0, msk_sa = 0;
+    const double2* tab_g = nullptr;
+    const uint32_t* msk_g = C.mask;
+    if (SMEM) {
+        const double l0 = C.scal[SC_L0], l0c = C.scal[SC_L0C];
+        double2* s_tab = reinterpret_cast<double2*>(smem_raw);
+        uint32_t* s_msk = reinterpret_cast<uint32_t*>(smem_raw + sizeof(double2) * (size_t)C.N);
+        for (int64_t i = threadIdx.x; i < C.N; i += blockDim.x) {
+            const int64_t t = C.n_tab == 1 ? 0 : i;
+            double du = C.l1[t] - l0, dv = C.l1c[t] - l0c;
+            const uint32_t m = C.mask[i];
+            if (PACKED) {
+                du = __hiloint2double(__double2hiint(du), (__double2loint(du) & ~0xff) | (int)(m & 0xffu));
+                dv = __hiloint2double(__double2hiint(dv), (__double2loint(dv) & ~0xff) | (int)((m >> 8) & 0xffu));
+            } else {
+                s_msk[i] = m;
+            }
+            s_tab[i] = make_double2(du, dv);
+        }
+        __syncthreads();
+        tab_sa = (uint32_t)__cvta_generic_to_shared(s_tab);
+        msk_sa = (uint32_t)__cvta_generic_to_shared(s_msk);
+    } else {
+        tab_g = reinterpret_cast<const double2*>(C.l1);   // pre-built (packed when K <= 16) table in global memory
+    }
+    const int lane = threadIdx.x & 31;
+    const int K = C.K;
+    for (;;) {
+        unsigned int s_u = 0;
+        if (lane == 0) s_u = atomicAdd(P.work, 1u);
+        s_u = __shfl_sync(0xffffffffu, s_u, 0);
+        const int64_t s = s_u;
+        if (s >= P.n_slices) break;
+        const int64_t g0 = P.slice_off[s], g1 = P.slice_off[s + 1];
+        const uint32_t jl = P.perm[s * 32 + lane];
+        const bool valid = jl != 0xffffffffu;
+        double acc[KP];
+#pragma unroll
+        for (int q = 0; q < KP; ++q) acc[q] = 0.0;
+        // two group slots in flight per lane ahead of the ones being accumulated; the look-ahead index is
+        // clamped to the slice's last slot so the loads need no predicate (at most two redundant loads per slice)
+        Grp<VIdx> q0, q1;
+        if (g0 < g1) {
+            q0.load(C.vidx, P.a8, P.b8, g0 * 32 + lane);
+            q1.load(C.vidx, P.a8, P.b8, min(g0 + 1, g1 - 1) * 32 + lane);
+        }
+        for (int64_t g = g0; g < g1; g += 2) {
+            Grp<VIdx> n0, n1;
+            n0.load(C.vidx, P.a8, P.b8, min(g + 2, g1 - 1) * 32 + lane);
+            n1.load(C.vidx, P.a8, P.b8, min(g + 3, g1 - 1) * 32 + lane);
+            sell_group<KP, VIdx, SMEM, PACKED>(acc, q0, tab_sa, msk_sa, tab_g, msk_g);
+            if (g + 1 < g1) sell_group<KP, VIdx, SMEM, PACKED>(acc, q1, tab_sa, msk_sa, tab_g, msk_g);
+            q0 = n0;
+            q1 = n1;
+        }
+        // ---- softmax over the lane's own K logits (:479-481) ----
+        double mx = -INFINITY;
+#pragma unroll
+        for (int k = 0; k < KP; ++k)
+            if (k < K) { acc[k] += C.logPsi[k]; mx = fmax(mx, acc[k]); }
+        double sm = 0.0;
+#pragma unroll
+        for (int k = 0; k < KP; ++k) {
+            if (k < K) { acc[k] = exp(acc[k] - mx); sm += acc[k]; }
+            else acc[k] = 0.0;
+        }
+#pragma unroll
+        for (int k = 0; k < KP; ++k)
+            if (k < K) acc[k] = acc[k] / sm;
+        if (valid) {
+            if (C.prob_row) {
+                double* o = C.prob_row + (int64_t)jl * K;
+#pragma unroll
+                for (int k = 0; k < KP; ++k) if (k < K) o[k] = acc[k];
+            }
+            if (C.prob_acc) {
+                double* o = C.prob_acc + (int64_t)jl * K;
+#pragma unroll
+                for (int k = 0; k < KP; ++k) if (k < K) o[k] += acc[k];
+            }
+        }
+        // ---- sample(seq_len(K), 1, prob = pr): walk the DESCENDING-sorted CDF with one uniform (:493) ----
+        double u = 0.5;
+        if (valid) u = C.rp_u ? C.rp_u[jl] : philox_uniform(C.key, C.chain, C.it, STREAM_ASSIGN,
+                                                            (uint32_t)(C.cell_offset + jl));
+        uint32_t used = 0;
+        double cum = 0.0, selv = 0.0;
+        int sel = 0;
+        bool pending = valid;
+        for (int r = 0; r < K; ++r) {
+            if (!__any_sync(0xffffffffu, pending)) break;
+            double bv = -1.0;
+            int bk = 0;
+#pragma unroll
+            for (int k = 0; k < KP; ++k) {
+                const bool take = (k < K) && !((used >> k) & 1u) && (acc[k] > bv);   // ties -> lowest index
+                bv = take ? acc[k] : bv;
+                bk = take ? k : bk;
+            }
+            if (pending) {
+                used |= 1u << bk;
+                cum += bv;
+                if (u <= cum || r == K - 1) { sel = bk; selv = bv; pending = false; }
+            }
+        }
+        // the order inside a group of exactly tied probabilities is revsort's; it only matters when the
+        // walk stops inside such a group (e.g. cells without any covered variant: all K tie)
+        int ntie = 0;
+#pragma unroll
+        for (int k = 0; k < KP; ++k) ntie += (k < K && acc[k] == selv) ? 1 : 0;
+        if (valid && ntie > 1 && selv > 0.0) {
+            double pa[KP];
+            int perm[KP];
+#pragma unroll
+            for (int k = 0; k < KP; ++k) { pa[k] = acc[k]; perm[k] = k; }
+            double tot = 0.0;
+            for (int l = 0; l < K; ++l) tot += pa[l];
+            for (int l = 0; l < K; ++l) pa[l] /= tot;
+            revsort_dev(pa, perm, K);
+            for (int l = 1; l < K; ++l) pa[l] += pa[l - 1];
+            int jj = 0;
+            while (jj < K - 1 && !(u <= pa[jj])) ++jj;
+            sel = perm[jj];
+        }
+        if (valid) {
+            C.z[jl] = (uint8_t)sel;
+            if (C.assign_row) C.assign_row[jl] = (uint8_t)(sel + 1);
+        }
+    }
+}
+
+// (du, dv) table in global memory for donors whose table does not fit shared memory; packed like the
+// shared-memory one when K <= 16
+__global__ void k_build_tab_sell(int64_t N, int n_tab, int packed, const double* __restrict__ l1,
+                                 const double* __restrict__ l1c, const double* __restrict__ scal,
+                                 const uint32_t* __restrict__ mask, double2* __restrict__ out) {
+    int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+    if (i >= N) return;
+    const int64_t t = n_tab == 1 ? 0 : i;
+    double du = l1[t] - scal[SC_L0], dv = l1c[t] - scal[SC_L0C];
+    if (packed) {
+        const uint32_t m = mask[i];
+        du = __hiloint2double(__double2hiint(du), (__double2loint(du) & ~0xff) | (int)(m & 0xffu));
+        dv = __hiloint2double(__double2hiint(dv), (__double2loint(dv) & ~0xff) | (int)((m >> 8) & 0xffu));
+    }
+    out[i] = make_double2(du, dv);
+}
+
+// ---- layout construction --------------------------------------------------------------------------
+__global__ void k_sell_keys(const uint32_t* __restrict__ rowgrp, int64_t M, int64_t slots,
+                            uint64_t* __restrict__ keys, uint32_t* __restrict__ vals) {
+    const int64_t j = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+    if (j >= slots) return;
+    const uint32_t len = j < M ? rowgrp[j + 1] - rowgrp[j] : 0u;
+    keys[j] = ((uint64_t)(j / SELL_SIGMA) << 32) | (uint64_t)(0xffffffffu - len);   // window asc, length desc
+    vals[j] = j < M ? (uint32_t)j : 0xffffffffu;
+}
+
+__global__ void k_sell_slice_len(const uint32_t* __restrict__ rowgrp, const uint32_t* __restrict__ perm,
+                                 int64_t n_slices, uint32_t* __restrict__ len) {
+    const int lane = threadIdx.x & 31;
+    const int64_t s = (blockIdx.x * (int64_t)blockDim.x + threadIdx.x) >> 5;
+    if (s > n_slices) return;
+    uint32_t l = 0;
+    if (s < n_slices) {
+        const uint32_t j = perm[s * 32 + lane];
+        if (j != 0xffffffffu) l = rowgrp[j + 1] - rowgrp[j];
+    }
+    l = __reduce_max_sync(0xffffffffu, l);
+    if (lane == 0) len[s] = l;      // len[n_slices] = 0 closes the scan
+}
+
+template <typename VIdx>
+__global__ void k_sell_fill(const uint32_t* __restrict__ rowgrp, const uint32_t* __restrict__ perm,
+                            const uint32_t* __restrict__ slice_off, int64_t n_slices, const uint4* __restrict__ cv,
+                            const uint4* __restrict__ ca, const uint4* __restrict__ cb, uint4* __restrict__ ov,
+                            uint4* __restrict__ oa, uint4* __restrict__ ob) {
+    constexpr int VW = sizeof(VIdx) / 2;   // uint4 words per group of variant indices
+    const int lane = threadIdx.x & 31;
+    const int64_t warp = (blockIdx.x * (int64_t)blockDim.x + threadIdx.x) >> 5;
+    const int64_t nwarps = ((int64_t)gridDim.x * blockDim.x) >> 5;
+    const uint4 zero4 = make_uint4(0, 0, 0, 0);
+    for (int64_t s = warp; s < n_slices; s += nwarps) {
+        const int64_t o0 = slice_off[s], o1 = slice_off[s + 1];
+        const uint32_t j = perm[s * 32 + lane];
+        int64_t r0 = 0, r1 = 0;
+        if (j != 0xffffffffu) { r0 = rowgrp[j]; r1 = rowgrp[j + 1]; }
+        for (int64_t g = 0; g < o1 - o0; ++g) {
+            const bool have = r0 + g < r1;
+            const int64_t dst = (o0 + g) * 32 + lane;
+            oa[dst] = have ? ca[r0 + g] : zero4;
+            ob[dst] = have ? cb[r0 + g] : zero4;
+#pragma unroll
+            for (int w = 0; w < VW; ++w) ov[dst * VW + w] = have ? cv[(r0 + g) * VW + w] : zero4;
+        }
+    }
+}
+
+template <int KP, typename VIdx>
+void launch_sell_t(const SellParams& P, bool smem_tab, size_t smem, int grid, cudaStream_t st) {
+    if (smem_tab) {
+        auto kern = k_cells_sell<KP, VIdx, true>;
+        CDL_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        kern<<<grid, SELL_THREADS, smem, st>>>(P);
+    } else {
+        k_cells_sell<KP, VIdx, false><<<grid, SELL_THREADS, 0, st>>>(P);
+    }
+}
+
+template <int KP>
+void launch_sell_v(const Donor& d, const SellParams& P, bool smem_tab, size_t smem, int grid, cudaStream_t st) {
+    if (d.vidx32) launch_sell_t<KP, uint32_t>(P, smem_tab, smem, grid, st);
+    else launch_sell_t<KP, uint16_t>(P, smem_tab, smem, grid, st);
+}
+
+}  // namespace
+
+void donor_free_sell(Donor& d) {
+    cudaFree(d.s_off); cudaFree(d.s_perm); cudaFree(d.s_vidx); cudaFree(d.s_a); cudaFree(d.s_b);
+    d.s_off = nullptr; d.s_perm = nullptr; d.s_vidx = nullptr; d.s_a = nullptr; d.s_b = nullptr;
+    d.s_slices = 0; d.s_slots = 0;
+}
+
+// Build the slice-major copy from the row layout (padding groups there are already (variant 0, 0, 0)).
+void donor_build_sell(Donor& d, cudaStream_t st) {
+    if (d.s_off) return;
+    const int64_t M = d.M;
+    const int64_t n_slices = (M + 31) / 32, slots = n_slices * 32;
+    uint64_t *keys = nullptr, *keys2 = nullptr;
+    uint32_t *vals = nullptr, *len = nullptr;
+    void* tmp = nullptr;
+    auto cleanup = [&]() { cudaFree(keys); cudaFree(keys2); cudaFree(vals); cudaFree(tmp); };
+    try {
+        CDL_CUDA(cudaMalloc(&keys, 8 * (size_t)slots));
+        CDL_CUDA(cudaMalloc(&keys2, 8 * (size_t)slots));
+        CDL_CUDA(cudaMalloc(&vals, 4 * (size_t)slots));
+        CDL_CUDA(cudaMalloc(&d.s_perm, 4 * (size_t)slots));
+        const int threads = 256;
+        k_sell_keys<<<(unsigned)((slots + threads - 1) / threads), threads, 0, st>>>(d.c_rowgrp, M, slots, keys, vals);
+        CDL_CUDA(cudaGetLastError());
+        size_t tmp_bytes = 0;
+        CDL_CUDA(cub::DeviceRadixSort::SortPairs(nullptr, tmp_bytes, keys, keys2, vals, d.s_perm, (int)slots, 0, 64, st));
+        CDL_CUDA(cudaMalloc(&tmp, tmp_bytes ? tmp_bytes : 1));
+        CDL_CUDA(cub::DeviceRadixSort::SortPairs(tmp, tmp_bytes, keys, keys2, vals, d.s_perm, (int)slots, 0, 64, st));
+        CDL_CUDA(cudaMalloc(&d.s_off, 4 * (size_t)(n_slices + 1)));
+        len = d.s_off;
+        k_sell_slice_len<<<(unsigned)(((n_slices + 1) * 32 + threads - 1) / threads), threads, 0, st>>>(
+            d.c_rowgrp, d.s_perm, n_slices, len);
+        CDL_CUDA(cudaGetLastError());
+        cudaFree(tmp); tmp = nullptr;
+        tmp_bytes = 0;
+        CDL_CUDA(cub::DeviceScan::ExclusiveSum(nullptr, tmp_bytes, len, len, (int)(n_slices + 1), st));
+        CDL_CUDA(cudaMalloc(&tmp, tmp_bytes ? tmp_bytes : 1));
+        CDL_CUDA(cub::DeviceScan::ExclusiveSum(tmp, tmp_bytes, len, len, (int)(n_slices + 1), st));
+        uint32_t total = 0;
+        CDL_CUDA(cudaMemcpyAsync(&total, d.s_off + n_slices, 4, cudaMemcpyDeviceToHost, st));
+        CDL_CUDA(cudaStreamSynchronize(st));
+        const size_t words = (size_t)std::max<int64_t>((int64_t)total * 32, 1);
+        const int vw = d.vidx32 ? 2 : 1;
+        CDL_CUDA(cudaMalloc(&d.s_vidx, 16 * words * vw));
+        CDL_CUDA(cudaMalloc(&d.s_a, 16 * words));
+        CDL_CUDA(cudaMalloc(&d.s_b, 16 * words));
+        const unsigned blocks = (unsigned)std::min<int64_t>((n_slices * 32 + threads - 1) / threads, 148 * 16);
+        if (d.vidx32)
+            k_sell_fill<uint32_t><<<blocks, threads, 0, st>>>(d.c_rowgrp, d.s_perm, d.s_off, n_slices,
+                (const uint4*)d.c_vidx, (const uint4*)d.c_a, (const uint4*)d.c_b, (uint4*)d.s_vidx, (uint4*)d.s_a, (uint4*)d.s_b);
+        else
+            k_sell_fill<uint16_t><<<blocks, threads, 0, st>>>(d.c_rowgrp, d.s_perm, d.s_off, n_slices,
+                (const uint4*)d.c_vidx, (const uint4*)d.c_a, (const uint4*)d.c_b, (uint4*)d.s_vidx, (uint4*)d.s_a, (uint4*)d.s_b);
+        CDL_CUDA(cudaGetLastError());
+        CDL_CUDA(cudaStreamSynchronize(st));
+        d.s_slices = n_slices;
+        d.s_slots = total;
+    } catch (...) {
+        cleanup();
+        donor_free_sell(d);
+        throw;
+    }
+    cleanup();
+}
+
+void launch_cells_sell(const Donor& d, const SweepArgs& a, ChainDev& c, int sm_count, cudaStream_t st) {
+    SellParams P{};
+    CellsParams& C = P.c;
+    C.rowgrp = nullptr; C.vidx = d.s_vidx; C.ca = nullptr; C.cb = nullptr;
+    C.M = d.M; C.N = d.N; C.cell_offset = d.cell_offset; C.K = a.K;
+    C.n_tab = a.wise == 1 ? (int)a.N : 1;
+    C.l1 = c.l1; C.l1c = c.l1c; C.scal = c.scal; C.mask = c.mask;
+    for (int k = 0; k < KMAX; ++k) C.logPsi[k] = a.logPsi[k];
+    const int64_t row = (int64_t)a.it - 1;
+    C.prob_row = c.prob_all ? c.prob_all + row * d.M * a.K : nullptr;
+    C.prob_acc = c.prob_acc;
+    C.z = c.z;
+    C.assign_row = c.assign_all ? c.assign_all + row * d.M : nullptr;
+    C.rp_u = a.rp_u_assign;
+    C.key = a.key; C.chain = a.chain; C.it = a.it;
+    P.slice_off = d.s_off; P.perm = d.s_perm;
+    P.v8 = nullptr; P.a8 = (const uint4*)d.s_a; P.b8 = (const uint4*)d.s_b;
+    P.n_slices = d.s_slices;
+    P.work = c.work;
+    const int KP = a.K <= 4 ? 4 : (a.K <= 8 ? 8 : (a.K <= 16 ? 16 : 32));
+    const bool packed = KP <= 16;
+    const size_t smem = (size_t)d.N * (sizeof(double2) + (packed ? 0 : sizeof(uint32_t)));
+    const bool smem_tab = smem <= 216 * 1024;
+    C.tab_in_smem = smem_tab;
+    CDL_CUDA(cudaMemsetAsync(c.work, 0, sizeof(unsigned int), st));
+    if (!smem_tab) {
+        if (!c.tab_g) throw Error(4, "global weight table not allocated");
+        k_build_tab_sell<<<(unsigned)((d.N + 255) / 256), 256, 0, st>>>(d.N, C.n_tab, packed ? 1 : 0, c.l1, c.l1c,
+                                                                         c.scal, c.mask, c.tab_g);
+        C.l1 = reinterpret_cast<const double*>(c.tab_g);
+    }
+    int64_t grid = sm_count;
+    const int64_t max_useful = (d.s_slices + SELL_THREADS / 32 - 1) / (SELL_THREADS / 32);
+    if (grid > max_useful) grid = std::max<int64_t>(max_useful, 1);
+    switch (KP) {
+        case 4: launch_sell_v<4>(d, P, smem_tab, smem, (int)grid, st); break;
+        case 8: launch_sell_v<8>(d, P, smem_tab, smem, (int)grid, st); break;
+        case 16: launch_sell_v<16>(d, P, smem_tab, smem, (int)grid, st); break;
+        default: launch_sell_v<32>(d, P, smem_tab, smem, (int)grid, st); break;
+    }
+    CDL_CUDA(cudaGetLastError());
+}
+
+}  // namespace cdl

@@ -48,6 +48,14 @@ struct Donor {
     uint16_t* v_a = nullptr;
     uint16_t* v_b = nullptr;
     int64_t v_groups = 0;
+    //  (C) slice-major copy of (A) for large donors (cells_sell.cu): slices of 32 length-sorted cells,
+    //      one lane per cell; built lazily by donor_build_sell.
+    uint32_t* s_off = nullptr;          // [s_slices + 1] group-slot offsets
+    uint32_t* s_perm = nullptr;         // [s_slices * 32] local cell id per lane (0xffffffff = empty)
+    void* s_vidx = nullptr;
+    uint16_t* s_a = nullptr;
+    uint16_t* s_b = nullptr;
+    int64_t s_slices = 0, s_slots = 0;
     double W_log = 0.0;                 // local shard's sum(lchoose(D, A))
     int32_t* labels = nullptr;          // synthetic ground truth (1-based), optional
     uint64_t max_variant_depth = 0;     // max_i sum_j D_ij (must stay < 2^32 for packed statistics)
@@ -55,6 +63,8 @@ struct Donor {
 };
 
 void donor_free(Donor& d);
+void donor_free_sell(Donor& d);
+void donor_build_sell(Donor& d, cudaStream_t st);
 // raw CSC (cells = columns) already on the device -> both layouts.  Frees nothing of the input.
 void donor_build(Donor& d, int64_t N, int64_t M, int64_t nnz, const int64_t* p_dev, const int32_t* i_dev,
                  const uint16_t* a_dev, const uint16_t* d_dev, cudaStream_t st);
@@ -85,6 +95,7 @@ struct ChainDev {
     unsigned long long* part_u; // [grid * 8]
     unsigned int* ticket;
     double2* tab_g;      // (du, dv) table in global memory when it does not fit shared memory, else nullptr
+    unsigned int* work;  // dynamic slice counter of k_cells_sell
 };
 
 enum {
@@ -117,6 +128,7 @@ struct KernelTimes { float cells = 0, stats = 0, table = 0; };
 int cells_smem_bytes(int64_t N, int K);
 void launch_init_chain(const SweepArgs& a, ChainDev& c, cudaStream_t st);
 void launch_cells(const Donor& d, const SweepArgs& a, ChainDev& c, int sm_count, cudaStream_t st);
+void launch_cells_sell(const Donor& d, const SweepArgs& a, ChainDev& c, int sm_count, cudaStream_t st);
 void launch_stats(const Donor& d, const SweepArgs& a, ChainDev& c, int sm_count, cudaStream_t st);
 void launch_table(const Donor& d, const SweepArgs& a, ChainDev& c, cudaStream_t st);
 

@@ -126,6 +126,12 @@ int cdl_data_info(cdl_handle h, int64_t* N, int64_t* M, int64_t* nnz, double* W_
  * number of ranks.  Call after cdl_load_*. */
 int cdl_set_shard(cdl_handle h, int64_t cell_offset, int64_t M_total);
 
+/* Which cell kernel the Gibbs sweep uses: ROWS = several lanes per cell on the row layout (small donors),
+ * SLICES = one lane per cell on the slice-major layout (large donors), AUTO = SLICES when the whole donor
+ * has >= 16384 cells.  Results agree to rounding (the per-cell summation order differs). */
+enum { CDL_CELLS_AUTO = 0, CDL_CELLS_ROWS = 1, CDL_CELLS_SLICES = 2 };
+int cdl_set_cells_layout(cdl_handle h, int32_t layout);
+
 /* ---- multi-GPU (cells sharded over ranks; one all-reduce of the N x K statistic table per sweep) ----
  * nccl_lib_path: libnccl.so.2 to dlopen (the host passes torch's bundled copy); unique_id: the 128-byte
  * ncclUniqueId broadcast by the host plumbing.  cdl_comm_unique_id fills it on rank 0. */

@@ -123,6 +123,57 @@ def test_gibbs_c2_four_chains(gpu_handle, c2_donor):
     assert (merged["prob"].argmax(1) + 1 == lab).mean() > 0.8
 
 
+@pytest.fixture()
+def slices_handle(gpu_handle):
+    """The session handle forced onto the slice-major cell kernel (one lane per cell), restored afterwards."""
+    gpu_handle.set_cells_layout("slices")
+    yield gpu_handle
+    gpu_handle.set_cells_layout("auto")
+
+
+@pytest.mark.parametrize("K", [0, 2, 3, 6, 12, 20])
+def test_slice_kernel_stepwise(slices_handle, example_donor, K):
+    """k_cells_sell against the oracle sweep by sweep: the reference test's configuration (K = 0 -> tree$Z)
+    and de-novo runs over every padded clone width (packed masks for K <= 16, separate mask table for
+    K > 16), including the exact-tie path (19 uncovered cells tie on all clones) and ragged slices
+    (428 cells = 13 full slices + one of 12 lanes, rows of 0-12 entries)."""
+    A, D, Z = example_donor
+    if K == 0:
+        _verify(_cb(), slices_handle, A, D, Z, T=60)
+        _verify(_cb(), slices_handle, A, D, Z, T=30, wise="global", relax_rate_fixed=0.3,
+                Psi=np.array([0.1, 0.2, 0.3, 0.4]))
+    else:
+        _verify(_cb(), slices_handle, A, D, np.zeros((34, K)), T=30, relax_rate_fixed=0.5)
+
+
+def test_slice_kernel_c2_and_wide_index(slices_handle, c2_donor):
+    A, D, Z, lab = c2_donor
+    _verify(_cb(), slices_handle, A, D, Z, T=30, seed=5)
+    test_many_variants_uint32_index_and_global_table(slices_handle)
+
+
+def test_slice_kernel_equals_row_kernel_at_full_size(gpu_handle):
+    """C3 shape: both cell kernels see the same state (teacher-forced by running one sweep from the same
+    seed) and must agree on every probability to rounding and on (nearly) every label."""
+    import bench
+    N, M, K, cov = bench.WORKLOADS["C3"]
+    cfg = bench.make_config(N, K)
+    h = gpu_handle
+    h.synth_generate(N, M, K, cfg, cov, 78)
+    out = {}
+    for layout in ("rows", "slices"):
+        h.set_cells_layout(layout)
+        h.gibbs_run(cfg, None, min_iter=3, max_iter=3, seed=6, keep_prob_all=1, keep_assign_all=1)
+        out[layout] = (h.fetch("prob_all"), h.fetch("assign_all"), h.fetch("logLik"))
+    h.set_cells_layout("auto")
+    pr, zr, lr = out["rows"]
+    ps, zs, ls = out["slices"]
+    assert np.abs(pr[1] - ps[1]).max() <= 1e-9           # sweep 2 starts from identical state
+    assert (zr[1] != zs[1]).mean() <= 1e-5
+    if np.array_equal(zr[1], zs[1]):
+        assert np.abs(pr[2] - ps[2]).max() <= 1e-9 and abs(lr[2] - ls[2]) <= 1e-9 * abs(lr[2])
+
+
 def test_replay_mode(gpu_handle, example_donor):
     """Correctness check 2 of the north star: inject a recorded run's uniforms and theta draws; the
     assignments and Config flips must be reproduced."""
