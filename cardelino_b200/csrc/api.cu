@@ -639,7 +639,7 @@ int cdl_gibbs_run(cdl_handle h, const double* Config, int32_t K, const double* P
             const size_t tgrid = (size_t)((N + 255) / 256) + 1;
             ch.part_d.alloc(tgrid * 4); ch.part_u.alloc(tgrid * 8);
             ch.ticket.alloc(1); ch.ticket.zero(h->st);
-            ch.work.alloc(1); ch.work.zero(h->st);
+            ch.work.alloc(2); ch.work.zero(h->st);
             ch.tab_g.alloc((size_t)N);
             ch.dev.scal = ch.scal.p; ch.dev.l1 = ch.l1.p; ch.dev.l1c = ch.l1c.p; ch.dev.mask = ch.mask.p;
             ch.dev.z = ch.z.p; ch.dev.sab = ch.sab.p;

@@ -74,8 +74,12 @@ __device__ __forceinline__ void sell_group(double (&acc)[KP], const Grp<VIdx>& q
                 du = t.x; dv = t.y;
             }
             const double del = fma(u16_to_double(a), du, u16_to_double(b) * dv);
-            masked_add8<0, (KP < 8 ? KP : 8), KP>(acc, del, (uint32_t)__double2loint(du));
-            if (KP > 8) masked_add8<8, KP - 8, KP>(acc, del, (uint32_t)__double2loint(dv));
+            // gather the two mask bytes into ONE integer register first: ptxas then turns the bit tests into
+            // R2P (seven predicates per instruction); testing the low words of du / dv in place makes it
+            // emit one LOP3 per clone instead
+            const uint32_t m = __byte_perm((uint32_t)__double2loint(du), (uint32_t)__double2loint(dv), 0x7740);
+            masked_add8<0, (KP < 8 ? KP : 8), KP>(acc, del, m);
+            if (KP > 8) masked_add8<8, KP - 8, KP>(acc, del, m >> 8);
         } else {
             uint32_t m;
             load_tab<SMEM>(tab_sa, msk_sa, tab_g, msk_g, q.idx(e), du, dv, m);

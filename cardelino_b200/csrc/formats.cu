@@ -57,8 +57,9 @@ __global__ void k_fill_cells(const int64_t* __restrict__ p, const int32_t* __res
     }
 }
 
-__global__ void k_seg_count(const int64_t* __restrict__ p, const int32_t* __restrict__ vi, int64_t M,
-                            int64_t N, uint32_t* __restrict__ cnt) {
+__global__ void k_seg_count(const int64_t* __restrict__ p, const int32_t* __restrict__ vi,
+                            const uint16_t* __restrict__ dd, int64_t M, int64_t N, uint32_t* __restrict__ cnt,
+                            uint32_t* __restrict__ maxdepth) {
     const int lane = threadIdx.x & 31;
     const int64_t warp = (blockIdx.x * (int64_t)blockDim.x + threadIdx.x) >> 5;
     const int64_t nwarps = ((int64_t)gridDim.x * blockDim.x) >> 5;
@@ -67,14 +68,25 @@ __global__ void k_seg_count(const int64_t* __restrict__ p, const int32_t* __rest
         const int64_t cb = j / CELL_BLOCK;
         for (int64_t e = e0 + lane; e < e1; e += 32) {
             const int32_t i = vi[e];
-            if (i >= 0 && i < N) atomicAdd(&cnt[cb * N + i], 1u);
+            if (i >= 0 && i < N) {
+                atomicAdd(&cnt[cb * N + i], 1u);
+                atomicMax(&maxdepth[cb * N + i], (uint32_t)dd[e]);
+            }
         }
     }
 }
 
-__global__ void k_to_groups(uint32_t* __restrict__ cnt, int64_t n) {
+__global__ void k_to_groups(uint32_t* __restrict__ cnt, int64_t n, const uint32_t* __restrict__ maxdepth,
+                            uint16_t* __restrict__ flush) {
     int64_t s = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
-    if (s < n) cnt[s] = (cnt[s] + GROUP - 1) / GROUP;
+    if (s < n) {
+        cnt[s] = (cnt[s] + GROUP - 1) / GROUP;
+        // k_stats keeps 16 + 16 bit packed bins per lane: a lane may add this many 8-entry groups before
+        // either half could overflow (0 = even one group could: that segment takes the 64-bit path)
+        const uint32_t md = maxdepth[s] ? maxdepth[s] : 1u;
+        const uint32_t f = 65535u / (GROUP * md);
+        flush[s] = (uint16_t)(f > 65535u ? 65535u : f);
+    }
     if (s == n) cnt[s] = 0;
 }
 
@@ -144,7 +156,7 @@ double sum_doubles(const double* data, int64_t n, cudaStream_t st) {
 void donor_free(Donor& d) {
     donor_free_sell(d);
     cudaFree(d.c_rowgrp); cudaFree(d.c_vidx); cudaFree(d.c_a); cudaFree(d.c_b);
-    cudaFree(d.v_seggrp); cudaFree(d.v_cell); cudaFree(d.v_a); cudaFree(d.v_b);
+    cudaFree(d.v_seggrp); cudaFree(d.v_flush); cudaFree(d.v_cell); cudaFree(d.v_a); cudaFree(d.v_b);
     cudaFree(d.labels);
     d = Donor();
 }
@@ -225,8 +237,12 @@ void donor_build(Donor& d, int64_t N, int64_t M, int64_t nnz, const int64_t* p, 
     uint32_t* cursor = dalloc<uint32_t>(nseg + 1);
     CDL_CUDA(cudaMemsetAsync(d.v_seggrp, 0, 4 * (size_t)(nseg + 1), st));
     CDL_CUDA(cudaMemsetAsync(cursor, 0, 4 * (size_t)(nseg + 1), st));
-    k_seg_count<<<blocks, threads, 0, st>>>(p, vi, M, N, d.v_seggrp);
-    k_to_groups<<<(unsigned)((nseg + 1 + threads - 1) / threads), threads, 0, st>>>(d.v_seggrp, nseg);
+    uint32_t* segdepth = dalloc<uint32_t>(nseg + 1);
+    CDL_CUDA(cudaMemsetAsync(segdepth, 0, 4 * (size_t)(nseg + 1), st));
+    d.v_flush = dalloc<uint16_t>(nseg + 1);
+    k_seg_count<<<blocks, threads, 0, st>>>(p, vi, dd, M, N, d.v_seggrp, segdepth);
+    k_to_groups<<<(unsigned)((nseg + 1 + threads - 1) / threads), threads, 0, st>>>(d.v_seggrp, nseg, segdepth,
+                                                                                      d.v_flush);
     exclusive_scan_u32(d.v_seggrp, nseg + 1, st);
     uint32_t vg = 0;
     CDL_CUDA(cudaMemcpyAsync(&vg, d.v_seggrp + nseg, 4, cudaMemcpyDeviceToHost, st));
@@ -243,6 +259,7 @@ void donor_build(Donor& d, int64_t N, int64_t M, int64_t nnz, const int64_t* p, 
     CDL_CUDA(cudaGetLastError());
     CDL_CUDA(cudaStreamSynchronize(st));
     cudaFree(cursor);
+    cudaFree(segdepth);
 }
 
 namespace {

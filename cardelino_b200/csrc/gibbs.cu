@@ -20,7 +20,7 @@ namespace cdl {
 namespace {
 
 constexpr int CELLS_THREADS = 512;
-constexpr int STATS_THREADS = 256;
+constexpr int STATS_THREADS = 512;
 constexpr int STATS_WARPS = STATS_THREADS / 32;
 constexpr int TABLE_THREADS = 256;
 
@@ -205,6 +205,7 @@ __global__ void k_build_tab(int64_t N, int n_tab, const double* __restrict__ l1,
 // ------------------------------------------------------------------------------------------------
 struct StatsParams {
     const uint32_t* seggrp;
+    const uint16_t* flush;
     const uint16_t* vc;
     const uint16_t* va;
     const uint16_t* vb;
@@ -212,83 +213,142 @@ struct StatsParams {
     unsigned long long* sab;
     int64_t N, M;
     int K;
-    int chunk;      // variants per CTA
+    int chunk;            // variants per work unit
+    int chunks_per_cb;    // units per cell block
+    int n_units;
+    unsigned int* work;   // dynamic unit counter (zeroed before the launch)
 };
 
-template <int KP>
-__global__ void __launch_bounds__(STATS_THREADS) k_stats(const StatsParams P) {
-    extern __shared__ __align__(16) unsigned char smem_raw[];
-    uint2* s_bins = reinterpret_cast<uint2*>(smem_raw);                    // [WARPS][KP][32]
-    uint8_t* s_z = smem_raw + sizeof(uint2) * STATS_WARPS * KP * 32;       // [cells of this block]
-    const int cb = blockIdx.y;
-    const int64_t c0 = (int64_t)cb * CELL_BLOCK;
-    const int ncell = (int)min((int64_t)CELL_BLOCK, P.M - c0);
-    {
-        const int nvec = ncell >> 4;
-        const uint4* src = reinterpret_cast<const uint4*>(P.z + c0);
-        uint4* dst = reinterpret_cast<uint4*>(s_z);
-        for (int t = threadIdx.x; t < nvec; t += blockDim.x) dst[t] = src[t];
-        for (int t = (nvec << 4) + threadIdx.x; t < ncell; t += blockDim.x) s_z[t] = P.z[c0 + t];
+// One 8-entry group of a variant segment into the lane-private clone bins.  A and B share one 32-bit bin
+// (A low half, B high half): one 32-bit shared load + store per entry.  The caller flushes the bins before
+// either half can overflow (Donor::v_flush).
+__device__ __forceinline__ void stats_group(const uint4 cw, const uint4 aw, const uint4 bw,
+                                            const uint8_t* __restrict__ s_z, uint32_t* __restrict__ bins_lane) {
+    const uint32_t cc[4] = {cw.x, cw.y, cw.z, cw.w};
+    const uint32_t aa[4] = {aw.x, aw.y, aw.z, aw.w};
+    const uint32_t bb[4] = {bw.x, bw.y, bw.z, bw.w};
+    uint32_t zz[8];
+#pragma unroll
+    for (int e = 0; e < 8; ++e) {
+        const uint32_t c = (e & 1) ? (cc[e >> 1] >> 16) : (cc[e >> 1] & 0xffffu);
+        zz[e] = s_z[c];
     }
-    __syncthreads();
+#pragma unroll
+    for (int e = 0; e < 8; ++e) {
+        const uint32_t ab = __byte_perm(aa[e >> 1], bb[e >> 1], (e & 1) ? 0x7632 : 0x5410);   // a | b << 16
+        bins_lane[zz[e] * 32] += ab;
+    }
+}
+
+// column sums of the lane-private packed bins -> global table, then clear the bins
+template <int KP>
+__device__ __forceinline__ void stats_flush(uint32_t* __restrict__ bins, int lane, int K,
+                                            unsigned long long* __restrict__ sab_row) {
+    __syncwarp();
+    // lane handles clone kk = lane % KP over a KP-wide slice of lanes, rotated so that the lanes of a
+    // wavefront touch distinct banks
+    const int kk = lane & (KP - 1);
+    const int h = lane / KP;                 // 0 .. 32/KP-1
+    unsigned long long sa = 0, sb = 0;
+#pragma unroll
+    for (int s = 0; s < KP; ++s) {
+        const int t = h * KP + ((s + kk) & (KP - 1));
+        const uint32_t v = bins[kk * 32 + t];
+        sa += v & 0xffffu;
+        sb += v >> 16;
+    }
+#pragma unroll
+    for (int off = KP; off < 32; off <<= 1) {
+        sa += __shfl_xor_sync(0xffffffffu, sa, off);
+        sb += __shfl_xor_sync(0xffffffffu, sb, off);
+    }
+    if (lane < K && (sa | sb)) atomicAdd(&sab_row[lane], sa | (sb << 32));
+    __syncwarp();
+#pragma unroll
+    for (int q = 0; q < KP; ++q) bins[q * 32 + lane] = 0u;
+    __syncwarp();
+}
+
+// Persistent CTAs pull (cell block, variant chunk) units from a counter, in cell-block-major order so the
+// block's labels are re-staged in shared memory only when the cell block changes.  Inside a unit each warp
+// owns whole variant segments; a lane keeps private per-clone bins in shared memory, so no atomics are
+// needed until the segment's K sums go to the global table.  The kernel is bound by the latency of the
+// shared-memory update chain as much as by HBM, so it runs 32 warps per SM (2 CTAs x 16 warps, <= 64
+// registers) with one group per lane prefetched ahead of the updates.
+template <int KP>
+__global__ void __launch_bounds__(STATS_THREADS, 2) k_stats(const StatsParams P) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    uint32_t* s_bins = reinterpret_cast<uint32_t*>(smem_raw);                  // [WARPS][KP][32]
+    uint8_t* s_z = smem_raw + sizeof(uint32_t) * STATS_WARPS * KP * 32;        // [cells of the staged block]
+    __shared__ unsigned int s_unit;
     const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
-    uint2* bins = s_bins + (size_t)w * KP * 32;
-    const int64_t i_lo = (int64_t)blockIdx.x * P.chunk;
-    const int64_t i_hi = min(P.N, i_lo + P.chunk);
+    uint32_t* bins = s_bins + (size_t)w * KP * 32;
     const uint4* c8 = reinterpret_cast<const uint4*>(P.vc);
     const uint4* a8 = reinterpret_cast<const uint4*>(P.va);
     const uint4* b8 = reinterpret_cast<const uint4*>(P.vb);
-    for (int64_t i = i_lo + w; i < i_hi; i += STATS_WARPS) {
-        const int64_t seg = (int64_t)cb * P.N + i;
-        const int64_t g0 = P.seggrp[seg], g1 = P.seggrp[seg + 1];
-        if (g0 == g1) continue;
 #pragma unroll
-        for (int q = 0; q < KP; ++q) bins[q * 32 + lane] = make_uint2(0u, 0u);
-        for (int64_t g = g0 + lane; g < g1; g += 64) {
-            const bool two = (g + 32) < g1;
-            uint4 cw[2], aw[2], bw[2];
-            cw[0] = ld_stream(c8 + g); aw[0] = ld_stream(a8 + g); bw[0] = ld_stream(b8 + g);
-            if (two) { cw[1] = ld_stream(c8 + g + 32); aw[1] = ld_stream(a8 + g + 32); bw[1] = ld_stream(b8 + g + 32); }
+    for (int q = 0; q < KP; ++q) bins[q * 32 + lane] = 0u;
+    int staged_cb = -1;
+    for (;;) {
+        __syncthreads();                       // everyone is done with the previous unit (and with s_unit)
+        if (threadIdx.x == 0) s_unit = atomicAdd(P.work, 1u);
+        __syncthreads();
+        const unsigned int u = s_unit;
+        if (u >= (unsigned int)P.n_units) break;
+        const int cb = (int)(u / (unsigned int)P.chunks_per_cb);
+        const int ch = (int)(u - (unsigned int)cb * (unsigned int)P.chunks_per_cb);
+        if (cb != staged_cb) {
+            const int64_t c0 = (int64_t)cb * CELL_BLOCK;
+            const int ncell = (int)min((int64_t)CELL_BLOCK, P.M - c0);
+            const int nvec = ncell >> 4;
+            const uint4* src = reinterpret_cast<const uint4*>(P.z + c0);
+            uint4* dst = reinterpret_cast<uint4*>(s_z);
+            for (int t = threadIdx.x; t < nvec; t += blockDim.x) dst[t] = src[t];
+            for (int t = (nvec << 4) + threadIdx.x; t < ncell; t += blockDim.x) s_z[t] = P.z[c0 + t];
+            staged_cb = cb;
+            __syncthreads();
+        }
+        const int64_t i_lo = (int64_t)ch * P.chunk;
+        const int64_t i_hi = min(P.N, i_lo + P.chunk);
+        for (int64_t i = i_lo + w; i < i_hi; i += STATS_WARPS) {
+            const int64_t seg = (int64_t)cb * P.N + i;
+            const int64_t g0 = P.seggrp[seg], g1 = P.seggrp[seg + 1];
+            if (g0 == g1) continue;
+            const int flush_every = P.flush[seg];
+            unsigned long long* sab_row = P.sab + i * P.K;
+            if (flush_every == 0) {
+                // depths above 8191 in this segment: a single group could overflow a 16-bit half; take the
+                // (rare) direct path, one 64-bit atomic per entry
+                for (int64_t g = g0 + lane; g < g1; g += 32) {
+                    const uint4 cw = ld_stream(c8 + g), aw = ld_stream(a8 + g), bw = ld_stream(b8 + g);
+                    const uint32_t cc[4] = {cw.x, cw.y, cw.z, cw.w};
+                    const uint32_t aa[4] = {aw.x, aw.y, aw.z, aw.w};
+                    const uint32_t bb[4] = {bw.x, bw.y, bw.z, bw.w};
 #pragma unroll
-            for (int h = 0; h < 2; ++h) {
-                if (h == 1 && !two) break;
-                const uint32_t cc[4] = {cw[h].x, cw[h].y, cw[h].z, cw[h].w};
-                const uint32_t aa[4] = {aw[h].x, aw[h].y, aw[h].z, aw[h].w};
-                const uint32_t bb[4] = {bw[h].x, bw[h].y, bw[h].z, bw[h].w};
-#pragma unroll
-                for (int e = 0; e < 8; ++e) {
-                    const uint32_t c = (e & 1) ? (cc[e >> 1] >> 16) : (cc[e >> 1] & 0xffffu);
-                    const uint32_t a = (e & 1) ? (aa[e >> 1] >> 16) : (aa[e >> 1] & 0xffffu);
-                    const uint32_t b = (e & 1) ? (bb[e >> 1] >> 16) : (bb[e >> 1] & 0xffffu);
-                    const uint32_t zz = s_z[c];
-                    uint2* bp = bins + zz * 32 + lane;
-                    uint2 v = *bp;
-                    v.x += a;
-                    v.y += b;
-                    *bp = v;
+                    for (int e = 0; e < 8; ++e) {
+                        const uint32_t c = (e & 1) ? (cc[e >> 1] >> 16) : (cc[e >> 1] & 0xffffu);
+                        const unsigned long long a = (e & 1) ? (aa[e >> 1] >> 16) : (aa[e >> 1] & 0xffffu);
+                        const unsigned long long b = (e & 1) ? (bb[e >> 1] >> 16) : (bb[e >> 1] & 0xffffu);
+                        if (a | b) atomicAdd(&sab_row[s_z[c]], a | (b << 32));
+                    }
                 }
+                continue;
             }
+            // software pipeline: the next group of each lane is loaded before the current one is binned;
+            // out-of-range slots re-read the segment's last group and are skipped
+            int64_t g = g0 + lane;
+            int64_t gi = min(g, g1 - 1);
+            uint4 cw = ld_stream(c8 + gi), aw = ld_stream(a8 + gi), bw = ld_stream(b8 + gi);
+            int since = 0;
+            for (int64_t gb = g0; gb < g1; gb += 32, g += 32) {       // warp-uniform trip count
+                gi = min(g + 32, g1 - 1);
+                const uint4 cn = ld_stream(c8 + gi), an = ld_stream(a8 + gi), bn = ld_stream(b8 + gi);
+                if (g < g1) stats_group(cw, aw, bw, s_z, bins + lane);
+                cw = cn; aw = an; bw = bn;
+                if (++since == flush_every) { stats_flush<KP>(bins, lane, P.K, sab_row); since = 0; }
+            }
+            if (since) stats_flush<KP>(bins, lane, P.K, sab_row);
         }
-        __syncwarp();
-        // column sums of the per-lane private bins: lane handles clone kk = lane % KP over a KP-wide
-        // slice of lanes, rotated so that a half-warp touches 16 distinct banks
-        const int kk = lane & (KP - 1);
-        const int h = lane / KP;                 // 0 .. 32/KP-1
-        unsigned long long sa = 0, sb = 0;
-#pragma unroll
-        for (int s = 0; s < KP; ++s) {
-            const int t = h * KP + ((s + kk) & (KP - 1));
-            const uint2 v = bins[kk * 32 + t];
-            sa += v.x;
-            sb += v.y;
-        }
-#pragma unroll
-        for (int off = KP; off < 32; off <<= 1) {
-            sa += __shfl_xor_sync(0xffffffffu, sa, off);
-            sb += __shfl_xor_sync(0xffffffffu, sb, off);
-        }
-        if (lane < P.K && (sa | sb)) atomicAdd(&P.sab[i * P.K + lane], sa | (sb << 32));
-        __syncwarp();
     }
 }
 
@@ -545,7 +605,7 @@ void launch_cells_v(const Donor& d, const CellsParams& P, bool smem_tab, size_t 
 }
 
 template <int KP>
-void launch_stats_t(const StatsParams& P, dim3 grid, size_t smem, cudaStream_t st) {
+void launch_stats_t(const StatsParams& P, unsigned grid, size_t smem, cudaStream_t st) {
     auto kern = k_stats<KP>;
     CDL_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     kern<<<grid, STATS_THREADS, smem, st>>>(P);
@@ -639,19 +699,26 @@ void launch_cells(const Donor& d, const SweepArgs& a, ChainDev& c, int sm_count,
 
 void launch_stats(const Donor& d, const SweepArgs& a, ChainDev& c, int sm_count, cudaStream_t st) {
     CDL_CUDA(cudaMemsetAsync(c.sab, 0, sizeof(unsigned long long) * (size_t)(d.N * a.K), st));
+    CDL_CUDA(cudaMemsetAsync(c.work + 1, 0, sizeof(unsigned int), st));
     StatsParams P{};
-    P.seggrp = d.v_seggrp; P.vc = d.v_cell; P.va = d.v_a; P.vb = d.v_b; P.z = c.z; P.sab = c.sab;
+    P.seggrp = d.v_seggrp; P.flush = d.v_flush; P.vc = d.v_cell; P.va = d.v_a; P.vb = d.v_b; P.z = c.z; P.sab = c.sab;
     P.N = d.N; P.M = d.M; P.K = a.K;
+    P.work = c.work + 1;
     const int KP = pad_k(a.K);
-    const int target_ctas = sm_count * 2;
-    int chunks = std::max(1, (target_ctas + d.n_cb - 1) / d.n_cb);
-    int64_t chunk = (d.N + chunks - 1) / chunks;
-    if (chunk < STATS_WARPS) chunk = STATS_WARPS;
-    chunks = (int)((d.N + chunk - 1) / chunk);
-    P.chunk = (int)chunk;
     const int ncell_max = (int)std::min<int64_t>(CELL_BLOCK, d.M);
-    const size_t smem = sizeof(uint2) * STATS_WARPS * KP * 32 + (size_t)((ncell_max + 15) / 16 * 16);
-    dim3 grid((unsigned)chunks, (unsigned)d.n_cb);
+    const size_t smem = sizeof(uint32_t) * STATS_WARPS * KP * 32 + (size_t)((ncell_max + 15) / 16 * 16);
+    const int ctas_per_sm = (int)std::max<size_t>(1, std::min<size_t>(2, (220 * 1024) / (smem + 1024)));
+    const int ctas = sm_count * ctas_per_sm;
+    // units: small enough that the dynamic tail is a few percent of a CTA's share, large enough that a
+    // unit streams a few hundred KB (about 16 units per CTA)
+    int64_t chunks = std::max<int64_t>(1, ((int64_t)ctas * 16 + d.n_cb - 1) / d.n_cb);
+    int64_t chunk = std::max<int64_t>(STATS_WARPS, (d.N + chunks - 1) / chunks);
+    chunk = (chunk + STATS_WARPS - 1) / STATS_WARPS * STATS_WARPS;
+    chunks = (d.N + chunk - 1) / chunk;
+    P.chunk = (int)chunk;
+    P.chunks_per_cb = (int)chunks;
+    P.n_units = (int)(chunks * d.n_cb);
+    const unsigned grid = (unsigned)std::min<int64_t>(ctas, P.n_units);
     switch (KP) {
         case 4: launch_stats_t<4>(P, grid, smem, st); break;
         case 8: launch_stats_t<8>(P, grid, smem, st); break;

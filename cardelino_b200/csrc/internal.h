@@ -44,6 +44,7 @@ struct Donor {
     int64_t c_groups = 0;
     int n_cb = 0;
     uint32_t* v_seggrp = nullptr;
+    uint16_t* v_flush = nullptr;        // [n_cb*N] groups a lane may bin before a 16+16-bit bin could overflow (k_stats)
     uint16_t* v_cell = nullptr;
     uint16_t* v_a = nullptr;
     uint16_t* v_b = nullptr;
@@ -95,7 +96,7 @@ struct ChainDev {
     unsigned long long* part_u; // [grid * 8]
     unsigned int* ticket;
     double2* tab_g;      // (du, dv) table in global memory when it does not fit shared memory, else nullptr
-    unsigned int* work;  // dynamic slice counter of k_cells_sell
+    unsigned int* work;  // [2] dynamic work counters: [0] slices of k_cells_sell, [1] units of k_stats
 };
 
 enum {
