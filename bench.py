@@ -94,6 +94,16 @@ class ClockSampler:
                 "reasons": reasons, "samples": len(sm)}
 
 
+def ncu_traffic(workload, kernel):
+    """DRAM bytes per launch (dram__bytes_read.sum + dram__bytes_write.sum) of `kernel` from the committed
+    `ncu --set full` capture of this workload, or None if there is no capture for it."""
+    try:
+        with open(os.path.join(ROOT, "profiles", "ncu_traffic.json")) as f:
+            return json.load(f).get(workload, {}).get(kernel)
+    except Exception:
+        return None
+
+
 def algorithmic_bytes(nnz, M, K, N):
     """Per sweep per chain: cell pass = nnz*(2+2+2) + 4(M+1) + M + 8MK (fp64 prob row);
     statistic pass = nnz*(2+2+2) + M."""
@@ -208,12 +218,14 @@ def run_ours(args):
             "nnz_clone_updates_per_s": value * nnz * K,
             "roofline": {"bound": "hbm", "kernel": "%s (logLik + softmax + draw)" % ("k_cells_sell" if M >= 16384 else "k_cells"),
                          "achieved": cells_b / (cells_ms * 1e-3) / 1e9, "peak": peak, "unit": "GB/s",
-                         "frac": cells_b / (cells_ms * 1e-3) / 1e9 / peak, "traffic": None,
+                         "frac": cells_b / (cells_ms * 1e-3) / 1e9 / peak,
+                         "traffic": ncu_traffic(args.workload, "k_cells_sell") if world == 1 else None,
                          "peak_source": peak_src, "algorithmic_bytes_per_launch": cells_b,
                          "ms_per_launch": cells_ms,
                          "second_kernel": {"kernel": "k_stats (per-variant x clone read sums)",
                                            "achieved": stats_b / (stats_ms * 1e-3) / 1e9,
                                            "frac": stats_b / (stats_ms * 1e-3) / 1e9 / peak,
+                                           "traffic": ncu_traffic(args.workload, "k_stats") if world == 1 else None,
                                            "algorithmic_bytes_per_launch": stats_b, "ms_per_launch": stats_ms},
                          "table_kernel_ms": bd["ms_table"] / nb},
             "cpu_baseline": cpu, "e2e": e2e, "clocks": clocks,
