@@ -24,7 +24,7 @@ namespace cdl {
 
 namespace {
 
-constexpr int SELL_THREADS = 512;
+// launch shapes: (threads per CTA, group slots per lane loaded ahead of the ones being accumulated)
 constexpr int SELL_SIGMA = 4096;   // sorting window in cells (multiple of 32)
 
 struct SellParams {
@@ -94,7 +94,7 @@ __device__ __forceinline__ void sell_group(double (&acc)[KP], const Grp<VIdx>& q
     }
 }
 
-template <int KP, typename VIdx, bool SMEM>
+template <int KP, typename VIdx, bool SMEM, int SELL_THREADS, int SELL_DEPTH>
 __global__ void __launch_bounds__(SELL_THREADS, 1) k_cells_sell(const SellParams P) {
     constexpr bool PACKED = KP <= 16;
     extern __shared__ __align__(16) unsigned char smem_raw[];
@@ -138,21 +138,23 @@ __global__ void __launch_bounds__(SELL_THREADS, 1) k_cells_sell(const SellParams
         double acc[KP];
 #pragma unroll
         for (int q = 0; q < KP; ++q) acc[q] = 0.0;
-        // two group slots in flight per lane ahead of the ones being accumulated; the look-ahead index is
-        // clamped to the slice's last slot so the loads need no predicate (at most two redundant loads per slice)
-        Grp<VIdx> q0, q1;
+        // SELL_DEPTH group slots per lane are loaded ahead of the ones being accumulated; the look-ahead index
+        // is clamped to the slice's last slot so the loads need no predicate (a few redundant loads per slice)
+        Grp<VIdx> q[SELL_DEPTH];
         if (g0 < g1) {
-            q0.load(C.vidx, P.a8, P.b8, g0 * 32 + lane);
-            q1.load(C.vidx, P.a8, P.b8, min(g0 + 1, g1 - 1) * 32 + lane);
+#pragma unroll
+            for (int h = 0; h < SELL_DEPTH; ++h) q[h].load(C.vidx, P.a8, P.b8, min(g0 + h, g1 - 1) * 32 + lane);
         }
-        for (int64_t g = g0; g < g1; g += 2) {
-            Grp<VIdx> n0, n1;
-            n0.load(C.vidx, P.a8, P.b8, min(g + 2, g1 - 1) * 32 + lane);
-            n1.load(C.vidx, P.a8, P.b8, min(g + 3, g1 - 1) * 32 + lane);
-            sell_group<KP, VIdx, SMEM, PACKED>(acc, q0, tab_sa, msk_sa, tab_g, msk_g);
-            if (g + 1 < g1) sell_group<KP, VIdx, SMEM, PACKED>(acc, q1, tab_sa, msk_sa, tab_g, msk_g);
-            q0 = n0;
-            q1 = n1;
+        for (int64_t g = g0; g < g1; g += SELL_DEPTH) {
+            Grp<VIdx> n[SELL_DEPTH];
+#pragma unroll
+            for (int h = 0; h < SELL_DEPTH; ++h)
+                n[h].load(C.vidx, P.a8, P.b8, min(g + SELL_DEPTH + h, g1 - 1) * 32 + lane);
+#pragma unroll
+            for (int h = 0; h < SELL_DEPTH; ++h)
+                if (h == 0 || g + h < g1) sell_group<KP, VIdx, SMEM, PACKED>(acc, q[h], tab_sa, msk_sa, tab_g, msk_g);
+#pragma unroll
+            for (int h = 0; h < SELL_DEPTH; ++h) q[h] = n[h];
         }
         // ---- softmax over the lane's own K logits (:479-481) ----
         double mx = -INFINITY;
@@ -271,47 +273,88 @@ __global__ void k_sell_slice_len(const uint32_t* __restrict__ rowgrp, const uint
     if (lane == 0) len[s] = l;      // len[n_slices] = 0 closes the scan
 }
 
+// One thread per lane slot.  Inside a cell the order of the entries is free (the logit is a sum), so the row
+// is dealt out such that entry slot e of every group of lane l holds a variant with
+// (variant mod 8) == (l + e) mod 8: the eight lanes of a quarter-warp then gather eight DISTINCT 16-byte bank
+// groups of the shared-memory weight table with each 128-bit load (conflict-free) instead of eight random ones
+// (about 2.4-way conflicts).  A class with more entries than the row has groups spills into free slots of
+// other classes (a few percent of the entries); empty slots are padded with a zero-count entry of the
+// matching class.
 template <typename VIdx>
 __global__ void k_sell_fill(const uint32_t* __restrict__ rowgrp, const uint32_t* __restrict__ perm,
-                            const uint32_t* __restrict__ slice_off, int64_t n_slices, const uint4* __restrict__ cv,
-                            const uint4* __restrict__ ca, const uint4* __restrict__ cb, uint4* __restrict__ ov,
-                            uint4* __restrict__ oa, uint4* __restrict__ ob) {
-    constexpr int VW = sizeof(VIdx) / 2;   // uint4 words per group of variant indices
-    const int lane = threadIdx.x & 31;
-    const int64_t warp = (blockIdx.x * (int64_t)blockDim.x + threadIdx.x) >> 5;
-    const int64_t nwarps = ((int64_t)gridDim.x * blockDim.x) >> 5;
-    const uint4 zero4 = make_uint4(0, 0, 0, 0);
-    for (int64_t s = warp; s < n_slices; s += nwarps) {
-        const int64_t o0 = slice_off[s], o1 = slice_off[s + 1];
-        const uint32_t j = perm[s * 32 + lane];
-        int64_t r0 = 0, r1 = 0;
-        if (j != 0xffffffffu) { r0 = rowgrp[j]; r1 = rowgrp[j + 1]; }
-        for (int64_t g = 0; g < o1 - o0; ++g) {
-            const bool have = r0 + g < r1;
-            const int64_t dst = (o0 + g) * 32 + lane;
-            oa[dst] = have ? ca[r0 + g] : zero4;
-            ob[dst] = have ? cb[r0 + g] : zero4;
+                            const uint32_t* __restrict__ slice_off, int64_t n_slices, int64_t N,
+                            const VIdx* __restrict__ cv, const uint16_t* __restrict__ ca,
+                            const uint16_t* __restrict__ cb, VIdx* __restrict__ ov, uint16_t* __restrict__ oa,
+                            uint16_t* __restrict__ ob) {
+    const int64_t slot = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+    if (slot >= n_slices * 32) return;
+    const int64_t s = slot >> 5;
+    const int lane = (int)(slot & 31);
+    const int64_t o0 = slice_off[s];
+    const int ngs = (int)(slice_off[s + 1] - o0);          // groups of the slice (>= groups of this row)
+    const uint32_t j = perm[slot];
+    int64_t e0 = 0, e1 = 0;
+    if (j != 0xffffffffu) { e0 = (int64_t)rowgrp[j] * GROUP; e1 = (int64_t)rowgrp[j + 1] * GROUP; }
+    auto out_index = [&](int g, int e) { return ((o0 + g) * 32 + lane) * GROUP + e; };
+    int cursor[GROUP];
 #pragma unroll
-            for (int w = 0; w < VW; ++w) ov[dst * VW + w] = have ? cv[(r0 + g) * VW + w] : zero4;
+    for (int e = 0; e < GROUP; ++e) cursor[e] = 0;
+    // pass 1: entries whose class column still has room
+    for (int64_t q = e0; q < e1; ++q) {
+        const uint32_t a = ca[q], b = cb[q];
+        if ((a | b) == 0) continue;                        // padding of the row layout
+        const uint32_t v = (uint32_t)cv[q];
+        const int e = (int)((v - (uint32_t)lane) & 7u);
+        if (cursor[e] < ngs) {
+            const int64_t o = out_index(cursor[e]++, e);
+            ov[o] = (VIdx)v; oa[o] = (uint16_t)a; ob[o] = (uint16_t)b;
+        }
+    }
+    // pass 2: the overflow of over-full classes goes to the free slots of the others
+    int placed[GROUP], fill[GROUP];
+#pragma unroll
+    for (int e = 0; e < GROUP; ++e) { placed[e] = 0; fill[e] = cursor[e]; }
+    int fe = 0;
+    for (int64_t q = e0; q < e1; ++q) {
+        const uint32_t a = ca[q], b = cb[q];
+        if ((a | b) == 0) continue;
+        const uint32_t v = (uint32_t)cv[q];
+        const int e = (int)((v - (uint32_t)lane) & 7u);
+        if (placed[e]++ < ngs) continue;                   // went out in pass 1
+        while (fe < GROUP && fill[fe] >= ngs) ++fe;
+        if (fe >= GROUP) break;                            // cannot happen: the row has <= 8 * ngs entries
+        const int64_t o = out_index(fill[fe]++, fe);
+        ov[o] = (VIdx)v; oa[o] = (uint16_t)a; ob[o] = (uint16_t)b;
+    }
+    // padding: zero counts, a variant id of the slot's class so that it gathers conflict-free too
+    for (int e = 0; e < GROUP; ++e) {
+        const uint32_t want = (uint32_t)(lane + e) & 7u;
+        const uint32_t vpad = (int64_t)want < N ? want : 0u;
+        for (int g = fill[e]; g < ngs; ++g) {
+            const int64_t o = out_index(g, e);
+            ov[o] = (VIdx)vpad; oa[o] = 0; ob[o] = 0;
         }
     }
 }
 
-template <int KP, typename VIdx>
+template <int KP, typename VIdx, int THREADS, int DEPTH>
 void launch_sell_t(const SellParams& P, bool smem_tab, size_t smem, int grid, cudaStream_t st) {
     if (smem_tab) {
-        auto kern = k_cells_sell<KP, VIdx, true>;
+        auto kern = k_cells_sell<KP, VIdx, true, THREADS, DEPTH>;
         CDL_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        kern<<<grid, SELL_THREADS, smem, st>>>(P);
+        kern<<<grid, THREADS, smem, st>>>(P);
     } else {
-        k_cells_sell<KP, VIdx, false><<<grid, SELL_THREADS, 0, st>>>(P);
+        k_cells_sell<KP, VIdx, false, THREADS, DEPTH><<<grid, THREADS, 0, st>>>(P);
     }
 }
 
 template <int KP>
-void launch_sell_v(const Donor& d, const SellParams& P, bool smem_tab, size_t smem, int grid, cudaStream_t st) {
-    if (d.vidx32) launch_sell_t<KP, uint32_t>(P, smem_tab, smem, grid, st);
-    else launch_sell_t<KP, uint16_t>(P, smem_tab, smem, grid, st);
+void launch_sell_v(const Donor& d, const SellParams& P, bool smem_tab, size_t smem, int grid, int shape,
+                   cudaStream_t st) {
+    if (d.vidx32) { launch_sell_t<KP, uint32_t, 512, 2>(P, smem_tab, smem, grid, st); return; }
+    if (shape == 1) launch_sell_t<KP, uint16_t, 768, 1>(P, smem_tab, smem, grid, st);
+    else if (shape == 2) launch_sell_t<KP, uint16_t, 1024, 1>(P, smem_tab, smem, grid, st);
+    else launch_sell_t<KP, uint16_t, 512, 2>(P, smem_tab, smem, grid, st);
 }
 
 }  // namespace
@@ -361,13 +404,13 @@ void donor_build_sell(Donor& d, cudaStream_t st) {
         CDL_CUDA(cudaMalloc(&d.s_vidx, 16 * words * vw));
         CDL_CUDA(cudaMalloc(&d.s_a, 16 * words));
         CDL_CUDA(cudaMalloc(&d.s_b, 16 * words));
-        const unsigned blocks = (unsigned)std::min<int64_t>((n_slices * 32 + threads - 1) / threads, 148 * 16);
+        const unsigned blocks = (unsigned)((n_slices * 32 + threads - 1) / threads);
         if (d.vidx32)
-            k_sell_fill<uint32_t><<<blocks, threads, 0, st>>>(d.c_rowgrp, d.s_perm, d.s_off, n_slices,
-                (const uint4*)d.c_vidx, (const uint4*)d.c_a, (const uint4*)d.c_b, (uint4*)d.s_vidx, (uint4*)d.s_a, (uint4*)d.s_b);
+            k_sell_fill<uint32_t><<<blocks, threads, 0, st>>>(d.c_rowgrp, d.s_perm, d.s_off, n_slices, d.N,
+                (const uint32_t*)d.c_vidx, d.c_a, d.c_b, (uint32_t*)d.s_vidx, d.s_a, d.s_b);
         else
-            k_sell_fill<uint16_t><<<blocks, threads, 0, st>>>(d.c_rowgrp, d.s_perm, d.s_off, n_slices,
-                (const uint4*)d.c_vidx, (const uint4*)d.c_a, (const uint4*)d.c_b, (uint4*)d.s_vidx, (uint4*)d.s_a, (uint4*)d.s_b);
+            k_sell_fill<uint16_t><<<blocks, threads, 0, st>>>(d.c_rowgrp, d.s_perm, d.s_off, n_slices, d.N,
+                (const uint16_t*)d.c_vidx, d.c_a, d.c_b, (uint16_t*)d.s_vidx, d.s_a, d.s_b);
         CDL_CUDA(cudaGetLastError());
         CDL_CUDA(cudaStreamSynchronize(st));
         d.s_slices = n_slices;
@@ -411,14 +454,19 @@ void launch_cells_sell(const Donor& d, const SweepArgs& a, ChainDev& c, int sm_c
                                                                          c.scal, c.mask, c.tab_g);
         C.l1 = reinterpret_cast<const double*>(c.tab_g);
     }
+    // 24 warps per SM with one group slot of look-ahead beat 16 warps with two (the kernel is bound by the
+    // fp64 pipe and needs the extra warps to keep it fed); CDL_SELL_SHAPE overrides for experiments
+    int shape = 1;
+    if (const char* e = getenv("CDL_SELL_SHAPE")) shape = atoi(e);
     int64_t grid = sm_count;
-    const int64_t max_useful = (d.s_slices + SELL_THREADS / 32 - 1) / (SELL_THREADS / 32);
+    const int threads = d.vidx32 ? 512 : (shape == 1 ? 768 : (shape == 2 ? 1024 : 512));
+    const int64_t max_useful = (d.s_slices + threads / 32 - 1) / (threads / 32);
     if (grid > max_useful) grid = std::max<int64_t>(max_useful, 1);
     switch (KP) {
-        case 4: launch_sell_v<4>(d, P, smem_tab, smem, (int)grid, st); break;
-        case 8: launch_sell_v<8>(d, P, smem_tab, smem, (int)grid, st); break;
-        case 16: launch_sell_v<16>(d, P, smem_tab, smem, (int)grid, st); break;
-        default: launch_sell_v<32>(d, P, smem_tab, smem, (int)grid, st); break;
+        case 4: launch_sell_v<4>(d, P, smem_tab, smem, (int)grid, shape, st); break;
+        case 8: launch_sell_v<8>(d, P, smem_tab, smem, (int)grid, shape, st); break;
+        case 16: launch_sell_v<16>(d, P, smem_tab, smem, (int)grid, shape, st); break;
+        default: launch_sell_v<32>(d, P, smem_tab, smem, (int)grid, shape, st); break;
     }
     CDL_CUDA(cudaGetLastError());
 }
