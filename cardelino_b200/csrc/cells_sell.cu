@@ -73,7 +73,10 @@ __device__ __forceinline__ void sell_group(double (&acc)[KP], const Grp<VIdx>& q
                 const double2 t = __ldg(tab_g + i);
                 du = t.x; dv = t.y;
             }
-            const double del = fma(u16_to_double(a), du, u16_to_double(b) * dv);
+            // counts -> double with I2F.F64.U16 (converts a register half directly, on the conversion pipe):
+            // the 2^52 trick of the row kernel would put two more DADDs per entry on the fp64 pipe, which is
+            // what bounds this kernel
+            const double del = fma((double)a, du, (double)b * dv);
             // gather the two mask bytes into ONE integer register first: ptxas then turns the bit tests into
             // R2P (seven predicates per instruction); testing the low words of du / dv in place makes it
             // emit one LOP3 per clone instead
