@@ -636,7 +636,7 @@ int cdl_gibbs_run(cdl_handle h, const double* Config, int32_t K, const double* P
             if (exact) { ch.prob_all.alloc((size_t)(T * M * K)); ch.prob_all.zero(h->st); }
             else { ch.prob_acc.alloc((size_t)(M * K)); ch.prob_acc.zero(h->st); }
             if (gp.keep_assign_all) { ch.assign_all.alloc((size_t)(T * M)); ch.assign_all.zero(h->st); }
-            const size_t tgrid = (size_t)((N + 255) / 256) + 1;
+            const size_t tgrid = (size_t)((N + 7) / 8) + 1;     // k_table blocks: 256 / KP variants each, KP <= 32
             ch.part_d.alloc(tgrid * 4); ch.part_u.alloc(tgrid * 8);
             ch.ticket.alloc(1); ch.ticket.zero(h->st);
             ch.work.alloc(2); ch.work.zero(h->st);

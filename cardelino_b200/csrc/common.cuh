@@ -66,8 +66,9 @@ __host__ __device__ inline double philox_uniform(PhiloxKey key, uint32_t chain, 
 struct PhiloxSeq {
     PhiloxKey key;
     uint32_t idx, it, sw, sub;
-    __host__ __device__ PhiloxSeq(PhiloxKey k, uint32_t chain, uint32_t it_, uint32_t stream, uint32_t idx_)
-        : key(k), idx(idx_), it(it_), sw(stream_word(chain, stream)), sub(0) {}
+    __host__ __device__ PhiloxSeq(PhiloxKey k, uint32_t chain, uint32_t it_, uint32_t stream, uint32_t idx_,
+                                  uint32_t sub0 = 0)
+        : key(k), idx(idx_), it(it_), sw(stream_word(chain, stream)), sub(sub0) {}
     // two 53-bit uniforms per block
     __host__ __device__ inline void next2(double& u, double& v) {
         uint32_t o[4];
@@ -114,6 +115,12 @@ __host__ __device__ inline double clamp_theta(double t) {
     return t < lo ? lo : (t > hi ? hi : t);
 }
 
+// Beta(a, b) from two independent Gamma draws X ~ Gamma(a), Y ~ Gamma(b) made by different threads
+__host__ __device__ inline double beta_from_gammas(double x, double y) {
+    const double sum = x + y;
+    return clamp_theta((sum > 0.0) ? x / sum : 0.5);
+}
+
 __host__ __device__ inline double beta_draw(double a, double b, PhiloxSeq& s) {
     const double x = gamma_mt(a, s);
     const double y = gamma_mt(b, s);
@@ -153,6 +160,12 @@ __device__ __forceinline__ unsigned long long warp_sum_u64(unsigned long long v)
 // exact u16 -> double without the (slow) I2F.F64 path: 2^52 + a has `a` in the low mantissa bits
 __device__ __forceinline__ double u16_to_double(uint32_t a) {
     return __hiloint2double(0x43300000, (int)a) - 4503599627370496.0;
+}
+// 64-bit load of another GPU's memory over NVLink (or of local memory): system scope, never from a stale L1 line
+__device__ __forceinline__ unsigned long long ld_peer_u64(const unsigned long long* p) {
+    unsigned long long r;
+    asm volatile("ld.relaxed.sys.global.u64 %0, [%1];" : "=l"(r) : "l"(p));
+    return r;
 }
 // streaming 128-bit load, bypassing L1 allocation (read-once data)
 __device__ __forceinline__ uint4 ld_stream(const uint4* p) {

@@ -372,6 +372,9 @@ struct TableParams {
     PhiloxKey key; uint32_t chain;
     const double* rp_u_config; const double* rp_theta0; const double* rp_theta1; const double* rp_relax_next;
     double* part_d; unsigned long long* part_u; unsigned int* ticket;
+    // cell-sharded runs with peer access: the other ranks' statistic tables, summed on the fly (else n_peer = 0)
+    int n_peer;
+    const unsigned long long* peer_sab[MAX_PEERS];
 };
 
 __device__ __forceinline__ unsigned long long block_sum_u64(unsigned long long v, unsigned long long* sm) {
@@ -395,72 +398,86 @@ __device__ __forceinline__ double block_sum_d(double v, double* sm) {
     return r;
 }
 
+// One thread per (variant, clone) element; the KP lanes of a variant sit in one warp.
+//   phase A  Config flip of the element and its contribution to the theta statistics / logLik trace, reduced
+//            over the variant's lanes with shuffles; block partials go through a ticket and the last block
+//            reduces them in block order (deterministic).
+//   phase B  every Beta draw of the sweep is two independent Gamma draws (Marsaglia-Tsang on their own Philox
+//            sub-streams); each Gamma is one job on one thread: 2 per variant of the block for theta1, plus --
+//            in the last block -- theta0, the next relax rate and the global theta1.  A serial fp64
+//            rejection sampler is ~10 cycles per dependent instruction, so the kernel's duration is one Gamma
+//            draw, not a chain of them.
+template <int KP>
 __global__ void __launch_bounds__(TABLE_THREADS) k_table(const TableParams P) {
+    constexpr int VPB = TABLE_THREADS / KP;          // variants per block
+    constexpr int NJOB = 2 * VPB + 6;
+    static_assert(NJOB <= TABLE_THREADS, "one Gamma job per thread");
     __shared__ unsigned long long sm_u[TABLE_THREADS / 32];
     __shared__ double sm_d[TABLE_THREADS / 32];
+    __shared__ unsigned long long s_s3[VPB], s_s4[VPB], s_tot[5];
+    __shared__ double s_gam[NJOB];
     __shared__ bool is_last;
-    const int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+    const int k = threadIdx.x & (KP - 1);
+    const int v = threadIdx.x / KP;
+    const int64_t i = (int64_t)blockIdx.x * VPB + v;
     const double l0 = P.scal[SC_L0], l0c = P.scal[SC_L0C], r = P.scal[SC_RELAX];
     const double odd1 = log(1.0 - r) - log(r);   // Config == 1: log(prior) - log(1 - prior), prior = 1 - r
     const double odd0 = log(r) - log(1.0 - r);   // Config == 0: prior = r
     unsigned long long S1 = 0, S2 = 0, S3 = 0, S4 = 0, diff1 = 0;
     double ll = 0.0;
-    if (i < P.N) {
+    uint32_t bitk = 0;
+    if (i < P.N && k < P.K) {
         const int64_t t = P.wise == 1 ? i : 0;
         const double l1 = P.l1[t], l1c = P.l1c[t];
         const double du = l1 - l0, dv = l1c - l0c;
         const uint32_t c0 = P.cfg0[i];
-        uint32_t nm = 0;
-        for (int k = 0; k < P.K; ++k) {
-            const unsigned long long pk = P.sab[i * P.K + k];
-            const double SA = (double)(uint32_t)pk, SB = (double)(uint32_t)(pk >> 32);
-            const uint32_t cbit = (c0 >> k) & 1u;
-            uint32_t bit = cbit;
-            if (P.relax) {
-                double prior;
-                if (P.keep_base && k == 0) prior = cbit ? INFINITY : -INFINITY;
-                else prior = cbit ? odd1 : odd0;
-                double x = SA * du + SB * dv + prior;
-                x = x > 50.0 ? 50.0 : (x < -50.0 ? -50.0 : x);
-                const double ex = exp(x);
-                const double p = ex / (ex + 1.0);
-                const uint32_t idx = (uint32_t)(i + (int64_t)k * P.N);
-                const double u = P.rp_u_config ? P.rp_u_config[idx]
-                                               : philox_uniform(P.key, P.chain, P.it, STREAM_CONFIG, idx);
-                bit = (uint32_t)rbinom1(p, u);
-            }
-            // Config_all row (:535); with relax off the row holds Config itself (the reference stops
-            // with "object 'Config_new' not found" there)
-            P.config_all[(int64_t)(P.it - 1) * P.N * P.K + i + (int64_t)k * P.N] = (uint8_t)bit;
-            nm |= bit << k;
-            if (bit) {
-                S3 += (uint32_t)pk; S4 += (uint32_t)(pk >> 32);
-                ll += SA * l1 + SB * l1c;
-            } else {
-                S1 += (uint32_t)pk; S2 += (uint32_t)(pk >> 32);
-                ll += SA * l0 + SB * l0c;
-            }
-            if (k >= 1) diff1 += (bit != cbit);
+        unsigned long long pk = P.sab[i * P.K + k];
+        for (int q = 0; q < P.n_peer; ++q) pk += ld_peer_u64(P.peer_sab[q] + i * P.K + k);
+        const double SA = (double)(uint32_t)pk, SB = (double)(uint32_t)(pk >> 32);
+        const uint32_t cbit = (c0 >> k) & 1u;
+        uint32_t bit = cbit;
+        if (P.relax) {
+            double prior;
+            if (P.keep_base && k == 0) prior = cbit ? INFINITY : -INFINITY;
+            else prior = cbit ? odd1 : odd0;
+            double x = SA * du + SB * dv + prior;
+            x = x > 50.0 ? 50.0 : (x < -50.0 ? -50.0 : x);
+            const double ex = exp(x);
+            const double p = ex / (ex + 1.0);
+            const uint32_t idx = (uint32_t)(i + (int64_t)k * P.N);
+            const double u = P.rp_u_config ? P.rp_u_config[idx]
+                                           : philox_uniform(P.key, P.chain, P.it, STREAM_CONFIG, idx);
+            bit = (uint32_t)rbinom1(p, u);
         }
-        P.mask[i] = nm;
-        if (P.wise == 1) {
-            double th;
-            if (P.rp_theta1) th = clamp_theta(P.rp_theta1[i]);
-            else {
-                const double pa = P.prior1_mat ? P.prior1_mat[i] : P.prior1[0];
-                const double pb = P.prior1_mat ? P.prior1_mat[P.n_el + i] : P.prior1[1];
-                PhiloxSeq s(P.key, P.chain, P.it, STREAM_THETA1, (uint32_t)i);
-                th = beta_draw(pa + (double)S3, pb + (double)S4, s);
-            }
-            P.theta1_all[(int64_t)(P.it - 1) * P.n_el + i] = th;
-            P.l1[i] = log(th);
-            P.l1c[i] = log(1.0 - th);
+        // Config_all row (:535); with relax off the row holds Config itself (the reference stops
+        // with "object 'Config_new' not found" there)
+        P.config_all[(int64_t)(P.it - 1) * P.N * P.K + i + (int64_t)k * P.N] = (uint8_t)bit;
+        bitk = bit << k;
+        if (bit) {
+            S3 = (uint32_t)pk; S4 = (uint32_t)(pk >> 32);
+            ll = SA * l1 + SB * l1c;
+        } else {
+            S1 = (uint32_t)pk; S2 = (uint32_t)(pk >> 32);
+            ll = SA * l0 + SB * l0c;
         }
+        if (k >= 1) diff1 = (bit != cbit);
+    }
+    // per-variant sums over the KP lanes (fixed butterfly order)
+    unsigned long long v3 = S3, v4 = S4;
+#pragma unroll
+    for (int off = 1; off < KP; off <<= 1) {
+        v3 += __shfl_xor_sync(0xffffffffu, v3, off);
+        v4 += __shfl_xor_sync(0xffffffffu, v4, off);
+        bitk |= __shfl_xor_sync(0xffffffffu, bitk, off);
+    }
+    if (k == 0) {
+        s_s3[v] = v3; s_s4[v] = v4;
+        if (i < P.N) P.mask[i] = bitk;
     }
     const unsigned long long b1 = block_sum_u64(S1, sm_u), b2 = block_sum_u64(S2, sm_u);
     const unsigned long long b3 = block_sum_u64(S3, sm_u), b4 = block_sum_u64(S4, sm_u);
     const unsigned long long bd = block_sum_u64(diff1, sm_u);
-    const double bl = block_sum_d(ll, sm_d);
+    const double bl = block_sum_d(ll, sm_d);          // (the block sums synchronise: s_s3 / s_s4 are visible)
     if (threadIdx.x == 0) {
         unsigned long long* pu = P.part_u + (size_t)blockIdx.x * 8;
         pu[0] = b1; pu[1] = b2; pu[2] = b3; pu[3] = b4; pu[4] = bd;
@@ -470,58 +487,95 @@ __global__ void __launch_bounds__(TABLE_THREADS) k_table(const TableParams P) {
         is_last = (tk == gridDim.x - 1);
     }
     __syncthreads();
-    if (!is_last) return;
-    __threadfence();
-    // deterministic final reduction in block order
-    unsigned long long t1 = 0, t2 = 0, t3 = 0, t4 = 0, td = 0;
-    double tl = 0.0;
-    for (unsigned b = threadIdx.x; b < gridDim.x; b += blockDim.x) {
-        const volatile unsigned long long* pu = P.part_u + (size_t)b * 8;
-        t1 += pu[0]; t2 += pu[1]; t3 += pu[2]; t4 += pu[3]; td += pu[4];
-        tl += ((const volatile double*)P.part_d)[b];
-    }
-    t1 = block_sum_u64(t1, sm_u); t2 = block_sum_u64(t2, sm_u); t3 = block_sum_u64(t3, sm_u);
-    t4 = block_sum_u64(t4, sm_u); td = block_sum_u64(td, sm_u);
-    tl = block_sum_d(tl, sm_d);
-    if (threadIdx.x == 0) {
-        *P.ticket = 0;
-        const int64_t row = (int64_t)P.it - 1;
-        P.loglik_all[row] = tl + P.W_log;
-        double th0;
-        if (P.rp_theta0) th0 = clamp_theta(P.rp_theta0[0]);
-        else {
-            PhiloxSeq s(P.key, P.chain, P.it, STREAM_THETA0, 0);
-            th0 = beta_draw(P.prior0[0] + (double)t1, P.prior0[1] + (double)t2, s);
+    const bool last = is_last;                        // block-uniform
+    if (last) {
+        __threadfence();
+        // deterministic final reduction in block order
+        unsigned long long t1 = 0, t2 = 0, t3 = 0, t4 = 0, td = 0;
+        double tl = 0.0;
+        for (unsigned b = threadIdx.x; b < gridDim.x; b += blockDim.x) {
+            const volatile unsigned long long* pu = P.part_u + (size_t)b * 8;
+            t1 += pu[0]; t2 += pu[1]; t3 += pu[2]; t4 += pu[3]; td += pu[4];
+            tl += ((const volatile double*)P.part_d)[b];
         }
+        t1 = block_sum_u64(t1, sm_u); t2 = block_sum_u64(t2, sm_u); t3 = block_sum_u64(t3, sm_u);
+        t4 = block_sum_u64(t4, sm_u); td = block_sum_u64(td, sm_u);
+        tl = block_sum_d(tl, sm_d);
+        if (threadIdx.x == 0) {
+            *P.ticket = 0;
+            P.loglik_all[(int64_t)P.it - 1] = tl + P.W_log;
+            s_tot[0] = t1; s_tot[1] = t2; s_tot[2] = t3; s_tot[3] = t4; s_tot[4] = td;
+        }
+        __syncthreads();
+    }
+    // ---- phase B: one Gamma job per thread ----
+    {
+        const int j = threadIdx.x;
+        double shape = -1.0;
+        uint32_t stream = 0, idx = 0, it = P.it;
+        if (j < 2 * VPB) {
+            const int64_t iv = (int64_t)blockIdx.x * VPB + (j >> 1);
+            if (P.wise == 1 && iv < P.N && !P.rp_theta1) {
+                const double pa = P.prior1_mat ? P.prior1_mat[iv] : P.prior1[0];
+                const double pb = P.prior1_mat ? P.prior1_mat[P.n_el + iv] : P.prior1[1];
+                shape = (j & 1) ? pb + (double)s_s4[j >> 1] : pa + (double)s_s3[j >> 1];
+                stream = STREAM_THETA1; idx = (uint32_t)iv;
+            }
+        } else if (last && j < NJOB) {
+            const int q = j - 2 * VPB;               // 0,1 theta0; 2,3 next relax rate; 4,5 global theta1
+            if (q < 2 && !P.rp_theta0) {
+                shape = P.prior0[q] + (double)s_tot[q];
+                stream = STREAM_THETA0;
+            } else if (q >= 2 && q < 4 && P.learn_relax_next && (int64_t)P.it < P.T && !P.rp_relax_next) {
+                const double d1 = (double)s_tot[4];
+                shape = (q == 2) ? P.relax_prior[0] + d1
+                                 : P.relax_prior[1] + (double)P.N * (double)(P.K - 1) - d1;
+                stream = STREAM_RELAX; it = P.it + 1;
+            } else if (q >= 4 && P.wise == 0 && !P.rp_theta1) {
+                const double pa = P.prior1_mat ? P.prior1_mat[0] : P.prior1[0];
+                const double pb = P.prior1_mat ? P.prior1_mat[1] : P.prior1[1];
+                shape = (q == 4) ? pa + (double)s_tot[2] : pb + (double)s_tot[3];
+                stream = STREAM_THETA1;
+            }
+        }
+        if (shape >= 0.0) {
+            PhiloxSeq sq(P.key, P.chain, it, stream, idx, (uint32_t)(j & 1) << 31);   // X and Y: disjoint halves
+            s_gam[j] = gamma_mt(shape, sq);
+        }
+    }
+    __syncthreads();
+    if (P.wise == 1 && threadIdx.x < VPB) {
+        const int64_t iv = (int64_t)blockIdx.x * VPB + threadIdx.x;
+        if (iv < P.N) {
+            const double th = P.rp_theta1 ? clamp_theta(P.rp_theta1[iv])
+                                          : beta_from_gammas(s_gam[2 * threadIdx.x], s_gam[2 * threadIdx.x + 1]);
+            P.theta1_all[(int64_t)(P.it - 1) * P.n_el + iv] = th;
+            P.l1[iv] = log(th);
+            P.l1c[iv] = log(1.0 - th);
+        }
+    }
+    if (!last) return;
+    const int64_t row = (int64_t)P.it - 1;
+    if (threadIdx.x == 32) {
+        const double th0 = P.rp_theta0 ? clamp_theta(P.rp_theta0[0])
+                                       : beta_from_gammas(s_gam[2 * VPB], s_gam[2 * VPB + 1]);
         P.theta0_all[row] = th0;
         P.scal[SC_THETA0] = th0;
         P.scal[SC_L0] = log(th0);
         P.scal[SC_L0C] = log(1.0 - th0);
-        if (P.wise == 0) {
-            double th;
-            if (P.rp_theta1) th = clamp_theta(P.rp_theta1[0]);
-            else {
-                const double pa = P.prior1_mat ? P.prior1_mat[0] : P.prior1[0];
-                const double pb = P.prior1_mat ? P.prior1_mat[1] : P.prior1[1];
-                PhiloxSeq s(P.key, P.chain, P.it, STREAM_THETA1, 0);
-                th = beta_draw(pa + (double)t3, pb + (double)t4, s);
-            }
-            P.theta1_all[row] = th;
-            P.l1[0] = log(th);
-            P.l1c[0] = log(1.0 - th);
-        }
-        if (P.learn_relax_next && (int64_t)P.it < P.T) {
-            const double d1 = (double)td;
-            const double d0 = (double)P.N * (double)(P.K - 1) - d1;
-            double rr;
-            if (P.rp_relax_next) rr = P.rp_relax_next[0];
-            else {
-                PhiloxSeq s(P.key, P.chain, P.it + 1, STREAM_RELAX, 0);
-                rr = beta_draw(P.relax_prior[0] + d1, P.relax_prior[1] + d0, s);
-            }
-            P.scal[SC_RELAX] = rr;
-            P.relax_all[row + 1] = rr;
-        }
+    }
+    if (threadIdx.x == 64 && P.wise == 0) {
+        const double th = P.rp_theta1 ? clamp_theta(P.rp_theta1[0])
+                                      : beta_from_gammas(s_gam[2 * VPB + 4], s_gam[2 * VPB + 5]);
+        P.theta1_all[row] = th;
+        P.l1[0] = log(th);
+        P.l1c[0] = log(1.0 - th);
+    }
+    if (threadIdx.x == 96 && P.learn_relax_next && (int64_t)P.it < P.T) {
+        const double rr = P.rp_relax_next ? P.rp_relax_next[0]
+                                          : beta_from_gammas(s_gam[2 * VPB + 2], s_gam[2 * VPB + 3]);
+        P.scal[SC_RELAX] = rr;
+        P.relax_all[row + 1] = rr;
     }
 }
 
@@ -745,8 +799,16 @@ void launch_table(const Donor& d, const SweepArgs& a, ChainDev& c, cudaStream_t 
     P.rp_u_config = a.rp_u_config; P.rp_theta0 = a.rp_theta0; P.rp_theta1 = a.rp_theta1;
     P.rp_relax_next = a.rp_relax_next;
     P.part_d = c.part_d; P.part_u = c.part_u; P.ticket = c.ticket;
-    const unsigned grid = (unsigned)((d.N + TABLE_THREADS - 1) / TABLE_THREADS);
-    k_table<<<grid, TABLE_THREADS, 0, st>>>(P);
+    P.n_peer = 0;
+    const int KP = pad_k(a.K);
+    const int vpb = TABLE_THREADS / KP;
+    const unsigned grid = (unsigned)((d.N + vpb - 1) / vpb);
+    switch (KP) {
+        case 4: k_table<4><<<grid, TABLE_THREADS, 0, st>>>(P); break;
+        case 8: k_table<8><<<grid, TABLE_THREADS, 0, st>>>(P); break;
+        case 16: k_table<16><<<grid, TABLE_THREADS, 0, st>>>(P); break;
+        default: k_table<32><<<grid, TABLE_THREADS, 0, st>>>(P); break;
+    }
     CDL_CUDA(cudaGetLastError());
 }
 

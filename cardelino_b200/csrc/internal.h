@@ -11,6 +11,7 @@ namespace cdl {
 constexpr int GROUP = 8;           // entries per 128-bit load of uint16 payload
 constexpr int CELL_BLOCK = 65536;  // cells per variant-major block (local cell id fits uint16)
 constexpr int KMAX = 32;
+constexpr int MAX_PEERS = 7;        // other ranks of one NVSwitch box
 
 struct Error : std::runtime_error {
     int code;
