@@ -141,6 +141,7 @@ def run_ours(args):
             uid.copy_(torch.from_numpy(h.comm_unique_id(nccl_path)))
         dist.broadcast(uid, 0)
         h.comm_init(nccl_path, uid.cpu().numpy(), rank, world)
+        h.set_exchange_mode(args.exchange)
     h.synth_generate(N, M, K, cfg, cov, SEED_DATA, cell_offset=off, M_local=Ml)
     _, _, nnz_local, _ = h.data_info()
     T0 = 4
@@ -212,8 +213,10 @@ def run_ours(args):
             "config": {"workload": "%s: %d variants x %d cells x %d clones, %.0f%% coverage, nnz=%d, "
                                    "wise=variant, relax_Config=TRUE (learned rate), 1 chain" %
                                    (args.workload, N, M, K, cov * 100, nnz),
-                       "sharding": "cells over %d rank(s), one NCCL all-reduce of the %d x %d statistic "
-                                   "table per sweep" % (world, N, K),
+                       "sharding": "cells over %d rank(s); per sweep the %d x %d statistic table is %s" %
+                                   (world, N, K, "not exchanged (1 rank)" if world == 1 else
+                                    ("summed over peer memory inside the table kernel (NVLink loads, no collective call)"
+                                     if h.exchange_is_peer() else "all-reduced with NCCL")),
                        "l2": "inputs (%.1f GB per rank per pass) exceed the 126 MB L2" % (nnz_local * 6 / 1e9)},
             "nnz_clone_updates_per_s": value * nnz * K,
             "roofline": {"bound": "hbm", "kernel": "%s (logLik + softmax + draw)" % ("k_cells_sell" if M >= 16384 else "k_cells"),
@@ -319,6 +322,8 @@ def main():
     ap.add_argument("--e2e-iters", type=int, default=200)
     ap.add_argument("--cpu-cells", type=int, default=64)
     ap.add_argument("--cpu-iters", type=int, default=2)
+    ap.add_argument("--exchange", default="auto", choices=["auto", "nccl", "peer"],
+                    help="multi-GPU statistic-table exchange: peer memory fused into the table kernel, or NCCL")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu", action="store_true")
     args = ap.parse_args()

@@ -18,7 +18,7 @@ EXPORTS = [
     "cdl_fetch_prob", "cdl_fetch_config_prob", "cdl_fetch_theta", "cdl_fetch_theta_traces",
     "cdl_fetch_loglik_trace", "cdl_fetch_relax_rate", "cdl_fetch_prob_all", "cdl_fetch_config_all",
     "cdl_fetch_assign_all", "cdl_fetch_prob_variant", "cdl_fetch_element_index", "cdl_get_loglik",
-    "cdl_em_run", "cdl_bench_sweeps", "cdl_set_cells_layout",
+    "cdl_em_run", "cdl_bench_sweeps", "cdl_set_cells_layout", "cdl_set_exchange_mode", "cdl_exchange_is_peer",
 ]
 
 WISE = {"global": 0, "variant": 1, "element": 2}
@@ -143,6 +143,13 @@ class Handle:
     def set_cells_layout(self, layout):
         """'auto' | 'rows' | 'slices': which cell kernel the Gibbs sweep uses (include/cardelino_b200.h)."""
         self._check(self.lib.cdl_set_cells_layout(self.h, C.c_int32(CELLS_LAYOUT[layout])))
+
+    def set_exchange_mode(self, mode):
+        """'auto' | 'nccl' | 'peer': how the ranks of a cell-sharded run sum the statistic table per sweep."""
+        self._check(self.lib.cdl_set_exchange_mode(self.h, C.c_int32({"auto": 0, "nccl": 1, "peer": 2}[mode])))
+
+    def exchange_is_peer(self):
+        return bool(self.lib.cdl_exchange_is_peer(self.h))
 
     def set_shard(self, cell_offset, M_total):
         self._check(self.lib.cdl_set_shard(self.h, C.c_int64(cell_offset), C.c_int64(M_total)))

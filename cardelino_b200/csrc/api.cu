@@ -61,6 +61,7 @@ struct NcclApi {
     int (*GetUniqueId)(void*) = nullptr;
     int (*CommInitRank)(void**, int, Id128, int) = nullptr;
     int (*AllReduce)(const void*, void*, size_t, int, int, void*, cudaStream_t) = nullptr;
+    int (*AllGather)(const void*, void*, size_t, int, void*, cudaStream_t) = nullptr;
     int (*CommDestroy)(void*) = nullptr;
     const char* (*GetErrorString)(int) = nullptr;
 };
@@ -103,6 +104,11 @@ struct cdl_handle_s {
     void* comm = nullptr;
     int rank = 0, world = 1;
     int64_t launches = 0;
+    // statistic-table exchange of cell-sharded runs: peer memory (fused into k_table) or NCCL all-reduce
+    int exchange_mode = CDL_EXCHANGE_AUTO;
+    P2PState p2p;
+    bool p2p_active = false;
+    std::vector<void*> p2p_opened;       // cudaIpcOpenMemHandle mappings to close
     int cells_layout = CDL_CELLS_AUTO;   // cdl_set_cells_layout
     bool use_sell = false;               // decided per run
 };
@@ -144,6 +150,7 @@ void nccl_load(cdl_handle h, const char* path) {
     h->nccl.GetUniqueId = (int (*)(void*))dlsym(lib, "ncclGetUniqueId");
     h->nccl.CommInitRank = (int (*)(void**, int, Id128, int))dlsym(lib, "ncclCommInitRank");
     h->nccl.AllReduce = (int (*)(const void*, void*, size_t, int, int, void*, cudaStream_t))dlsym(lib, "ncclAllReduce");
+    h->nccl.AllGather = (int (*)(const void*, void*, size_t, int, void*, cudaStream_t))dlsym(lib, "ncclAllGather");
     h->nccl.CommDestroy = (int (*)(void*))dlsym(lib, "ncclCommDestroy");
     h->nccl.GetErrorString = (const char* (*)(int))dlsym(lib, "ncclGetErrorString");
     if (!h->nccl.GetUniqueId || !h->nccl.CommInitRank || !h->nccl.AllReduce || !h->nccl.CommDestroy)
@@ -260,6 +267,86 @@ void dic_from_trace(const std::vector<double>& ll, double logLik_post, double ou
     out[0] = DICG; out[1] = var; out[2] = -2 * m; out[3] = -2 * logLik_post; out[4] = DICG; out[5] = DICS;
 }
 
+constexpr int NCCL_U8 = 1, NCCL_MIN = 3;   // ncclUint8 / ncclMin (nccl.h)
+
+void p2p_release(cdl_handle h) {
+    for (void* q : h->p2p_opened) cudaIpcCloseMemHandle(q);
+    h->p2p_opened.clear();
+    cudaFree(h->p2p.arena); cudaFree(h->p2p.my_flags); cudaFree(h->p2p.error);
+    h->p2p = P2PState();
+    h->p2p_active = false;
+}
+
+// Collective over the ranks: make sure every rank owns a table arena of `elems` uint64 per buffer and has the
+// peers' arenas and flag arrays mapped.  Falls back to the NCCL all-reduce (on ALL ranks) if any rank cannot
+// map peer memory.  Returns whether the peer-memory exchange is active.
+bool p2p_ensure(cdl_handle h, size_t elems) {
+    if (h->world <= 1 || h->exchange_mode == CDL_EXCHANGE_NCCL || h->world - 1 > MAX_PEERS || !h->nccl.AllGather) {
+        if (h->exchange_mode == CDL_EXCHANGE_PEER && h->world > 1)
+            throw Error(CDL_ERR_COMM, "peer-memory exchange requested but not available (world size or NCCL symbols)");
+        return false;
+    }
+    if (h->p2p_active && h->p2p.table_elems == elems) return true;
+    p2p_release(h);
+    P2PState& q = h->p2p;
+    int ok = 1;
+    struct Pack { cudaIpcMemHandle_t arena, flags; };
+    Pack mine{};
+    q.table_elems = elems; q.my_rank = h->rank; q.n_peer = h->world - 1;
+    if (cudaMalloc(&q.arena, sizeof(unsigned long long) * 2 * elems) != cudaSuccess ||
+        cudaMalloc(&q.my_flags, sizeof(unsigned long long) * (size_t)h->world) != cudaSuccess ||
+        cudaMalloc(&q.error, sizeof(unsigned int)) != cudaSuccess) ok = 0;
+    if (ok) {
+        cudaMemsetAsync(q.arena, 0, sizeof(unsigned long long) * 2 * elems, h->st);
+        cudaMemsetAsync(q.my_flags, 0, sizeof(unsigned long long) * (size_t)h->world, h->st);
+        cudaMemsetAsync(q.error, 0, sizeof(unsigned int), h->st);
+        if (cudaIpcGetMemHandle(&mine.arena, q.arena) != cudaSuccess ||
+            cudaIpcGetMemHandle(&mine.flags, q.my_flags) != cudaSuccess) ok = 0;
+    }
+    cudaGetLastError();
+    // exchange the handles with the communicator we already have
+    std::vector<Pack> all((size_t)h->world);
+    {
+        DevBuf<uint8_t> snd(sizeof(Pack)), rcv(sizeof(Pack) * (size_t)h->world);
+        snd.upload(reinterpret_cast<const uint8_t*>(&mine), sizeof(Pack), h->st);
+        nccl_check(h, h->nccl.AllGather(snd.p, rcv.p, sizeof(Pack), NCCL_U8, h->comm, h->st), "ncclAllGather(ipc handles)");
+        rcv.download(reinterpret_cast<uint8_t*>(all.data()), sizeof(Pack) * (size_t)h->world, h->st);
+    }
+    int slot = 0;
+    for (int r = 0; r < h->world && ok; ++r) {
+        if (r == h->rank) continue;
+        void *pa = nullptr, *pf = nullptr;
+        if (cudaIpcOpenMemHandle(&pa, all[(size_t)r].arena, cudaIpcMemLazyEnablePeerAccess) != cudaSuccess) { ok = 0; break; }
+        h->p2p_opened.push_back(pa);
+        if (cudaIpcOpenMemHandle(&pf, all[(size_t)r].flags, cudaIpcMemLazyEnablePeerAccess) != cudaSuccess) { ok = 0; break; }
+        h->p2p_opened.push_back(pf);
+        q.peer_arena[slot] = (unsigned long long*)pa;
+        q.peer_flags[slot] = (unsigned long long*)pf;
+        q.peer_rank[slot] = r;
+        ++slot;
+    }
+    cudaGetLastError();
+    // every rank must take the same path
+    {
+        DevBuf<uint8_t> f(1);
+        const uint8_t v = (uint8_t)ok;
+        f.upload(&v, 1, h->st);
+        nccl_check(h, h->nccl.AllReduce(f.p, f.p, 1, NCCL_U8, NCCL_MIN, h->comm, h->st), "ncclAllReduce(p2p ok)");
+        uint8_t all_ok = 0;
+        f.download(&all_ok, 1, h->st);
+        ok = all_ok;
+    }
+    if (!ok) {
+        p2p_release(h);
+        if (h->exchange_mode == CDL_EXCHANGE_PEER)
+            throw Error(CDL_ERR_COMM, "peer-memory exchange requested but cudaIpc mapping failed on some rank");
+        return false;
+    }
+    q.epoch = 0;
+    h->p2p_active = true;
+    return true;
+}
+
 void one_sweep(cdl_handle h, Chain& ch, SweepArgs& a, uint32_t it, const cdl_replay* rp_dev, int64_t n_el) {
     a.it = it;
     const cdl_gibbs_params& gp = h->gp;
@@ -274,10 +361,24 @@ void one_sweep(cdl_handle h, Chain& ch, SweepArgs& a, uint32_t it, const cdl_rep
     }
     if (h->use_sell) launch_cells_sell(h->donor, a, ch.dev, h->sm_count, h->st);
     else launch_cells(h->donor, a, ch.dev, h->sm_count, h->st);
-    launch_stats(h->donor, a, ch.dev, h->sm_count, h->st);
-    allreduce_u64(h, ch.dev.sab, (size_t)(a.N * a.K));
-    launch_table(h->donor, a, ch.dev, h->st);
-    h->launches += 3;   // k_cells / k_cells_sell, k_stats, k_table (+ memset nodes)
+    if (h->p2p_active) {
+        // statistic table into this sweep's half of the peer-visible arena; publish; the table kernel sums
+        // the peers' halves while it reads them (no collective call)
+        P2PState& q = h->p2p;
+        ++q.epoch;
+        ch.dev.sab = q.arena + (size_t)(q.epoch & 1ull) * q.table_elems;
+        a.p2p = &q;
+        launch_stats(h->donor, a, ch.dev, h->sm_count, h->st);
+        launch_signal(q, h->st);
+        launch_table(h->donor, a, ch.dev, h->st);
+        h->launches += 4;   // + k_signal
+    } else {
+        a.p2p = nullptr;
+        launch_stats(h->donor, a, ch.dev, h->sm_count, h->st);
+        allreduce_u64(h, ch.dev.sab, (size_t)(a.N * a.K));
+        launch_table(h->donor, a, ch.dev, h->st);
+        h->launches += 3;   // k_cells / k_cells_sell, k_stats, k_table (+ memset nodes)
+    }
 }
 
 double geweke_fraction(cdl_handle h, Chain& ch, int64_t n_rows, DevBuf<unsigned long long>& counts) {
@@ -336,6 +437,7 @@ int cdl_create(int device, cdl_handle* out) {
 int cdl_destroy(cdl_handle h) {
     if (!h) return CDL_OK;
     cudaSetDevice(h->device);
+    p2p_release(h);
     if (h->comm && h->nccl.CommDestroy) h->nccl.CommDestroy(h->comm);
     h->chains.clear();
     donor_free(h->donor);
@@ -490,6 +592,17 @@ int cdl_set_cells_layout(cdl_handle h, int32_t layout) {
     });
 }
 
+int cdl_set_exchange_mode(cdl_handle h, int32_t mode) {
+    return guard(h, [&] {
+        if (mode != CDL_EXCHANGE_AUTO && mode != CDL_EXCHANGE_NCCL && mode != CDL_EXCHANGE_PEER)
+            throw Error(CDL_ERR_INVALID, "unknown exchange mode");
+        h->exchange_mode = mode;
+        if (mode == CDL_EXCHANGE_NCCL) p2p_release(h);
+    });
+}
+
+int cdl_exchange_is_peer(cdl_handle h) { return (h && h->p2p_active) ? 1 : 0; }
+
 int cdl_comm_unique_id(cdl_handle h, const char* nccl_lib_path, uint8_t* id128) {
     return guard(h, [&] {
         nccl_load(h, nccl_lib_path);
@@ -559,6 +672,7 @@ int cdl_gibbs_run(cdl_handle h, const double* Config, int32_t K, const double* P
         h->use_sell = h->cells_layout == CDL_CELLS_SLICES ||
                       (h->cells_layout == CDL_CELLS_AUTO && d.M_total >= 16384);
         if (h->use_sell) donor_build_sell(h->donor, h->st);
+        p2p_ensure(h, (size_t)(d.N * K));
         const int64_t N = d.N, M = d.M, T = gp.max_iter;
         const int64_t n_el = gp.wise == CDL_WISE_VARIANT ? N : 1;
         h->T = T;
@@ -718,7 +832,14 @@ int cdl_gibbs_run(cdl_handle h, const double* Config, int32_t K, const double* P
             ch.done = true;
             h->chains.push_back(std::move(chp));
         }
+        if (h->p2p_active) {
+            unsigned int perr = 0;
+            CDL_CUDA(cudaMemcpyAsync(&perr, h->p2p.error, sizeof(perr), cudaMemcpyDeviceToHost, h->st));
+            CDL_CUDA(cudaStreamSynchronize(h->st));
+            if (perr) throw Error(CDL_ERR_COMM, "a peer rank's statistic table did not arrive (peer-memory exchange timed out)");
+        }
         a.rp_u_assign = a.rp_u_config = a.rp_theta0 = a.rp_theta1 = a.rp_relax_next = nullptr;
+        a.p2p = nullptr;
         h->sweep = a;
         h->have_sweep = true;
         CDL_CUDA(cudaStreamSynchronize(h->st));
@@ -966,8 +1087,18 @@ int cdl_bench_sweeps(cdl_handle h, int32_t warmup, int32_t n, float* ms_total, f
                 if (h->use_sell) launch_cells_sell(h->donor, a, ch.dev, h->sm_count, h->st);
                 else launch_cells(h->donor, a, ch.dev, h->sm_count, h->st);
                 CDL_CUDA(cudaEventRecord(ev[1], h->st));
-                launch_stats(h->donor, a, ch.dev, h->sm_count, h->st);
-                allreduce_u64(h, ch.dev.sab, (size_t)(a.N * a.K));
+                if (h->p2p_active) {
+                    P2PState& q = h->p2p;
+                    ++q.epoch;
+                    ch.dev.sab = q.arena + (size_t)(q.epoch & 1ull) * q.table_elems;
+                    a.p2p = &q;
+                    launch_stats(h->donor, a, ch.dev, h->sm_count, h->st);
+                    launch_signal(q, h->st);
+                } else {
+                    a.p2p = nullptr;
+                    launch_stats(h->donor, a, ch.dev, h->sm_count, h->st);
+                    allreduce_u64(h, ch.dev.sab, (size_t)(a.N * a.K));
+                }
                 CDL_CUDA(cudaEventRecord(ev[2], h->st));
                 launch_table(h->donor, a, ch.dev, h->st);
                 CDL_CUDA(cudaEventRecord(ev[3], h->st));

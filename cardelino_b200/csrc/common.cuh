@@ -167,6 +167,14 @@ __device__ __forceinline__ unsigned long long ld_peer_u64(const unsigned long lo
     asm volatile("ld.relaxed.sys.global.u64 %0, [%1];" : "=l"(r) : "l"(p));
     return r;
 }
+__device__ __forceinline__ unsigned long long ld_acquire_sys_u64(const unsigned long long* p) {
+    unsigned long long r;
+    asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(r) : "l"(p) : "memory");
+    return r;
+}
+__device__ __forceinline__ void st_release_sys_u64(unsigned long long* p, unsigned long long v) {
+    asm volatile("st.release.sys.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
+}
 // streaming 128-bit load, bypassing L1 allocation (read-once data)
 __device__ __forceinline__ uint4 ld_stream(const uint4* p) {
     uint4 r;

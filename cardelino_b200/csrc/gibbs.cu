@@ -372,9 +372,14 @@ struct TableParams {
     PhiloxKey key; uint32_t chain;
     const double* rp_u_config; const double* rp_theta0; const double* rp_theta1; const double* rp_relax_next;
     double* part_d; unsigned long long* part_u; unsigned int* ticket;
-    // cell-sharded runs with peer access: the other ranks' statistic tables, summed on the fly (else n_peer = 0)
+    // cell-sharded runs over peer memory (NVLink): the other ranks' statistic tables are summed on the fly
+    // once their "table of sweep `epoch` is complete" flags have arrived (else n_peer = 0)
     int n_peer;
     const unsigned long long* peer_sab[MAX_PEERS];
+    const unsigned long long* my_flags;       // [world] written by the peers into THIS rank's memory
+    int peer_rank[MAX_PEERS];
+    unsigned long long epoch;
+    unsigned int* p2p_error;                  // set to 1 if a peer's flag did not arrive in time
 };
 
 __device__ __forceinline__ unsigned long long block_sum_u64(unsigned long long v, unsigned long long* sm) {
@@ -426,6 +431,20 @@ __global__ void __launch_bounds__(TABLE_THREADS) k_table(const TableParams P) {
     unsigned long long S1 = 0, S2 = 0, S3 = 0, S4 = 0, diff1 = 0;
     double ll = 0.0;
     uint32_t bitk = 0;
+    if (P.n_peer > 0) {
+        // fused all-reduce: wait until every peer has published its table of this sweep (k_signal on the peer,
+        // after its k_stats), then read the peers' tables straight over NVLink below.  Bounded spin: a peer
+        // that died must not hang this GPU.
+        if ((int)threadIdx.x < P.n_peer) {
+            const unsigned long long* f = P.my_flags + P.peer_rank[threadIdx.x];
+            const long long t0 = clock64();
+            while (ld_acquire_sys_u64(f) < P.epoch) {
+                if (clock64() - t0 > 20000000000ll) { atomicExch(P.p2p_error, 1u); break; }   // ~10 s
+                __nanosleep(100);
+            }
+        }
+        __syncthreads();
+    }
     if (i < P.N && k < P.K) {
         const int64_t t = P.wise == 1 ? i : 0;
         const double l1 = P.l1[t], l1c = P.l1c[t];
@@ -576,6 +595,21 @@ __global__ void __launch_bounds__(TABLE_THREADS) k_table(const TableParams P) {
                                           : beta_from_gammas(s_gam[2 * VPB + 2], s_gam[2 * VPB + 3]);
         P.scal[SC_RELAX] = rr;
         P.relax_all[row + 1] = rr;
+    }
+}
+
+// After this rank's k_stats: tell every peer that the table of sweep `epoch` in this rank's arena is complete.
+// The table was written with device-scope atomics into this GPU's memory; peers read it through NVLink from
+// this GPU's L2, the coherence point, so a system-scope fence + release store of the flag is sufficient.
+struct SignalParams {
+    int n_peer, my_rank;
+    unsigned long long* peer_flags[MAX_PEERS];   // flag arrays in the peers' memory
+    unsigned long long epoch;
+};
+__global__ void k_signal(const SignalParams P) {
+    if ((int)threadIdx.x < P.n_peer) {
+        __threadfence_system();
+        st_release_sys_u64(P.peer_flags[threadIdx.x] + P.my_rank, P.epoch);
     }
 }
 
@@ -782,6 +816,14 @@ void launch_stats(const Donor& d, const SweepArgs& a, ChainDev& c, int sm_count,
     CDL_CUDA(cudaGetLastError());
 }
 
+void launch_signal(const P2PState& q, cudaStream_t st) {
+    SignalParams P{};
+    P.n_peer = q.n_peer; P.my_rank = q.my_rank; P.epoch = q.epoch;
+    for (int r = 0; r < q.n_peer; ++r) P.peer_flags[r] = q.peer_flags[r];
+    k_signal<<<1, 32, 0, st>>>(P);
+    CDL_CUDA(cudaGetLastError());
+}
+
 void launch_table(const Donor& d, const SweepArgs& a, ChainDev& c, cudaStream_t st) {
     TableParams P{};
     P.N = d.N; P.K = a.K; P.wise = a.wise; P.relax = a.relax; P.keep_base = a.keep_base;
@@ -800,6 +842,17 @@ void launch_table(const Donor& d, const SweepArgs& a, ChainDev& c, cudaStream_t 
     P.rp_relax_next = a.rp_relax_next;
     P.part_d = c.part_d; P.part_u = c.part_u; P.ticket = c.ticket;
     P.n_peer = 0;
+    if (a.p2p && a.p2p->n_peer > 0) {
+        const P2PState& q = *a.p2p;
+        P.n_peer = q.n_peer;
+        for (int r = 0; r < q.n_peer; ++r) {
+            P.peer_sab[r] = q.peer_arena[r] + (size_t)(q.epoch & 1ull) * q.table_elems;
+            P.peer_rank[r] = q.peer_rank[r];
+        }
+        P.my_flags = q.my_flags;
+        P.epoch = q.epoch;
+        P.p2p_error = q.error;
+    }
     const int KP = pad_k(a.K);
     const int vpb = TABLE_THREADS / KP;
     const unsigned grid = (unsigned)((d.N + vpb - 1) / vpb);

@@ -105,6 +105,23 @@ enum {
     SC_N
 };
 
+// Peer-memory exchange of the statistic table between the ranks of one NVSwitch box (cell-sharded runs).
+// Every rank owns an arena [2][table_elems] (double-buffered by sweep parity) that the chain's k_stats fills,
+// and a flag array [world] that the PEERS write.  k_signal publishes "sweep `epoch` complete" into the peers'
+// flag arrays; k_table waits for all flags and sums the peers' tables while it reads them -- the all-reduce
+// is fused into the table kernel, no NCCL call per sweep.
+struct P2PState {
+    int n_peer = 0, my_rank = 0;
+    unsigned long long* arena = nullptr;             // this rank's [2][table_elems]
+    unsigned long long* my_flags = nullptr;          // [world]
+    unsigned long long* peer_arena[MAX_PEERS] = {};  // mapped with cudaIpcOpenMemHandle
+    unsigned long long* peer_flags[MAX_PEERS] = {};
+    int peer_rank[MAX_PEERS] = {};
+    size_t table_elems = 0;
+    unsigned long long epoch = 0;                    // sweeps since the arena was mapped (same on every rank)
+    unsigned int* error = nullptr;
+};
+
 struct SweepArgs {
     int64_t N, M, M_total, cell_offset;
     int K, KP;
@@ -123,6 +140,7 @@ struct SweepArgs {
     // replay (device pointers to row `it-1`), nullptr = own draws
     const double* rp_u_assign; const double* rp_u_config;
     const double* rp_theta0; const double* rp_theta1; const double* rp_relax_next;
+    const P2PState* p2p;        // non-null: statistic tables are exchanged over peer memory
 };
 
 struct KernelTimes { float cells = 0, stats = 0, table = 0; };
@@ -133,6 +151,7 @@ void launch_cells(const Donor& d, const SweepArgs& a, ChainDev& c, int sm_count,
 void launch_cells_sell(const Donor& d, const SweepArgs& a, ChainDev& c, int sm_count, cudaStream_t st);
 void launch_stats(const Donor& d, const SweepArgs& a, ChainDev& c, int sm_count, cudaStream_t st);
 void launch_table(const Donor& d, const SweepArgs& a, ChainDev& c, cudaStream_t st);
+void launch_signal(const P2PState& q, cudaStream_t st);
 
 // post-processing
 void launch_geweke(const double* prob_all, int64_t cols, int64_t n_rows, unsigned long long* counts2,

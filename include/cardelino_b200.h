@@ -137,6 +137,14 @@ int cdl_set_cells_layout(cdl_handle h, int32_t layout);
  * ncclUniqueId broadcast by the host plumbing.  cdl_comm_unique_id fills it on rank 0. */
 int cdl_comm_unique_id(cdl_handle h, const char* nccl_lib_path, uint8_t* id128);
 int cdl_comm_init(cdl_handle h, const char* nccl_lib_path, const uint8_t* id128, int32_t rank, int32_t world);
+/* How the per-sweep N x K statistic table is summed over the ranks: PEER = every rank's table lives in a
+ * cudaIpc-shared arena and the table kernel sums the peers' tables over NVLink while it reads them (flags in
+ * peer memory order the sweeps; no collective call per sweep); NCCL = one ncclAllReduce per sweep; AUTO = PEER
+ * when every rank can map its peers (one NVSwitch box, <= 8 ranks, one rank per GPU), else NCCL.  Must be set
+ * identically on every rank before cdl_gibbs_run.  Integer sums: both give bit-identical chains. */
+enum { CDL_EXCHANGE_AUTO = 0, CDL_EXCHANGE_NCCL = 1, CDL_EXCHANGE_PEER = 2 };
+int cdl_set_exchange_mode(cdl_handle h, int32_t mode);
+int cdl_exchange_is_peer(cdl_handle h);   /* 1 if the last cdl_gibbs_run used the peer-memory exchange */
 
 /* ---- clone_id_Gibbs (R/clone_id.R:351-675) ---- */
 void cdl_gibbs_defaults(cdl_gibbs_params* p);

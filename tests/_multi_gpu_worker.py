@@ -1,0 +1,69 @@
+"""Worker of tests/test_multi_gpu.py (run under torch.distributed.run, one rank per GPU).
+
+Every rank holds a contiguous cell shard of one synthetic donor.  The sharded chain is run twice -- with
+the NCCL all-reduce of the statistic table and with the peer-memory exchange fused into the table kernel --
+and rank 0 also runs the WHOLE donor on its own GPU without any communicator.  All three must give the
+same labels, Config flips, theta traces and logLik trace bit for bit (integer statistics, Philox keyed by
+global cell id)."""
+import json
+import os
+import sys
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+
+
+def main():
+    import torch
+    import torch.distributed as dist
+    import cardelino_b200 as cb
+    from cardelino_b200 import distributed as D
+    import bench
+
+    rank, world, local = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"]), int(os.environ["LOCAL_RANK"])
+    torch.cuda.set_device(local)
+    dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    N, M, K, cov, T = 600, 50000, 8, 0.1, 10
+    cfg = bench.make_config(N, K, seed=3)
+    lo, hi = D.shard_bounds(M, world)[rank]
+    h = cb.Handle(local)
+    D.init_comm(h)
+    h.synth_generate(N, M, K, cfg, cov, 99, cell_offset=lo, M_local=hi - lo)
+    out = {}
+    for mode in ("nccl", "peer"):
+        h.set_exchange_mode(mode)
+        h.gibbs_run(cfg, None, min_iter=T, max_iter=T, seed=4, keep_prob_all=1, keep_assign_all=1)
+        assert h.exchange_is_peer() == (mode == "peer"), mode
+        z = torch.from_numpy(h.fetch("assign_all").astype(np.int32)).cuda()          # T x M_local
+        parts = [torch.empty((T, b - a), dtype=torch.int32, device="cuda") for a, b in D.shard_bounds(M, world)]
+        dist.all_gather(parts, z)
+        out[mode] = {"z": torch.cat(parts, dim=1).cpu().numpy(), "cfg": h.fetch("Config_all"),
+                     "ll": h.fetch("logLik"), "t0": h.fetch("theta_traces")[0], "t1": h.fetch("theta_traces")[1]}
+    ok = True
+    msg = []
+    if rank == 0:
+        full = cb.Handle(local)
+        full.synth_generate(N, M, K, cfg, cov, 99)
+        full.gibbs_run(cfg, None, min_iter=T, max_iter=T, seed=4, keep_prob_all=1, keep_assign_all=1)
+        ref = {"z": full.fetch("assign_all"), "cfg": full.fetch("Config_all"), "ll": full.fetch("logLik"),
+               "t0": full.fetch("theta_traces")[0], "t1": full.fetch("theta_traces")[1]}
+        for mode in out:
+            for key in ("z", "cfg", "t0", "t1"):
+                if not np.array_equal(out[mode][key], ref[key]):
+                    ok = False
+                    msg.append("%s/%s differs from the single-GPU chain" % (mode, key))
+            # logLik: each rank adds its shard's W_log in a different order -> equal to rounding
+            if not np.allclose(out[mode]["ll"], ref["ll"], rtol=1e-12, atol=0):
+                ok = False
+                msg.append("%s/logLik differs" % mode)
+        print(json.dumps({"ok": ok, "world": world, "messages": msg}))
+    dist.barrier()
+    dist.destroy_process_group()
+    if rank == 0 and not ok:
+        sys.exit(1)
+
+
+if __name__ == "__main__":
+    main()
