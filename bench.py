@@ -25,6 +25,7 @@ WORKLOADS = {
     # name: (N variants, M cells, K clones, coverage)
     "C4": (10000, 1000000, 16, 0.05),     # BASELINE.json configs[3], the metric's configuration
     "C3": (2000, 100000, 8, 0.19),        # configs[2] (sim_read_count-shaped 19 % coverage)
+    "C4s8": (10000, 125000, 16, 0.05),    # one rank's share of C4 at 8 GPUs (tuning aid)
     "tiny": (200, 4000, 4, 0.2),
 }
 SEED_DATA = 20261019 + 4
@@ -155,12 +156,14 @@ def run_ours(args):
             torch.cuda.synchronize()
 
     sampler = ClockSampler(local) if rank == 0 else None
-    barrier()
-    h.bench_sweeps(args.warmup, 0, breakdown=False)
-    barrier()
     if sampler:
         sampler.start()
-    r = h.bench_sweeps(0, args.steps, breakdown=False)
+    barrier()
+    # W untimed warm-up sweeps and the K timed sweeps are enqueued by ONE library call: the CUDA events that
+    # bracket the K sweeps are recorded on the stream right after the warm-up sweeps, whose per-sweep exchange
+    # has already aligned the ranks -- otherwise the few milliseconds of host-side skew between the ranks'
+    # Python processes would be charged to the first timed sweep.  barrier + synchronize on both sides.
+    r = h.bench_sweeps(args.warmup, args.steps, breakdown=False)
     barrier()
     clocks = sampler.stop() if sampler else None
     ms = torch.tensor([r["ms_total"]], dtype=torch.float64, device="cuda")
@@ -182,7 +185,10 @@ def run_ours(args):
     # ---- end to end through the public API with host buffers (load + T sweeps + fetch) ----
     e2e = None
     if not args.no_e2e:
-        p, i, a, d = h.export_csc_u16()
+        def pinned(x):      # the donor sits in PINNED host memory, as the bench contract asks
+            return torch.from_numpy(x.view(np.uint8)).pin_memory().numpy().view(x.dtype)
+
+        p, i, a, d = [pinned(x) for x in h.export_csc_u16()]
         counts = cb.SparseCounts(N, Ml, p, i, a, d, cell_offset=off, M_total=M)
         T = args.e2e_iters
         barrier()
@@ -319,7 +325,8 @@ def main():
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--workload", default="C4", choices=list(WORKLOADS))
-    ap.add_argument("--e2e-iters", type=int, default=200)
+    ap.add_argument("--e2e-iters", type=int, default=1000,
+                    help="sweeps of the end-to-end clone_id_Gibbs call (the reference default is min_iter=5000)")
     ap.add_argument("--cpu-cells", type=int, default=64)
     ap.add_argument("--cpu-iters", type=int, default=2)
     ap.add_argument("--exchange", default="auto", choices=["auto", "nccl", "peer"],
@@ -329,10 +336,37 @@ def main():
     args = ap.parse_args()
     if args.warmup < 3 and args.impl == "ours":
         args.warmup = 3
-    if args.impl == "reference":
-        run_reference(args)
-    else:
-        run_ours(args)
+    # stdout carries exactly ONE JSON line: anything libraries print while we work (NCCL's version banner,
+    # torchrun notices) goes to stderr instead
+    sys.stdout.flush()
+    real_stdout = os.dup(1)
+    os.dup2(2, 1)
+    lines = []
+    real_print = print
+
+    def capture(*a, **k):
+        if k.get("file") in (None, sys.stdout):
+            lines.append(" ".join(str(x) for x in a))
+        else:
+            real_print(*a, **k)
+
+    import builtins
+    builtins.print = capture
+    try:
+        if args.impl == "reference":
+            run_reference(args)
+        else:
+            run_ours(args)
+    finally:
+        builtins.print = real_print
+        sys.stdout.flush()
+        os.dup2(real_stdout, 1)
+        os.close(real_stdout)
+    for ln in lines:
+        if ln.startswith("{"):
+            real_print(ln, flush=True)
+        else:
+            real_print(ln, file=sys.stderr, flush=True)
 
 
 if __name__ == "__main__":

@@ -72,7 +72,8 @@ struct Chain {
     DevBuf<uint32_t> mask;
     DevBuf<uint8_t> z, config_all, assign_all;
     DevBuf<unsigned long long> sab, part_u;
-    DevBuf<unsigned int> ticket, work;
+    DevBuf<unsigned int> ticket, work, sell_tickets, stats_work;
+    DevBuf<double> sell_scratch;
     DevBuf<double2> tab_g;
     // summaries
     DevBuf<double> prob_mean, config_prob, theta1_mean;
@@ -754,6 +755,7 @@ int cdl_gibbs_run(cdl_handle h, const double* Config, int32_t K, const double* P
             ch.part_d.alloc(tgrid * 4); ch.part_u.alloc(tgrid * 8);
             ch.ticket.alloc(1); ch.ticket.zero(h->st);
             ch.work.alloc(2); ch.work.zero(h->st);
+            ch.stats_work.alloc((size_t)d.n_cb); ch.stats_work.zero(h->st);
             ch.tab_g.alloc((size_t)N);
             ch.dev.scal = ch.scal.p; ch.dev.l1 = ch.l1.p; ch.dev.l1c = ch.l1c.p; ch.dev.mask = ch.mask.p;
             ch.dev.z = ch.z.p; ch.dev.sab = ch.sab.p;
@@ -766,6 +768,14 @@ int cdl_gibbs_run(cdl_handle h, const double* Config, int32_t K, const double* P
             ch.dev.part_d = ch.part_d.p; ch.dev.part_u = ch.part_u.p; ch.dev.ticket = ch.ticket.p;
             ch.dev.tab_g = ch.tab_g.p;
             ch.dev.work = ch.work.p;
+            ch.dev.stats_work = ch.stats_work.p;
+            ch.dev.sell_scratch = nullptr; ch.dev.sell_tickets = nullptr;
+            if (h->use_sell && d.s_slices < 64 * (int64_t)h->sm_count) {
+                const int KPs = K <= 4 ? 4 : (K <= 8 ? 8 : (K <= 16 ? 16 : 32));
+                ch.sell_scratch.alloc((size_t)d.s_slices * 4 * 32 * KPs);
+                ch.sell_tickets.alloc((size_t)d.s_slices); ch.sell_tickets.zero(h->st);
+                ch.dev.sell_scratch = ch.sell_scratch.p; ch.dev.sell_tickets = ch.sell_tickets.p;
+            }
 
             a.chain = (uint32_t)c;
             // initial draws (row 1)
@@ -1061,11 +1071,11 @@ int cdl_bench_sweeps(cdl_handle h, int32_t warmup, int32_t n, float* ms_total, f
         a.chain = 0;
         const uint32_t it = (uint32_t)h->T;     // keep overwriting the last trace row
         ch.dev.prob_acc = nullptr;
-        for (int w = 0; w < warmup; ++w) one_sweep(h, ch, a, it, nullptr, h->n_el);
         cudaEvent_t e0, e1;
         CDL_CUDA(cudaEventCreate(&e0));
         CDL_CUDA(cudaEventCreate(&e1));
-        CDL_CUDA(cudaStreamSynchronize(h->st));
+        // warm-up and timed sweeps go down the stream back to back; the start event sits between them
+        for (int w = 0; w < warmup; ++w) one_sweep(h, ch, a, it, nullptr, h->n_el);
         const int64_t l0 = h->launches;
         CDL_CUDA(cudaEventRecord(e0, h->st));
         for (int q = 0; q < n; ++q) one_sweep(h, ch, a, it, nullptr, h->n_el);

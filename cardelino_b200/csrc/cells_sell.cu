@@ -35,7 +35,13 @@ struct SellParams {
     const uint4* a8;
     const uint4* b8;
     int64_t n_slices;
-    unsigned int* work;          // dynamic slice counter (zeroed before the launch)
+    unsigned int* work;          // dynamic work-item counter (zeroed before the launch)
+    // small shards: a slice's groups are split over `parts` warps (work item = slice * parts + part); each
+    // part leaves its partial logits in `scratch`, the part that finishes last (ticket) adds them up in part
+    // order -- deterministic -- and runs the epilogue
+    int parts;
+    double* scratch;             // [n_slices][parts][32][KP]
+    unsigned int* tickets;       // [n_slices], zero between launches
 };
 
 // acc[k] += bit_q(bits) ? del : 0 for NK clones starting at K0.  Written as a branch around the add in
@@ -97,7 +103,7 @@ __device__ __forceinline__ void sell_group(double (&acc)[KP], const Grp<VIdx>& q
     }
 }
 
-template <int KP, typename VIdx, bool SMEM, int SELL_THREADS, int SELL_DEPTH>
+template <int KP, typename VIdx, bool SMEM, int SELL_THREADS, int SELL_DEPTH, bool SPLIT>
 __global__ void __launch_bounds__(SELL_THREADS, 1) k_cells_sell(const SellParams P) {
     constexpr bool PACKED = KP <= 16;
     extern __shared__ __align__(16) unsigned char smem_raw[];
@@ -133,9 +139,16 @@ __global__ void __launch_bounds__(SELL_THREADS, 1) k_cells_sell(const SellParams
         unsigned int s_u = 0;
         if (lane == 0) s_u = atomicAdd(P.work, 1u);
         s_u = __shfl_sync(0xffffffffu, s_u, 0);
-        const int64_t s = s_u;
+        const int parts = SPLIT ? P.parts : 1;
+        const int64_t s = (int64_t)(s_u / (unsigned int)parts);
+        const int part = (int)(s_u - (unsigned int)s * (unsigned int)parts);
         if (s >= P.n_slices) break;
-        const int64_t g0 = P.slice_off[s], g1 = P.slice_off[s + 1];
+        int64_t g0 = P.slice_off[s], g1 = P.slice_off[s + 1];
+        if (SPLIT && parts > 1) {
+            const int64_t len = g1 - g0;
+            g1 = g0 + (len * (part + 1)) / parts;
+            g0 = g0 + (len * part) / parts;
+        }
         const uint32_t jl = P.perm[s * 32 + lane];
         const bool valid = jl != 0xffffffffu;
         double acc[KP];
@@ -158,6 +171,28 @@ __global__ void __launch_bounds__(SELL_THREADS, 1) k_cells_sell(const SellParams
                 if (h == 0 || g + h < g1) sell_group<KP, VIdx, SMEM, PACKED>(acc, q[h], tab_sa, msk_sa, tab_g, msk_g);
 #pragma unroll
             for (int h = 0; h < SELL_DEPTH; ++h) q[h] = n[h];
+        }
+        if (SPLIT && parts > 1) {
+            double* mine = P.scratch + (((size_t)s * parts + part) * 32 + lane) * KP;
+#pragma unroll
+            for (int k = 0; k < KP; k += 2) __stcg(reinterpret_cast<double2*>(mine + k), make_double2(acc[k], acc[k + 1]));
+            __threadfence();
+            unsigned int tk = 0;
+            if (lane == 0) tk = atomicAdd(P.tickets + s, 1u);
+            tk = __shfl_sync(0xffffffffu, tk, 0);
+            if (tk != (unsigned int)(parts - 1)) continue;        // another part finishes this slice
+            __threadfence();
+            if (lane == 0) P.tickets[s] = 0;
+#pragma unroll
+            for (int k = 0; k < KP; ++k) acc[k] = 0.0;
+            for (int q = 0; q < parts; ++q) {                      // fixed order: bit-reproducible
+                const double* src = P.scratch + (((size_t)s * parts + q) * 32 + lane) * KP;
+#pragma unroll
+                for (int k = 0; k < KP; k += 2) {
+                    const double2 t = __ldcg(reinterpret_cast<const double2*>(src + k));
+                    acc[k] += t.x; acc[k + 1] += t.y;
+                }
+            }
         }
         // ---- softmax over the lane's own K logits (:479-481) ----
         double mx = -INFINITY;
@@ -340,14 +375,31 @@ __global__ void k_sell_fill(const uint32_t* __restrict__ rowgrp, const uint32_t*
     }
 }
 
+// Warps per CTA (one CTA per SM): slices are handed out dynamically, one per warp at a time, so a launch takes
+// ceil(slices per SM / warps) rounds.  With few slices per SM (a 1/8 shard of C4 has 26) a full CTA of 24
+// warps would run one full round and a nearly empty second one; using just enough warps to fill the same
+// number of rounds evenly removes that tail.
+inline int sell_warps(int64_t n_items, int grid, int max_warps) {
+    const int64_t per_sm = (n_items + grid - 1) / grid;
+    const int64_t rounds = (per_sm + max_warps - 1) / max_warps;
+    int64_t w = (per_sm + rounds - 1) / rounds;
+    if (w < 4) w = 4;
+    if (w > max_warps) w = max_warps;
+    return (int)w;
+}
+
 template <int KP, typename VIdx, int THREADS, int DEPTH>
 void launch_sell_t(const SellParams& P, bool smem_tab, size_t smem, int grid, cudaStream_t st) {
+    const int threads = 32 * sell_warps(P.n_slices * P.parts, grid, THREADS / 32);
     if (smem_tab) {
-        auto kern = k_cells_sell<KP, VIdx, true, THREADS, DEPTH>;
+        auto kern = P.parts > 1 ? k_cells_sell<KP, VIdx, true, THREADS, DEPTH, true>
+                                : k_cells_sell<KP, VIdx, true, THREADS, DEPTH, false>;
         CDL_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        kern<<<grid, THREADS, smem, st>>>(P);
+        kern<<<grid, threads, smem, st>>>(P);
+    } else if (P.parts > 1) {
+        k_cells_sell<KP, VIdx, false, THREADS, DEPTH, true><<<grid, threads, 0, st>>>(P);
     } else {
-        k_cells_sell<KP, VIdx, false, THREADS, DEPTH><<<grid, THREADS, 0, st>>>(P);
+        k_cells_sell<KP, VIdx, false, THREADS, DEPTH, false><<<grid, threads, 0, st>>>(P);
     }
 }
 
@@ -356,7 +408,6 @@ void launch_sell_v(const Donor& d, const SellParams& P, bool smem_tab, size_t sm
                    cudaStream_t st) {
     if (d.vidx32) { launch_sell_t<KP, uint32_t, 512, 2>(P, smem_tab, smem, grid, st); return; }
     if (shape == 1) launch_sell_t<KP, uint16_t, 768, 1>(P, smem_tab, smem, grid, st);
-    else if (shape == 2) launch_sell_t<KP, uint16_t, 1024, 1>(P, smem_tab, smem, grid, st);
     else launch_sell_t<KP, uint16_t, 512, 2>(P, smem_tab, smem, grid, st);
 }
 
@@ -445,6 +496,15 @@ void launch_cells_sell(const Donor& d, const SweepArgs& a, ChainDev& c, int sm_c
     P.v8 = nullptr; P.a8 = (const uint4*)d.s_a; P.b8 = (const uint4*)d.s_b;
     P.n_slices = d.s_slices;
     P.work = c.work;
+    // too few slices to give every SM a CTA's worth of warps: split each slice's groups over 2 or 4 warps
+    {
+        const int64_t per_sm = (d.s_slices + sm_count - 1) / sm_count;
+        P.parts = per_sm >= 20 ? 1 : (per_sm >= 10 ? 2 : 4);
+        if (const char* e = getenv("CDL_SELL_PARTS")) { const int v = atoi(e); if (v == 1 || v == 2 || v == 4) P.parts = v; }
+        if (P.parts > 1 && (!c.sell_scratch || !c.sell_tickets)) P.parts = 1;
+        P.scratch = c.sell_scratch;
+        P.tickets = c.sell_tickets;
+    }
     const int KP = a.K <= 4 ? 4 : (a.K <= 8 ? 8 : (a.K <= 16 ? 16 : 32));
     const bool packed = KP <= 16;
     const size_t smem = (size_t)d.N * (sizeof(double2) + (packed ? 0 : sizeof(uint32_t)));
@@ -459,10 +519,13 @@ void launch_cells_sell(const Donor& d, const SweepArgs& a, ChainDev& c, int sm_c
     }
     // 24 warps per SM with one group slot of look-ahead beat 16 warps with two (the kernel is bound by the
     // fp64 pipe and needs the extra warps to keep it fed); CDL_SELL_SHAPE overrides for experiments
+    // On a small shard that cannot fill 16 warps per SM anyway the extra warps buy nothing: take the
+    // 16-warp shape, whose two slots of look-ahead hide the HBM latency that few warps cannot.
     int shape = 1;
+    if (sell_warps(d.s_slices * P.parts, sm_count, 24) <= 16) shape = 0;
     if (const char* e = getenv("CDL_SELL_SHAPE")) shape = atoi(e);
     int64_t grid = sm_count;
-    const int threads = d.vidx32 ? 512 : (shape == 1 ? 768 : (shape == 2 ? 1024 : 512));
+    const int threads = d.vidx32 ? 512 : (shape == 1 ? 768 : 512);
     const int64_t max_useful = (d.s_slices + threads / 32 - 1) / (threads / 32);
     if (grid > max_useful) grid = std::max<int64_t>(max_useful, 1);
     switch (KP) {

@@ -156,7 +156,7 @@ double sum_doubles(const double* data, int64_t n, cudaStream_t st) {
 void donor_free(Donor& d) {
     donor_free_sell(d);
     cudaFree(d.c_rowgrp); cudaFree(d.c_vidx); cudaFree(d.c_a); cudaFree(d.c_b);
-    cudaFree(d.v_seggrp); cudaFree(d.v_flush); cudaFree(d.v_cell); cudaFree(d.v_a); cudaFree(d.v_b);
+    cudaFree(d.v_seggrp); cudaFree(d.v_flush); cudaFree(d.v_plan); cudaFree(d.v_cell); cudaFree(d.v_a); cudaFree(d.v_b);
     cudaFree(d.labels);
     d = Donor();
 }

@@ -14,6 +14,7 @@
 #include "internal.h"
 #include "cells.cuh"
 #include <cstdlib>
+#include <vector>
 
 namespace cdl {
 
@@ -213,10 +214,10 @@ struct StatsParams {
     unsigned long long* sab;
     int64_t N, M;
     int K;
-    int chunk;            // variants per work unit
-    int chunks_per_cb;    // units per cell block
-    int n_units;
-    unsigned int* work;   // dynamic unit counter (zeroed before the launch)
+    int n_cb;             // cell blocks
+    const int* plan;      // [grid + 2 * n_cb]: home block of each CTA, first CTA and CTA count of each block
+    int chunks_per_warp;  // 1: one static range per warp; > 1: ranges are pulled from the block's counter
+    unsigned int* work;   // [n_cb] chunk counters (zeroed before the launch; used when chunks_per_warp > 1)
 };
 
 // One 8-entry group of a variant segment into the lane-private clone bins.  A and B share one 32-bit bin
@@ -269,18 +270,21 @@ __device__ __forceinline__ void stats_flush(uint32_t* __restrict__ bins, int lan
     __syncwarp();
 }
 
-// Persistent CTAs pull (cell block, variant chunk) units from a counter, in cell-block-major order so the
-// block's labels are re-staged in shared memory only when the cell block changes.  Inside a unit each warp
-// owns whole variant segments; a lane keeps private per-clone bins in shared memory, so no atomics are
-// needed until the segment's K sums go to the global table.  The kernel is bound by the latency of the
-// shared-memory update chain as much as by HBM, so it runs 32 warps per SM (2 CTAs x 16 warps, <= 64
-// registers) with one group per lane prefetched ahead of the updates.
+// Every CTA stages the labels of ONE cell block in shared memory (CTAs are dealt to the cell blocks in
+// proportion to their entries; with more cell blocks than CTAs a CTA walks several).  The block's variant
+// segments are contiguous in memory, so the block's groups are cut into one contiguous range per warp and each
+// warp STREAMS its range: the loads of the next 32 groups are always in flight while the current 32 are binned,
+// across segment boundaries too, and the next 32 segment boundaries / flush intervals sit in one register per
+// lane (shuffled out as needed) -- no per-unit atomics or dependent metadata loads, which on a 1/8 shard cost
+// as much as the work itself.  A range may start or end inside a segment: the partial sums simply meet in the
+// global table (integer atomics, exact).  A lane keeps private per-clone bins in shared memory (A and B packed
+// 16 + 16 bits, flushed before either half can overflow).  32 warps per SM (2 CTAs x 16 warps, <= 64 registers):
+// the kernel is bound by the latency of the shared-memory update chain as much as by HBM.
 template <int KP>
-__global__ void __launch_bounds__(STATS_THREADS, 2) k_stats(const StatsParams P) {
+__global__ void __launch_bounds__(STATS_THREADS, 2) k_stats_stream(const StatsParams P) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     uint32_t* s_bins = reinterpret_cast<uint32_t*>(smem_raw);                  // [WARPS][KP][32]
     uint8_t* s_z = smem_raw + sizeof(uint32_t) * STATS_WARPS * KP * 32;        // [cells of the staged block]
-    __shared__ unsigned int s_unit;
     const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
     uint32_t* bins = s_bins + (size_t)w * KP * 32;
     const uint4* c8 = reinterpret_cast<const uint4*>(P.vc);
@@ -288,16 +292,21 @@ __global__ void __launch_bounds__(STATS_THREADS, 2) k_stats(const StatsParams P)
     const uint4* b8 = reinterpret_cast<const uint4*>(P.vb);
 #pragma unroll
     for (int q = 0; q < KP; ++q) bins[q * 32 + lane] = 0u;
-    int staged_cb = -1;
-    for (;;) {
-        __syncthreads();                       // everyone is done with the previous unit (and with s_unit)
-        if (threadIdx.x == 0) s_unit = atomicAdd(P.work, 1u);
-        __syncthreads();
-        const unsigned int u = s_unit;
-        if (u >= (unsigned int)P.n_units) break;
-        const int cb = (int)(u / (unsigned int)P.chunks_per_cb);
-        const int ch = (int)(u - (unsigned int)cb * (unsigned int)P.chunks_per_cb);
-        if (cb != staged_cb) {
+    const int G = (int)gridDim.x;
+    int cb, cb_step;
+    int64_t r, R;            // this warp's rank among the R warps that share the cell block
+    if (P.n_cb <= G) {
+        cb = P.plan[blockIdx.x];                                  // home block of this CTA
+        const int first = P.plan[G + cb], count = P.plan[G + P.n_cb + cb];
+        r = (int64_t)((int)blockIdx.x - first) * STATS_WARPS + w;
+        R = (int64_t)count * STATS_WARPS;
+        cb_step = P.n_cb;
+    } else {
+        cb = (int)blockIdx.x; cb_step = G; r = w; R = STATS_WARPS;
+    }
+    for (; cb < P.n_cb; cb += cb_step) {
+        __syncthreads();                       // all warps are done with the previous block's labels
+        {
             const int64_t c0 = (int64_t)cb * CELL_BLOCK;
             const int ncell = (int)min((int64_t)CELL_BLOCK, P.M - c0);
             const int nvec = ncell >> 4;
@@ -305,20 +314,166 @@ __global__ void __launch_bounds__(STATS_THREADS, 2) k_stats(const StatsParams P)
             uint4* dst = reinterpret_cast<uint4*>(s_z);
             for (int t = threadIdx.x; t < nvec; t += blockDim.x) dst[t] = src[t];
             for (int t = (nvec << 4) + threadIdx.x; t < ncell; t += blockDim.x) s_z[t] = P.z[c0 + t];
-            staged_cb = cb;
-            __syncthreads();
         }
-        const int64_t i_lo = (int64_t)ch * P.chunk;
-        const int64_t i_hi = min(P.N, i_lo + P.chunk);
-        for (int64_t i = i_lo + w; i < i_hi; i += STATS_WARPS) {
+        __syncthreads();
+        const uint32_t* sg = P.seggrp + (int64_t)cb * P.N;       // sg[0..N]: group offsets of the block's segments
+        const uint16_t* fl = P.flush + (int64_t)cb * P.N;
+        const int64_t G0 = sg[0], G1 = sg[P.N];
+        const int64_t n_chunks = R * P.chunks_per_warp;
+        for (int64_t pass = 0;; ++pass) {
+        // a large block is cut into a few chunks per warp that are pulled from the block's counter (the warps of
+        // a slower SM take fewer); a small one into exactly one static range per warp (no atomics at all)
+        int64_t ck = r;
+        if (P.chunks_per_warp > 1) {
+            unsigned int u = 0;
+            if (lane == 0) u = atomicAdd(P.work + cb, 1u);
+            ck = (int64_t)__shfl_sync(0xffffffffu, u, 0);
+        } else if (pass > 0) break;
+        if (ck >= n_chunks) break;
+        const int64_t lo = G0 + ((G1 - G0) * ck) / n_chunks, hi = G0 + ((G1 - G0) * (ck + 1)) / n_chunks;
+        if (lo >= hi) continue;
+        // segment that holds group `lo`: largest i with sg[i] <= lo (32-ary search, the lanes probe in parallel)
+        int64_t i = 0;
+        {
+            int64_t span = P.N;                 // answer in [i, i + span)
+            while (span > 1) {
+                const int64_t stepw = (span + 31) / 32;
+                const int64_t probe = min(i + stepw * lane, P.N - 1);
+                const bool le = (int64_t)sg[probe] <= lo && (i + stepw * lane) < i + span;
+                const unsigned m = __ballot_sync(0xffffffffu, le);
+                const int top = 31 - __clz((int)m);                // lane 0 always votes (sg[i] <= lo)
+                const int64_t ni = i + stepw * top;
+                span = min(stepw, i + span - ni);
+                i = ni;
+            }
+        }
+        // boundary window: lane l holds sg[win + 1 + l] (end of segment win + l) and fl[win + l]
+        int64_t win = i;
+        uint32_t wend = sg[min(win + 1 + lane, P.N)];
+        uint32_t wfl = fl[min(win + lane, P.N - 1)];
+        auto seg_end_of = [&](int64_t seg) -> int64_t {
+            return (int64_t)__shfl_sync(0xffffffffu, wend, (int)(seg - win));
+        };
+        int64_t cur = lo;
+        int64_t send = min(seg_end_of(i), hi);
+        while (send <= cur) {                  // cannot happen for i found above, but keep the invariant explicit
+            ++i;
+            if (i - win >= 32) { win = i; wend = sg[min(win + 1 + lane, P.N)]; wfl = fl[min(win + lane, P.N - 1)]; }
+            send = min(seg_end_of(i), hi);
+        }
+        int flush_every = (int)__shfl_sync(0xffffffffu, wfl, (int)(i - win));
+        int64_t gi = min(cur + lane, send - 1);
+        uint4 cw = ld_stream(c8 + gi), aw = ld_stream(a8 + gi), bw = ld_stream(b8 + gi);
+        int since = 0;
+        while (cur < hi) {
+            // where the NEXT iteration starts: the next 32 groups of this segment, or the start of the next
+            // non-empty segment
+            int64_t nbase, nsend = send, ni = i;
+            int nfl = flush_every;
+            const bool seg_done = cur + 32 >= send;
+            if (!seg_done) nbase = cur + 32;
+            else {
+                nbase = send;
+                if (nbase < hi) {
+                    do {
+                        ++ni;
+                        if (ni - win >= 32) { win = ni; wend = sg[min(win + 1 + lane, P.N)]; wfl = fl[min(win + lane, P.N - 1)]; }
+                        nsend = min(seg_end_of(ni), hi);
+                    } while (nsend <= nbase);
+                    nfl = (int)__shfl_sync(0xffffffffu, wfl, (int)(ni - win));
+                }
+            }
+            uint4 cn = cw, an = aw, bn = bw;
+            if (nbase < hi) {
+                gi = min(nbase + lane, nsend - 1);
+                cn = ld_stream(c8 + gi); an = ld_stream(a8 + gi); bn = ld_stream(b8 + gi);
+            }
+            unsigned long long* sab_row = P.sab + i * P.K;
+            if (cur + lane < send) {
+                if (flush_every) stats_group(cw, aw, bw, s_z, bins + lane);
+                else {
+                    // depths above 8191 in this segment: a single group could overflow a 16-bit half; take the
+                    // (rare) direct path, one 64-bit atomic per entry
+                    const uint32_t cc[4] = {cw.x, cw.y, cw.z, cw.w};
+                    const uint32_t aa[4] = {aw.x, aw.y, aw.z, aw.w};
+                    const uint32_t bb[4] = {bw.x, bw.y, bw.z, bw.w};
+#pragma unroll
+                    for (int e = 0; e < 8; ++e) {
+                        const uint32_t c = (e & 1) ? (cc[e >> 1] >> 16) : (cc[e >> 1] & 0xffffu);
+                        const unsigned long long a = (e & 1) ? (aa[e >> 1] >> 16) : (aa[e >> 1] & 0xffffu);
+                        const unsigned long long b = (e & 1) ? (bb[e >> 1] >> 16) : (bb[e >> 1] & 0xffffu);
+                        if (a | b) atomicAdd(&sab_row[s_z[c]], a | (b << 32));
+                    }
+                }
+            }
+            ++since;
+            if (flush_every && (seg_done || since == flush_every)) { stats_flush<KP>(bins, lane, P.K, sab_row); since = 0; }
+            if (seg_done) since = 0;
+            cw = cn; aw = an; bw = bn;
+            cur = nbase; send = nsend; i = ni; flush_every = nfl;
+        }
+        }   // chunks
+    }
+}
+
+// The same statistics for LARGE shards (many segments per warp): the warps pull whole variant segments (or
+// 1/parts of one) from the cell block's counter, each warp on its own.  One atomic and two dependent metadata
+// loads per unit are noise when a unit is a few thousand entries and 30+ units are queued per warp, and the
+// per-iteration bookkeeping is lighter than the streaming kernel's (C4 on one GPU: 0.51 ms vs 0.58 ms); on a
+// 1/8 shard or at C3 the streaming kernel wins by 15-25 %.  A CTA starts on its home block and then walks the
+// others, helping wherever units are left.
+template <int KP>
+__global__ void __launch_bounds__(STATS_THREADS, 2) k_stats_units(const StatsParams P) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    uint32_t* s_bins = reinterpret_cast<uint32_t*>(smem_raw);                  // [WARPS][KP][32]
+    uint8_t* s_z = smem_raw + sizeof(uint32_t) * STATS_WARPS * KP * 32;        // [cells of the staged block]
+    __shared__ unsigned int s_peek;
+    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+    uint32_t* bins = s_bins + (size_t)w * KP * 32;
+    const uint4* c8 = reinterpret_cast<const uint4*>(P.vc);
+    const uint4* a8 = reinterpret_cast<const uint4*>(P.va);
+    const uint4* b8 = reinterpret_cast<const uint4*>(P.vb);
+#pragma unroll
+    for (int q = 0; q < KP; ++q) bins[q * 32 + lane] = 0u;
+    const int G = (int)gridDim.x;
+    const int cb0 = P.n_cb <= G ? P.plan[blockIdx.x] : (int)(blockIdx.x % (unsigned int)P.n_cb);
+    const int parts = P.chunks_per_warp;                 // here: work units per segment
+    const unsigned int n_units = (unsigned int)(P.N * parts);
+    for (int step = 0; step < P.n_cb; ++step) {
+        int cb = cb0 + step;
+        if (cb >= P.n_cb) cb -= P.n_cb;
+        __syncthreads();                       // all warps are done with the previous block's labels / s_peek
+        if (threadIdx.x == 0) s_peek = *((volatile unsigned int*)(P.work + cb));
+        __syncthreads();
+        if (s_peek >= n_units) continue;       // nothing left in that block
+        {
+            const int64_t c0 = (int64_t)cb * CELL_BLOCK;
+            const int ncell = (int)min((int64_t)CELL_BLOCK, P.M - c0);
+            const int nvec = ncell >> 4;
+            const uint4* src = reinterpret_cast<const uint4*>(P.z + c0);
+            uint4* dst = reinterpret_cast<uint4*>(s_z);
+            for (int t = threadIdx.x; t < nvec; t += blockDim.x) dst[t] = src[t];
+            for (int t = (nvec << 4) + threadIdx.x; t < ncell; t += blockDim.x) s_z[t] = P.z[c0 + t];
+        }
+        __syncthreads();
+        for (;;) {
+            unsigned int u = 0;
+            if (lane == 0) u = atomicAdd(P.work + cb, 1u);
+            u = __shfl_sync(0xffffffffu, u, 0);
+            if (u >= n_units) break;
+            const int64_t i = (int64_t)(u / (unsigned int)parts);
+            const int part = (int)(u - (unsigned int)i * (unsigned int)parts);
             const int64_t seg = (int64_t)cb * P.N + i;
-            const int64_t g0 = P.seggrp[seg], g1 = P.seggrp[seg + 1];
-            if (g0 == g1) continue;
+            int64_t g0 = P.seggrp[seg], g1 = P.seggrp[seg + 1];
+            if (parts > 1) {
+                const int64_t len = g1 - g0;
+                g1 = g0 + (len * (part + 1)) / parts;
+                g0 = g0 + (len * part) / parts;
+            }
+            if (g0 >= g1) continue;
             const int flush_every = P.flush[seg];
             unsigned long long* sab_row = P.sab + i * P.K;
             if (flush_every == 0) {
-                // depths above 8191 in this segment: a single group could overflow a 16-bit half; take the
-                // (rare) direct path, one 64-bit atomic per entry
                 for (int64_t g = g0 + lane; g < g1; g += 32) {
                     const uint4 cw = ld_stream(c8 + g), aw = ld_stream(a8 + g), bw = ld_stream(b8 + g);
                     const uint32_t cc[4] = {cw.x, cw.y, cw.z, cw.w};
@@ -334,8 +489,6 @@ __global__ void __launch_bounds__(STATS_THREADS, 2) k_stats(const StatsParams P)
                 }
                 continue;
             }
-            // software pipeline: the next group of each lane is loaded before the current one is binned;
-            // out-of-range slots re-read the segment's last group and are skipped
             int64_t g = g0 + lane;
             int64_t gi = min(g, g1 - 1);
             uint4 cw = ld_stream(c8 + gi), aw = ld_stream(a8 + gi), bw = ld_stream(b8 + gi);
@@ -693,8 +846,8 @@ void launch_cells_v(const Donor& d, const CellsParams& P, bool smem_tab, size_t 
 }
 
 template <int KP>
-void launch_stats_t(const StatsParams& P, unsigned grid, size_t smem, cudaStream_t st) {
-    auto kern = k_stats<KP>;
+void launch_stats_t(const StatsParams& P, unsigned grid, size_t smem, bool units, cudaStream_t st) {
+    auto kern = units ? k_stats_units<KP> : k_stats_stream<KP>;
     CDL_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     kern<<<grid, STATS_THREADS, smem, st>>>(P);
 }
@@ -785,33 +938,89 @@ void launch_cells(const Donor& d, const SweepArgs& a, ChainDev& c, int sm_count,
     CDL_CUDA(cudaGetLastError());
 }
 
+// CTA -> cell block plan of k_stats for a grid of `ctas` CTAs (n_cb <= ctas): CTAs in proportion to the blocks'
+// entries, at least one each.  Layout: [ctas] home block of every CTA, [n_cb] first CTA, [n_cb] CTA count.
+std::vector<int> stats_plan(const std::vector<int64_t>& groups_per_cb, int ctas) {
+    const int n_cb = (int)groups_per_cb.size();
+    std::vector<int> cnt((size_t)n_cb, 1);
+    int64_t total = 0;
+    for (int64_t g : groups_per_cb) total += g;
+    int left = ctas - n_cb;
+    if (total > 0 && left > 0) {
+        std::vector<double> want((size_t)n_cb);
+        int given = 0;
+        for (int c = 0; c < n_cb; ++c) {
+            want[(size_t)c] = (double)groups_per_cb[(size_t)c] / (double)total * (double)ctas;
+            const int extra = std::max(0, (int)want[(size_t)c] - 1);
+            cnt[(size_t)c] += extra; given += extra;
+        }
+        for (int rest = left - given; rest > 0; --rest) {        // hand out the remainder by largest deficit
+            int best = 0; double bd = -1e300;
+            for (int c = 0; c < n_cb; ++c) { const double df = want[(size_t)c] - cnt[(size_t)c]; if (df > bd) { bd = df; best = c; } }
+            ++cnt[(size_t)best];
+        }
+    }
+    std::vector<int> plan((size_t)ctas + 2 * (size_t)n_cb);
+    int b = 0;
+    for (int c = 0; c < n_cb; ++c) {
+        plan[(size_t)ctas + c] = b;
+        plan[(size_t)ctas + n_cb + c] = cnt[(size_t)c];
+        for (int q = 0; q < cnt[(size_t)c]; ++q) plan[(size_t)b++] = c;
+    }
+    return plan;
+}
+
 void launch_stats(const Donor& d, const SweepArgs& a, ChainDev& c, int sm_count, cudaStream_t st) {
     CDL_CUDA(cudaMemsetAsync(c.sab, 0, sizeof(unsigned long long) * (size_t)(d.N * a.K), st));
-    CDL_CUDA(cudaMemsetAsync(c.work + 1, 0, sizeof(unsigned int), st));
     StatsParams P{};
     P.seggrp = d.v_seggrp; P.flush = d.v_flush; P.vc = d.v_cell; P.va = d.v_a; P.vb = d.v_b; P.z = c.z; P.sab = c.sab;
-    P.N = d.N; P.M = d.M; P.K = a.K;
-    P.work = c.work + 1;
+    P.N = d.N; P.M = d.M; P.K = a.K; P.n_cb = d.n_cb;
     const int KP = pad_k(a.K);
     const int ncell_max = (int)std::min<int64_t>(CELL_BLOCK, d.M);
     const size_t smem = sizeof(uint32_t) * STATS_WARPS * KP * 32 + (size_t)((ncell_max + 15) / 16 * 16);
     const int ctas_per_sm = (int)std::max<size_t>(1, std::min<size_t>(2, (220 * 1024) / (smem + 1024)));
     const int ctas = sm_count * ctas_per_sm;
-    // units: small enough that the dynamic tail is a few percent of a CTA's share, large enough that a
-    // unit streams a few hundred KB (about 16 units per CTA)
-    int64_t chunks = std::max<int64_t>(1, ((int64_t)ctas * 16 + d.n_cb - 1) / d.n_cb);
-    int64_t chunk = std::max<int64_t>(STATS_WARPS, (d.N + chunks - 1) / chunks);
-    chunk = (chunk + STATS_WARPS - 1) / STATS_WARPS * STATS_WARPS;
-    chunks = (d.N + chunk - 1) / chunk;
-    P.chunk = (int)chunk;
-    P.chunks_per_cb = (int)chunks;
-    P.n_units = (int)(chunks * d.n_cb);
-    const unsigned grid = (unsigned)std::min<int64_t>(ctas, P.n_units);
+    if (d.n_cb <= ctas) {
+        Donor& dm = const_cast<Donor&>(d);          // lazily built launch plan, cached with the donor
+        if (!dm.v_plan || dm.v_plan_ctas != ctas) {
+            std::vector<uint32_t> ends((size_t)d.n_cb + 1);
+            for (int cb = 0; cb <= d.n_cb; ++cb)
+                CDL_CUDA(cudaMemcpyAsync(&ends[(size_t)cb], d.v_seggrp + (int64_t)cb * d.N, 4, cudaMemcpyDeviceToHost, st));
+            CDL_CUDA(cudaStreamSynchronize(st));
+            std::vector<int64_t> gp((size_t)d.n_cb);
+            for (int cb = 0; cb < d.n_cb; ++cb) gp[(size_t)cb] = (int64_t)ends[(size_t)cb + 1] - (int64_t)ends[(size_t)cb];
+            const std::vector<int> plan = stats_plan(gp, ctas);
+            cudaFree(dm.v_plan);
+            dm.v_plan = nullptr;
+            CDL_CUDA(cudaMalloc(&dm.v_plan, sizeof(int) * plan.size()));
+            CDL_CUDA(cudaMemcpyAsync(dm.v_plan, plan.data(), sizeof(int) * plan.size(), cudaMemcpyHostToDevice, st));
+            CDL_CUDA(cudaStreamSynchronize(st));
+            dm.v_plan_ctas = ctas;
+        }
+        P.plan = d.v_plan;
+    }
+    // Many segments per warp (a whole C4): the unit-pulling kernel; few (a 1/8 shard, C3): the streaming kernel
+    // with one static range per warp.
+    const int64_t warps = (int64_t)ctas * STATS_WARPS;
+    const int64_t segs = d.N * (int64_t)d.n_cb;
+    bool units = segs >= 16 * warps;
+    if (const char* e = getenv("CDL_STATS_KERNEL")) units = e[0] == 'u';
+    P.work = c.stats_work;
+    P.chunks_per_warp = 1;
+    if (units) {
+        // work units per segment: at least ~8 units per warp, no unit shorter than ~64 groups
+        int64_t parts = (8 * warps + segs - 1) / segs;
+        const int64_t avg_groups = std::max<int64_t>(1, d.v_groups / std::max<int64_t>(segs, 1));
+        parts = std::min<int64_t>(parts, std::max<int64_t>(1, avg_groups / 64));
+        P.chunks_per_warp = (int)std::max<int64_t>(1, std::min<int64_t>(parts, 64));
+        CDL_CUDA(cudaMemsetAsync(c.stats_work, 0, sizeof(unsigned int) * (size_t)d.n_cb, st));
+    }
+    const unsigned grid = (unsigned)ctas;
     switch (KP) {
-        case 4: launch_stats_t<4>(P, grid, smem, st); break;
-        case 8: launch_stats_t<8>(P, grid, smem, st); break;
-        case 16: launch_stats_t<16>(P, grid, smem, st); break;
-        default: launch_stats_t<32>(P, grid, smem, st); break;
+        case 4: launch_stats_t<4>(P, grid, smem, units, st); break;
+        case 8: launch_stats_t<8>(P, grid, smem, units, st); break;
+        case 16: launch_stats_t<16>(P, grid, smem, units, st); break;
+        default: launch_stats_t<32>(P, grid, smem, units, st); break;
     }
     CDL_CUDA(cudaGetLastError());
 }

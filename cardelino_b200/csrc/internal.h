@@ -45,6 +45,8 @@ struct Donor {
     int64_t c_groups = 0;
     int n_cb = 0;
     uint32_t* v_seggrp = nullptr;
+    int* v_plan = nullptr;              // k_stats launch plan (CTA -> cell block), built on first use
+    int v_plan_ctas = 0;
     uint16_t* v_flush = nullptr;        // [n_cb*N] groups a lane may bin before a 16+16-bit bin could overflow (k_stats)
     uint16_t* v_cell = nullptr;
     uint16_t* v_a = nullptr;
@@ -97,7 +99,10 @@ struct ChainDev {
     unsigned long long* part_u; // [grid * 8]
     unsigned int* ticket;
     double2* tab_g;      // (du, dv) table in global memory when it does not fit shared memory, else nullptr
-    unsigned int* work;  // [2] dynamic work counters: [0] slices of k_cells_sell, [1] units of k_stats
+    double* sell_scratch;        // [s_slices][4][32][KP] partial logits of split slices (small shards) or nullptr
+    unsigned int* sell_tickets;  // [s_slices]
+    unsigned int* work;  // dynamic work-item counter of k_cells_sell
+    unsigned int* stats_work;    // [n_cb] dynamic unit counters of k_stats
 };
 
 enum {
