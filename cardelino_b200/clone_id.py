@@ -267,9 +267,16 @@ def _collect(h, chain, Av, Config, wise, relabel, verbose, keep_assign_all, ligh
     if keep_assign_all:
         out["assign_all"] = h.fetch("assign_all", chain)
     if N * M <= _DENSE_LIMIT:
-        out["element"] = np.arange(N * M)                      # idx_mat for global / variant (:408,411)
-        out["theta1"] = (np.full((N, M), theta1_el[0]) if wise == "global"
-                         else np.repeat(theta1_el.reshape(N, 1), M, axis=1))
+        if wise == "element":
+            el = h.fetch("element")                            # which(!is.na(D)), column-major (:413-415)
+            th = np.full(N * M, np.nan)                        # theta1 stays NA off the covered entries (:463,653)
+            th[el] = theta1_el
+            out["element"] = el
+            out["theta1"] = th.reshape(M, N).T.copy()
+        else:
+            out["element"] = np.arange(N * M)                  # idx_mat for global / variant (:408,411)
+            out["theta1"] = (np.full((N, M), theta1_el[0]) if wise == "global"
+                             else np.repeat(theta1_el.reshape(N, 1), M, axis=1))
         out["prob_variant"] = h.fetch("prob_variant", chain)
     else:
         out["theta1_elements"] = theta1_el

@@ -69,6 +69,7 @@ struct NcclApi {
 struct Chain {
     ChainDev dev{};
     DevBuf<double> scal, l1, l1c, theta0_all, theta1_all, loglik_all, relax_all, prob_all, prob_acc, part_d;
+    DevBuf<double> el_l1, el_l1c, sd1;
     DevBuf<uint32_t> mask;
     DevBuf<uint8_t> z, config_all, assign_all;
     DevBuf<unsigned long long> sab, part_u;
@@ -360,6 +361,16 @@ void one_sweep(cdl_handle h, Chain& ch, SweepArgs& a, uint32_t it, const cdl_rep
         a.rp_theta1 = rp_dev->theta1 ? rp_dev->theta1 + row * n_el : nullptr;
         a.rp_relax_next = (rp_dev->relax_rate && (int64_t)it < a.T) ? rp_dev->relax_rate + row + 1 : nullptr;
     }
+    if (a.wise == 2) {
+        // wise = element: per-entry theta1 (element.cu); single GPU
+        a.p2p = nullptr;
+        launch_el_cells(h->donor, a, ch.dev, h->st);
+        launch_el_stats(h->donor, a, ch.dev, h->st);
+        launch_table(h->donor, a, ch.dev, h->st);
+        launch_el_theta(h->donor, a, ch.dev, h->st);
+        h->launches += 4;
+        return;
+    }
     if (h->use_sell) launch_cells_sell(h->donor, a, ch.dev, h->sm_count, h->st);
     else launch_cells(h->donor, a, ch.dev, h->sm_count, h->st);
     if (h->p2p_active) {
@@ -650,11 +661,11 @@ int cdl_gibbs_run(cdl_handle h, const double* Config, int32_t K, const double* P
         const cdl_gibbs_params gp = *params;
         const Donor& d = h->donor;
         if (K < 1 || K > KMAX) throw Error(CDL_ERR_UNSUPPORTED, "number of clones must be in 1..32");
-        if (gp.wise != CDL_WISE_GLOBAL && gp.wise != CDL_WISE_VARIANT) {
-            if (gp.wise == CDL_WISE_ELEMENT)
-                throw Error(CDL_ERR_UNSUPPORTED, "wise = \"element\" is not implemented yet in this build");
+        if (gp.wise != CDL_WISE_GLOBAL && gp.wise != CDL_WISE_VARIANT && gp.wise != CDL_WISE_ELEMENT)
             throw Error(CDL_ERR_INVALID, "Input wise mode: unknown, while only supporting: element, variant, global");
-        }
+        const bool element = gp.wise == CDL_WISE_ELEMENT;
+        if (element && h->world > 1)
+            throw Error(CDL_ERR_UNSUPPORTED, "wise = \"element\" runs on one GPU (per-entry parameters are not sharded)");
         if (gp.max_iter < 2) throw Error(CDL_ERR_INVALID, "max_iter must be at least 2");
         if (gp.relax_Config && gp.relax_rate_fixed_set && (gp.relax_rate_fixed > 1 || gp.relax_rate_fixed < 0))
             throw Error(CDL_ERR_INVALID, "relax_rate_fixed needs to be NULL or in [0, 1].");
@@ -672,10 +683,16 @@ int cdl_gibbs_run(cdl_handle h, const double* Config, int32_t K, const double* P
         // The choice depends on the WHOLE donor's cell count so that it is the same on every rank.
         h->use_sell = h->cells_layout == CDL_CELLS_SLICES ||
                       (h->cells_layout == CDL_CELLS_AUTO && d.M_total >= 16384);
+        if (element) h->use_sell = false;
         if (h->use_sell) donor_build_sell(h->donor, h->st);
         p2p_ensure(h, (size_t)(d.N * K));
         const int64_t N = d.N, M = d.M, T = gp.max_iter;
-        const int64_t n_el = gp.wise == CDL_WISE_VARIANT ? N : 1;
+        const int64_t n_el = gp.wise == CDL_WISE_VARIANT ? N : (element ? d.nnz : 1);
+        if (element) {
+            if ((double)T * (double)n_el * 8.0 > (double)gp.trace_budget_bytes)
+                throw Error(CDL_ERR_UNSUPPORTED, "wise = \"element\": the max_iter x nnz theta1 trace exceeds trace_budget_bytes");
+            donor_build_elem0(h->donor, h->st);
+        }
         h->T = T;
         h->n_el = n_el;
         std::vector<uint32_t> masks = config_masks(Config, N, K, true);
@@ -734,7 +751,12 @@ int cdl_gibbs_run(cdl_handle h, const double* Config, int32_t K, const double* P
             std::unique_ptr<Chain> chp(new Chain());
             Chain& ch = *chp;
             ch.scal.alloc(16); ch.scal.zero(h->st);
-            ch.l1.alloc((size_t)n_el); ch.l1c.alloc((size_t)n_el);
+            ch.l1.alloc((size_t)(element ? 1 : n_el)); ch.l1c.alloc((size_t)(element ? 1 : n_el));
+            if (element) {
+                ch.el_l1.alloc((size_t)d.c_groups * GROUP); ch.el_l1.zero(h->st);
+                ch.el_l1c.alloc((size_t)d.c_groups * GROUP); ch.el_l1c.zero(h->st);
+                ch.sd1.alloc((size_t)(N * K)); ch.sd1.zero(h->st);
+            }
             ch.mask.alloc((size_t)N);
             ch.z.alloc((size_t)M); ch.z.zero(h->st);
             ch.sab.alloc((size_t)(N * K)); ch.sab.zero(h->st);
@@ -767,6 +789,7 @@ int cdl_gibbs_run(cdl_handle h, const double* Config, int32_t K, const double* P
             ch.dev.prob_acc = nullptr;
             ch.dev.part_d = ch.part_d.p; ch.dev.part_u = ch.part_u.p; ch.dev.ticket = ch.ticket.p;
             ch.dev.tab_g = ch.tab_g.p;
+            ch.dev.el_l1 = ch.el_l1.p; ch.dev.el_l1c = ch.el_l1c.p; ch.dev.sd1 = ch.sd1.p;
             ch.dev.work = ch.work.p;
             ch.dev.stats_work = ch.stats_work.p;
             ch.dev.sell_scratch = nullptr; ch.dev.sell_tickets = nullptr;
@@ -786,6 +809,7 @@ int cdl_gibbs_run(cdl_handle h, const double* Config, int32_t K, const double* P
                 a.rp_relax_next = rp->relax_rate ? rp->relax_rate + 1 : nullptr;
             }
             launch_init_chain(a, ch.dev, h->st);
+            if (element) launch_el_init(h->donor, a, ch.dev, h->st);
             // with relax off, Config_all rows hold Config (resolution of reference quirk 1); row 1 stays 0
             int64_t it_final = T;
             double frac = NAN;
@@ -986,7 +1010,9 @@ int cdl_get_loglik(cdl_handle h, const double* Config, int32_t K, const int32_t*
         if (!Config || !theta1 || !out || K < 1) throw Error(CDL_ERR_INVALID, "bad arguments");
         if ((assign == nullptr) == (assign_prob == nullptr))
             throw Error(CDL_ERR_INVALID, "give exactly one of assign / assign_prob");
-        if (n_theta1 != 1 && n_theta1 != d.N) throw Error(CDL_ERR_INVALID, "theta1 must have 1 or N values");
+        if (n_theta1 != 1 && n_theta1 != d.N && n_theta1 != d.nnz)
+            throw Error(CDL_ERR_INVALID, "theta1 must have 1, N or nnz values");
+        if (n_theta1 != 1 && n_theta1 != d.N) donor_build_elem0(h->donor, h->st);
         DevBuf<double> cfg((size_t)(d.N * K)), th1((size_t)n_theta1), pr;
         DevBuf<int32_t> as;
         cfg.upload(Config, (size_t)(d.N * K), h->st);

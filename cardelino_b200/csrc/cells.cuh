@@ -177,5 +177,67 @@ __device__ __forceinline__ void accumulate_group(double (&acc)[KP], const Grp<VI
 }
 
 
+// Per-lane softmax over K logits held in registers (R/clone_id.R:479-481): acc <- probabilities.
+template <int KP>
+__device__ __forceinline__ void lane_softmax(double (&acc)[KP], int K, const double* logPsi) {
+    double mx = -INFINITY;
+#pragma unroll
+    for (int k = 0; k < KP; ++k)
+        if (k < K) { acc[k] += logPsi[k]; mx = fmax(mx, acc[k]); }
+    double sm = 0.0;
+#pragma unroll
+    for (int k = 0; k < KP; ++k) {
+        if (k < K) { acc[k] = exp(acc[k] - mx); sm += acc[k]; }
+        else acc[k] = 0.0;
+    }
+#pragma unroll
+    for (int k = 0; k < KP; ++k)
+        if (k < K) acc[k] = acc[k] / sm;
+}
+
+// sample(seq_len(K), 1, prob = pr) with the uniform u (:493): walk the DESCENDING-sorted CDF; exact ties are
+// ordered by R's revsort.  Every lane of the warp must call it (warp votes end the walk early).
+template <int KP>
+__device__ __forceinline__ int lane_draw(const double (&pr)[KP], int K, double u, bool valid) {
+    uint32_t used = 0;
+    double cum = 0.0, selv = 0.0;
+    int sel = 0;
+    bool pending = valid;
+    for (int r = 0; r < K; ++r) {
+        if (!__any_sync(0xffffffffu, pending)) break;
+        double bv = -1.0;
+        int bk = 0;
+#pragma unroll
+        for (int k = 0; k < KP; ++k) {
+            const bool take = (k < K) && !((used >> k) & 1u) && (pr[k] > bv);   // ties -> lowest index
+            bv = take ? pr[k] : bv;
+            bk = take ? k : bk;
+        }
+        if (pending) {
+            used |= 1u << bk;
+            cum += bv;
+            if (u <= cum || r == K - 1) { sel = bk; selv = bv; pending = false; }
+        }
+    }
+    int ntie = 0;
+#pragma unroll
+    for (int k = 0; k < KP; ++k) ntie += (k < K && pr[k] == selv) ? 1 : 0;
+    if (valid && ntie > 1 && selv > 0.0) {
+        double pa[KP];
+        int perm[KP];
+#pragma unroll
+        for (int k = 0; k < KP; ++k) { pa[k] = pr[k]; perm[k] = k; }
+        double tot = 0.0;
+        for (int l = 0; l < K; ++l) tot += pa[l];
+        for (int l = 0; l < K; ++l) pa[l] /= tot;
+        revsort_dev(pa, perm, K);
+        for (int l = 1; l < K; ++l) pa[l] += pa[l - 1];
+        int jj = 0;
+        while (jj < K - 1 && !(u <= pa[jj])) ++jj;
+        sel = perm[jj];
+    }
+    return sel;
+}
+
 }  // namespace
 }  // namespace cdl

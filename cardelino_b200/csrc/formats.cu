@@ -155,6 +155,7 @@ double sum_doubles(const double* data, int64_t n, cudaStream_t st) {
 
 void donor_free(Donor& d) {
     donor_free_sell(d);
+    cudaFree(d.c_elem0);
     cudaFree(d.c_rowgrp); cudaFree(d.c_vidx); cudaFree(d.c_a); cudaFree(d.c_b);
     cudaFree(d.v_seggrp); cudaFree(d.v_flush); cudaFree(d.v_plan); cudaFree(d.v_cell); cudaFree(d.v_a); cudaFree(d.v_b);
     cudaFree(d.labels);
@@ -293,6 +294,23 @@ __global__ void k_row_len(const uint32_t* __restrict__ rowgrp, const uint16_t* _
     len[j] = n;
 }
 }  // namespace
+
+// element index of each cell's first covered entry (prefix sums of the true row lengths)
+void donor_build_elem0(Donor& d, cudaStream_t st) {
+    if (d.c_elem0) return;
+    int64_t* len = dalloc<int64_t>(d.M + 1);
+    CDL_CUDA(cudaMemsetAsync(len, 0, sizeof(int64_t) * (size_t)(d.M + 1), st));
+    const int threads = 256;
+    k_row_len<<<(unsigned)((d.M + threads - 1) / threads), threads, 0, st>>>(d.c_rowgrp, d.c_a, d.c_b, d.M, len);
+    size_t tmp_bytes = 0;
+    cudaError_t e = cub::DeviceScan::ExclusiveSum(nullptr, tmp_bytes, len, len, (int)(d.M + 1), st);
+    void* tmp = dalloc<uint8_t>((int64_t)tmp_bytes);
+    if (e == cudaSuccess) e = cub::DeviceScan::ExclusiveSum(tmp, tmp_bytes, len, len, (int)(d.M + 1), st);
+    cudaStreamSynchronize(st);
+    cudaFree(tmp);
+    if (e != cudaSuccess) { cudaFree(len); CDL_CUDA(e); }
+    d.c_elem0 = len;
+}
 
 void donor_export(const Donor& d, int64_t* p, int32_t* oi, uint16_t* oa, uint16_t* od, cudaStream_t st) {
     int64_t* len = dalloc<int64_t>(d.M + 1);

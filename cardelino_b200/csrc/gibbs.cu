@@ -515,6 +515,7 @@ struct TableParams {
     const uint32_t* cfg0;
     uint32_t* mask;
     const unsigned long long* sab;
+    const double* sd1;         // wise = element: SD[i,k] = sum_{j: z_j = k} A ln th1_ij + B ln(1 - th1_ij), else nullptr
     double* scal;
     double* l1;
     double* l1c;
@@ -599,20 +600,22 @@ __global__ void __launch_bounds__(TABLE_THREADS) k_table(const TableParams P) {
         __syncthreads();
     }
     if (i < P.N && k < P.K) {
+        const bool element = P.sd1 != nullptr;
         const int64_t t = P.wise == 1 ? i : 0;
-        const double l1 = P.l1[t], l1c = P.l1c[t];
+        const double l1 = element ? 0.0 : P.l1[t], l1c = element ? 0.0 : P.l1c[t];
         const double du = l1 - l0, dv = l1c - l0c;
         const uint32_t c0 = P.cfg0[i];
         unsigned long long pk = P.sab[i * P.K + k];
         for (int q = 0; q < P.n_peer; ++q) pk += ld_peer_u64(P.peer_sab[q] + i * P.K + k);
         const double SA = (double)(uint32_t)pk, SB = (double)(uint32_t)(pk >> 32);
+        const double sd = element ? P.sd1[i * P.K + k] : 0.0;       // per-entry theta1: the theta1 part, summed
         const uint32_t cbit = (c0 >> k) & 1u;
         uint32_t bit = cbit;
         if (P.relax) {
             double prior;
             if (P.keep_base && k == 0) prior = cbit ? INFINITY : -INFINITY;
             else prior = cbit ? odd1 : odd0;
-            double x = SA * du + SB * dv + prior;
+            double x = (element ? sd - (SA * l0 + SB * l0c) : SA * du + SB * dv) + prior;
             x = x > 50.0 ? 50.0 : (x < -50.0 ? -50.0 : x);
             const double ex = exp(x);
             const double p = ex / (ex + 1.0);
@@ -627,7 +630,7 @@ __global__ void __launch_bounds__(TABLE_THREADS) k_table(const TableParams P) {
         bitk = bit << k;
         if (bit) {
             S3 = (uint32_t)pk; S4 = (uint32_t)(pk >> 32);
-            ll = SA * l1 + SB * l1c;
+            ll = element ? sd : SA * l1 + SB * l1c;
         } else {
             S1 = (uint32_t)pk; S2 = (uint32_t)(pk >> 32);
             ll = SA * l0 + SB * l0c;
@@ -864,7 +867,8 @@ int cells_smem_bytes(int64_t N, int K) {
 
 void launch_init_chain(const SweepArgs& a, ChainDev& c, cudaStream_t st) {
     InitParams P{};
-    P.N = a.N; P.n_el = a.wise == 1 ? a.N : 1; P.K = a.K; P.wise = a.wise;
+    P.N = a.N; P.n_el = a.wise == 1 ? a.N : (a.wise == 2 ? 0 : 1);   // element: k_el_theta<INIT> draws theta1
+    P.K = a.K; P.wise = a.wise;
     P.prior0[0] = a.prior0[0]; P.prior0[1] = a.prior0[1];
     P.prior1[0] = a.prior1[0]; P.prior1[1] = a.prior1[1];
     P.prior1_mat = a.prior1_mat; P.cfg0 = a.cfg0; P.mask = c.mask;
@@ -1041,8 +1045,9 @@ void launch_table(const Donor& d, const SweepArgs& a, ChainDev& c, cudaStream_t 
         P.prior0[q] = a.prior0[q]; P.prior1[q] = a.prior1[q]; P.relax_prior[q] = a.relax_prior[q];
     }
     P.prior1_mat = a.prior1_mat;
-    P.n_el = a.wise == 1 ? d.N : 1;
+    P.n_el = a.wise == 1 ? d.N : (a.wise == 2 ? d.nnz : 1);
     P.cfg0 = a.cfg0; P.mask = c.mask; P.sab = c.sab; P.scal = c.scal; P.l1 = c.l1; P.l1c = c.l1c;
+    P.sd1 = a.wise == 2 ? c.sd1 : nullptr;
     P.W_log = a.W_log;
     P.theta0_all = c.theta0_all; P.theta1_all = c.theta1_all; P.loglik_all = c.loglik_all;
     P.relax_all = c.relax_all; P.config_all = c.config_all;

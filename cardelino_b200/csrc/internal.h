@@ -43,6 +43,7 @@ struct Donor {
     uint16_t* c_a = nullptr;
     uint16_t* c_b = nullptr;
     int64_t c_groups = 0;
+    int64_t* c_elem0 = nullptr;         // [M+1] element index (covered entries in cell-major order) of each cell's first entry; built on first use
     int n_cb = 0;
     uint32_t* v_seggrp = nullptr;
     int* v_plan = nullptr;              // k_stats launch plan (CTA -> cell block), built on first use
@@ -69,6 +70,7 @@ struct Donor {
 void donor_free(Donor& d);
 void donor_free_sell(Donor& d);
 void donor_build_sell(Donor& d, cudaStream_t st);
+void donor_build_elem0(Donor& d, cudaStream_t st);
 // raw CSC (cells = columns) already on the device -> both layouts.  Frees nothing of the input.
 void donor_build(Donor& d, int64_t N, int64_t M, int64_t nnz, const int64_t* p_dev, const int32_t* i_dev,
                  const uint16_t* a_dev, const uint16_t* d_dev, cudaStream_t st);
@@ -98,6 +100,9 @@ struct ChainDev {
     double* part_d;      // [grid * 4]
     unsigned long long* part_u; // [grid * 8]
     unsigned int* ticket;
+    double* el_l1;       // wise = element: ln theta1 of every entry of the row layout (padded positions are 0)
+    double* el_l1c;      //                 ln(1 - theta1)
+    double* sd1;         //                 [N*K] per-(variant, clone) sums of A ln th1 + B ln(1 - th1)
     double2* tab_g;      // (du, dv) table in global memory when it does not fit shared memory, else nullptr
     double* sell_scratch;        // [s_slices][4][32][KP] partial logits of split slices (small shards) or nullptr
     unsigned int* sell_tickets;  // [s_slices]
@@ -130,7 +135,7 @@ struct P2PState {
 struct SweepArgs {
     int64_t N, M, M_total, cell_offset;
     int K, KP;
-    int wise;            // 0 global, 1 variant
+    int wise;            // 0 global, 1 variant, 2 element
     int relax;           // Config flips enabled
     int learn_relax_next;// draw relax rate for iteration it+1 at the end of this sweep
     int keep_base;
@@ -157,6 +162,11 @@ void launch_cells_sell(const Donor& d, const SweepArgs& a, ChainDev& c, int sm_c
 void launch_stats(const Donor& d, const SweepArgs& a, ChainDev& c, int sm_count, cudaStream_t st);
 void launch_table(const Donor& d, const SweepArgs& a, ChainDev& c, cudaStream_t st);
 void launch_signal(const P2PState& q, cudaStream_t st);
+// wise = element (element.cu)
+void launch_el_init(const Donor& d, const SweepArgs& a, ChainDev& c, cudaStream_t st);
+void launch_el_cells(const Donor& d, const SweepArgs& a, ChainDev& c, cudaStream_t st);
+void launch_el_stats(const Donor& d, const SweepArgs& a, ChainDev& c, cudaStream_t st);
+void launch_el_theta(const Donor& d, const SweepArgs& a, ChainDev& c, cudaStream_t st);
 
 // post-processing
 void launch_geweke(const double* prob_all, int64_t cols, int64_t n_rows, unsigned long long* counts2,
@@ -164,7 +174,7 @@ void launch_geweke(const double* prob_all, int64_t cols, int64_t n_rows, unsigne
 void launch_col_means_d(const double* X, int64_t cols, int64_t r0, int64_t r1, double* out, cudaStream_t st);
 void launch_col_means_u8(const uint8_t* X, int64_t cols, int64_t r0, int64_t r1, double* out, cudaStream_t st);
 void launch_prob_variant(const Donor& d, int wise, const double* theta0_all, const double* theta1_all,
-                         int64_t n_el, int64_t r0, int64_t r1, double* out_dense, cudaStream_t st);
+                         int64_t n_el, int64_t r0, int64_t r1, double* out_dense, cudaStream_t st);   // wise 2 needs d.c_elem0
 double loglik_general(const Donor& d, const double* Config_dev, int K, const int32_t* assign_dev,
                       const double* prob_dev /* [M][K] device layout, or null */, double theta0,
                       const double* theta1_dev, int64_t n_theta1, cudaStream_t st);

@@ -51,7 +51,8 @@ template <typename VIdx>
 __global__ void k_prob_variant(const uint32_t* __restrict__ rowgrp, const VIdx* __restrict__ vidx,
                                const uint16_t* __restrict__ ca, const uint16_t* __restrict__ cb, int64_t M,
                                int64_t N, int wise, const double* __restrict__ th0, const double* __restrict__ th1,
-                               int64_t n_el, int64_t r0, int64_t r1, double* __restrict__ out) {
+                               int64_t n_el, int64_t r0, int64_t r1, const int64_t* __restrict__ elem0,
+                               double* __restrict__ out) {
     const int lane = threadIdx.x & 31;
     const int64_t warp = (blockIdx.x * (int64_t)blockDim.x + threadIdx.x) >> 5;
     const int64_t nwarps = ((int64_t)gridDim.x * blockDim.x) >> 5;
@@ -63,7 +64,7 @@ __global__ void k_prob_variant(const uint32_t* __restrict__ rowgrp, const VIdx* 
             const int64_t i = vidx[e];
             double p1 = 0.0, p0 = 0.0;
             for (int64_t r = r0; r < r1; ++r) {
-                const double t1 = th1[r * n_el + (wise == 1 ? i : 0)];
+                const double t1 = th1[r * n_el + (wise == 2 ? elem0[j] + (e - e0) : (wise == 1 ? i : 0))];
                 const double t0 = th0[r];
                 p1 += exp((double)a * log(t1) + (double)b * log(1.0 - t1));
                 p0 += exp((double)a * log(t0) + (double)b * log(1.0 - t0));
@@ -88,6 +89,7 @@ __global__ void k_loglik(const uint32_t* __restrict__ rowgrp, const VIdx* __rest
                          int K, const double* __restrict__ Config /* N x K col-major */,
                          const int32_t* __restrict__ assign, const double* __restrict__ prob /* [M][K] */,
                          double l0, double l0c, const double* __restrict__ theta1, int64_t n_th1,
+                         const int64_t* __restrict__ elem0 /* per-entry theta1 (n_th1 == nnz) or nullptr */,
                          double* __restrict__ cell_out) {
     const int lane = threadIdx.x & 31;
     const int64_t warp = (blockIdx.x * (int64_t)blockDim.x + threadIdx.x) >> 5;
@@ -104,7 +106,7 @@ __global__ void k_loglik(const uint32_t* __restrict__ rowgrp, const VIdx* __rest
             if (assign) q = Config[i + (int64_t)zlab * N];
             else
                 for (int k = 0; k < K; ++k) q += Config[i + (int64_t)k * N] * prob[j * K + k];
-            const double t1 = theta1[n_th1 == 1 ? 0 : i];
+            const double t1 = theta1[elem0 ? elem0[j] + (e - e0) : (n_th1 == 1 ? 0 : i)];
             const double w1 = exp(log(t1) * (double)a + log(1.0 - t1) * (double)b);
             const double w0 = exp(l0 * (double)a + l0c * (double)b);
             s += log(w1 * q + w0 * (1.0 - q));
@@ -254,14 +256,16 @@ void launch_col_means_u8(const uint8_t* X, int64_t cols, int64_t r0, int64_t r1,
 void launch_prob_variant(const Donor& d, int wise, const double* theta0_all, const double* theta1_all,
                          int64_t n_el, int64_t r0, int64_t r1, double* out_dense, cudaStream_t st) {
     const int64_t n = d.N * d.M;
-    k_fill<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(out_dense, n, 0.5);
+    // uncovered entries: dbinom(0, 0, .) = 1 on both sides -> 0.5 for global / variant; NA for element, where the
+    // reference only assigns the covered entries (R/clone_id.R:617-621)
+    k_fill<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(out_dense, n, wise == 2 ? (double)NAN : 0.5);
     const unsigned grid = warp_grid(d.M, 256);
     if (d.vidx32)
         k_prob_variant<uint32_t><<<grid, 256, 0, st>>>(d.c_rowgrp, (const uint32_t*)d.c_vidx, d.c_a, d.c_b, d.M, d.N,
-                                                       wise, theta0_all, theta1_all, n_el, r0, r1, out_dense);
+                                                       wise, theta0_all, theta1_all, n_el, r0, r1, d.c_elem0, out_dense);
     else
         k_prob_variant<uint16_t><<<grid, 256, 0, st>>>(d.c_rowgrp, (const uint16_t*)d.c_vidx, d.c_a, d.c_b, d.M, d.N,
-                                                       wise, theta0_all, theta1_all, n_el, r0, r1, out_dense);
+                                                       wise, theta0_all, theta1_all, n_el, r0, r1, d.c_elem0, out_dense);
     CDL_CUDA(cudaGetLastError());
 }
 
@@ -276,10 +280,12 @@ double loglik_general(const Donor& d, const double* Config_dev, int K, const int
     const double l0 = log(theta0), l0c = log(1.0 - theta0);
     if (d.vidx32)
         k_loglik<uint32_t><<<grid, 256, 0, st>>>(d.c_rowgrp, (const uint32_t*)d.c_vidx, d.c_a, d.c_b, d.M, d.N, K,
-                                                 Config_dev, assign_dev, prob_dev, l0, l0c, theta1_dev, n_theta1, cell);
+                                                 Config_dev, assign_dev, prob_dev, l0, l0c, theta1_dev, n_theta1,
+                                                 (n_theta1 != 1 && n_theta1 != d.N) ? d.c_elem0 : nullptr, cell);
     else
         k_loglik<uint16_t><<<grid, 256, 0, st>>>(d.c_rowgrp, (const uint16_t*)d.c_vidx, d.c_a, d.c_b, d.M, d.N, K,
-                                                 Config_dev, assign_dev, prob_dev, l0, l0c, theta1_dev, n_theta1, cell);
+                                                 Config_dev, assign_dev, prob_dev, l0, l0c, theta1_dev, n_theta1,
+                                                 (n_theta1 != 1 && n_theta1 != d.N) ? d.c_elem0 : nullptr, cell);
     k_sum_fixed<<<1, 256, 0, st>>>(cell, d.M, out);
     double h = 0.0;
     cudaError_t e = cudaMemcpyAsync(&h, out, sizeof(double), cudaMemcpyDeviceToHost, st);

@@ -173,7 +173,8 @@ int cdl_fetch_element_index(cdl_handle h, int64_t* out /* nnz */);
 
 /* ---- get_logLik (R/clone_id.R:734-752) ----
  * Config N x K doubles (may be fractional); exactly one of assign (1-based labels, M) / assign_prob
- * (M x K) is non-NULL; theta1 has n_theta1 in {1, N} values. */
+ * (M x K) is non-NULL; theta1 has n_theta1 in {1, N, nnz} values (nnz: one per covered entry in the order of
+ * cdl_fetch_element_index, wise = "element"). */
 int cdl_get_loglik(cdl_handle h, const double* Config, int32_t K, const int32_t* assign,
                    const double* assign_prob, double theta0, const double* theta1, int64_t n_theta1,
                    double* out);

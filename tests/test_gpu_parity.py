@@ -218,6 +218,35 @@ def test_both_statistic_kernels_agree(gpu_handle, monkeypatch):
     assert a[0][1:].any() and len(set(a[2][-1])) == K
 
 
+@pytest.mark.parametrize("kw", [dict(), dict(relax_rate_fixed=0.3, keep_base_clone=False), dict(relax_Config=False)])
+def test_element_wise_matches_oracle(gpu_handle, example_donor, kw):
+    """wise = "element" (R/clone_id.R:413-416): one theta1 per covered entry.  The oracle re-runs the chain with
+    the GPU's theta / relax-rate draws injected and its own uniforms from the same Philox streams: every
+    probability, label, Config flip and the logLik trace must agree."""
+    cb = _cb()
+    A, D, Z = example_donor
+    T, nnz = 40, 1874
+    g = cb.clone_id_Gibbs(A, D, Z, wise="element", min_iter=T, max_iter=T, seed=21, keep_assign_all=True,
+                          handle=gpu_handle, verbose=False, **kw)
+    assert g["theta1_all"].shape == (T, nnz) and np.all((g["theta1_all"] > 0) & (g["theta1_all"] < 1))
+    assert g["element"].shape == (nnz,) and np.array_equal(g["element"], np.flatnonzero(np.nan_to_num(D).T.ravel() > 0))
+    assert np.isnan(g["theta1"]).sum() == 34 * 428 - nnz
+    dr = O.ReplayDraws(seed=21, chain=0, theta0_all=g["theta0_all"], theta1_all=g["theta1_all"],
+                       relax_rate_all=g["relax_rate_all"])
+    o = O.clone_id_Gibbs(A, D, Z, wise="element", min_iter=T, max_iter=T, draws=dr, **kw)
+    assert np.abs(g["prob_all"] - o["prob_all"]).max() <= 1e-9
+    assert np.array_equal(g["assign_all"], o["assign_all"])
+    assert np.array_equal(g["Config_all"], o["Config_all"])
+    assert np.allclose(g["logLik"][1:], o["logLik"][1:], rtol=1e-9, atol=0)
+    assert np.abs(g["prob"] - o["prob"]).max() <= 1e-9
+    assert np.array_equal(np.isnan(g["prob_variant"]), np.isnan(o["prob_variant"]))
+    assert np.nanmax(np.abs(g["prob_variant"] - o["prob_variant"])) <= 1e-9
+    assert abs(g["logLik_post"] - o["logLik_post"]) <= REL * abs(o["logLik_post"])
+    # the per-entry Beta draws themselves: posterior shape is prior + (A, B) where the entry's variant is in
+    # the cell's clone, so covered entries of carried variants have larger means than the prior's 0.45
+    assert 0.2 < g["theta1_all"][0].mean() < 0.7
+
+
 def test_replay_mode(gpu_handle, example_donor):
     """Correctness check 2 of the north star: inject a recorded run's uniforms and theta draws; the
     assignments and Config flips must be reproduced."""
