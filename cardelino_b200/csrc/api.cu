@@ -747,7 +747,8 @@ int cdl_gibbs_run(cdl_handle h, const double* Config, int32_t K, const double* P
         const int64_t n_buin_planned = (int64_t)std::ceil((double)T * gp.buin_frac);
         DevBuf<unsigned long long> gcounts(2);
 
-        for (int c = 0; c < gp.n_chain; ++c) {
+        // ---- a chain's life in three steps, each on whatever stream h->st currently is ----
+        auto start_chain = [&](int c, SweepArgs& a) -> std::unique_ptr<Chain> {
             std::unique_ptr<Chain> chp(new Chain());
             Chain& ch = *chp;
             ch.scal.alloc(16); ch.scal.zero(h->st);
@@ -810,18 +811,9 @@ int cdl_gibbs_run(cdl_handle h, const double* Config, int32_t K, const double* P
             }
             launch_init_chain(a, ch.dev, h->st);
             if (element) launch_el_init(h->donor, a, ch.dev, h->st);
-            // with relax off, Config_all rows hold Config (resolution of reference quirk 1); row 1 stays 0
-            int64_t it_final = T;
-            double frac = NAN;
-            for (int64_t it = 2; it <= T; ++it) {
-                ch.dev.prob_acc = (!exact && it >= n_buin_planned) ? ch.prob_acc.p : nullptr;
-                one_sweep(h, ch, a, (uint32_t)it, rp, n_el);
-                if (exact && it >= gp.min_iter && it % check_every == 0) {
-                    frac = geweke_fraction(h, ch, it, gcounts);
-                    if (gp.verbose) std::printf("%g%% converged.\n", r_round3_percent(frac));
-                    if (frac > 0.995) { it_final = it; break; }
-                }
-            }
+            return chp;
+        };
+        auto finish_chain = [&](Chain& ch, SweepArgs& a, int64_t it_final, double frac) {
             const int64_t itf = it_final;
             if (exact) frac = geweke_fraction(h, ch, itf, gcounts);
             ch.info.n_iter = (int32_t)itf;
@@ -864,7 +856,86 @@ int cdl_gibbs_run(cdl_handle h, const double* Config, int32_t K, const double* P
             std::vector<double> llw(ll.begin() + r0, ll.begin() + r1);
             dic_from_trace(llw, llp, ch.info.dic);
             ch.done = true;
-            h->chains.push_back(std::move(chp));
+        };
+
+        // Independent chains (the reference forks one R process per chain, R/clone_id.R:127-154) are interleaved
+        // on several streams when they fit in memory together: a small donor's sweep is a handful of tiny
+        // kernels, so chains overlap on the GPU instead of queueing behind one another.  Cell-sharded and replay
+        // runs keep one chain at a time on the library's stream.
+        const double per_chain_bytes = (exact ? trace_bytes : 0.0) + (double)T * (double)(N * K) +
+                                       (double)T * (double)n_el * 8.0;
+        const bool concurrent = gp.n_chain > 1 && h->world == 1 && !rp &&
+                                per_chain_bytes * gp.n_chain <= (double)gp.trace_budget_bytes;
+        if (!concurrent) {
+            for (int c = 0; c < gp.n_chain; ++c) {
+                std::unique_ptr<Chain> chp = start_chain(c, a);
+                Chain& ch = *chp;
+                int64_t it_final = T;
+                double frac = NAN;
+                for (int64_t it = 2; it <= T; ++it) {
+                    ch.dev.prob_acc = (!exact && it >= n_buin_planned) ? ch.prob_acc.p : nullptr;
+                    one_sweep(h, ch, a, (uint32_t)it, rp, n_el);
+                    if (exact && it >= gp.min_iter && it % check_every == 0) {
+                        frac = geweke_fraction(h, ch, it, gcounts);
+                        if (gp.verbose) std::printf("%g%% converged.\n", r_round3_percent(frac));
+                        if (frac > 0.995) { it_final = it; break; }
+                    }
+                }
+                finish_chain(ch, a, it_final, frac);
+                h->chains.push_back(std::move(chp));
+            }
+        } else {
+            struct Live { std::unique_ptr<Chain> ch; SweepArgs a; cudaStream_t st; int64_t it_final; double frac; bool active; };
+            // the host thread issues ~5 launches per chain sweep, so beyond a few streams the run is bound by
+            // launch rate, not by the GPU (measured on example_donor: 1 chain 24k, 4 chains 49k chain-iterations/s,
+            // 16 streams no better); capturing a sweep in a CUDA graph needs the iteration state on the device
+            // and is the next step
+            const int n_streams = std::min(gp.n_chain, 4);
+            std::vector<cudaStream_t> streams((size_t)n_streams, nullptr);
+            cudaStream_t home = h->st;
+            std::vector<Live> live;
+            try {
+                for (auto& s : streams) CDL_CUDA(cudaStreamCreateWithFlags(&s, cudaStreamNonBlocking));
+                CDL_CUDA(cudaStreamSynchronize(home));          // uploads made on the library's stream are done
+                for (int c = 0; c < gp.n_chain; ++c) {
+                    Live lv{nullptr, a, streams[(size_t)(c % n_streams)], T, NAN, true};
+                    h->st = lv.st;
+                    lv.ch = start_chain(c, lv.a);
+                    live.push_back(std::move(lv));
+                }
+                int n_active = gp.n_chain;
+                for (int64_t it = 2; it <= T && n_active > 0; ++it) {
+                    for (Live& lv : live) {
+                        if (!lv.active) continue;
+                        h->st = lv.st;
+                        lv.ch->dev.prob_acc = (!exact && it >= n_buin_planned) ? lv.ch->prob_acc.p : nullptr;
+                        one_sweep(h, *lv.ch, lv.a, (uint32_t)it, nullptr, n_el);
+                    }
+                    if (exact && it >= gp.min_iter && it % check_every == 0) {
+                        for (Live& lv : live) {
+                            if (!lv.active) continue;
+                            h->st = lv.st;
+                            lv.frac = geweke_fraction(h, *lv.ch, it, gcounts);
+                            if (gp.verbose) std::printf("%g%% converged.\n", r_round3_percent(lv.frac));
+                            if (lv.frac > 0.995) { lv.it_final = it; lv.active = false; --n_active; }
+                        }
+                    }
+                }
+                for (Live& lv : live) {
+                    h->st = lv.st;
+                    finish_chain(*lv.ch, lv.a, lv.it_final, lv.frac);
+                    CDL_CUDA(cudaStreamSynchronize(lv.st));
+                    h->chains.push_back(std::move(lv.ch));
+                }
+            } catch (...) {
+                h->st = home;
+                cudaDeviceSynchronize();
+                live.clear();
+                for (auto s : streams) if (s) cudaStreamDestroy(s);
+                throw;
+            }
+            h->st = home;
+            for (auto s : streams) if (s) cudaStreamDestroy(s);
         }
         if (h->p2p_active) {
             unsigned int perr = 0;
