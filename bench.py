@@ -208,7 +208,8 @@ def run_ours(args):
 
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu:
-        cpu = cpu_baseline(args.workload, args.cpu_cells, args.cpu_iters, procs=1)
+        cpu = cpu_sparse_port(args.workload, budget_s=20.0, counts=h.export_csc_u16())
+        cpu["dense_reference_shaped"] = cpu_dense_reference_shaped(args.workload, args.cpu_cells, args.cpu_iters)
 
     if rank == 0:
         out = {
@@ -246,9 +247,9 @@ def run_ours(args):
         dist.destroy_process_group()
 
 
-def _cpu_chain(job):
-    """One reference-algorithm chain (dense, op-for-op restatement) on a cell sample; returns seconds
-    per iteration."""
+def _cpu_dense_chain(job):
+    """One reference-SHAPED chain (dense, op-for-op NumPy restatement of R/clone_id.R:466-593) on a cell sample;
+    returns seconds per iteration."""
     workload, cells, iters, seed = job
     os.environ.setdefault("OMP_NUM_THREADS", "1")
     from oracle import cardelino_oracle as O
@@ -269,23 +270,45 @@ def _cpu_chain(job):
     return dt / (T - 1)
 
 
-def cpu_baseline(workload, cells, iters, procs):
-    """Reference algorithm (R/clone_id.R:466-593 restated in NumPy, float64, dense) on a bounded cell
-    sample; cost is linear in cells, so iterations/s on the full donor = measured * cells / M."""
+def cpu_dense_reference_shaped(workload, cells=64, iters=2):
+    """The reference's own DENSE formulation (4K dense N x M matrices, R/clone_id.R:394-403) cannot hold C3 / C4
+    (SURVEY.md fact 4); timed on a few cells, cost is linear in cells."""
     N, M, K, cov = WORKLOADS[workload]
-    from multiprocessing import get_context
-    jobs = [(workload, cells, iters, 100 + q) for q in range(procs)]
-    if procs == 1:
-        per = [_cpu_chain(jobs[0])]
+    sec = _cpu_dense_chain((workload, cells, iters, 100))
+    return {"value": cells / M / sec, "unit": "Gibbs iterations/s", "cores": 1,
+            "sample": "%d sweeps of the dense R-shaped NumPy restatement on %d of %d cells, scaled linearly in "
+                      "cells" % (iters, cells, M)}
+
+
+def cpu_sparse_port(workload, budget_s=20.0, counts=None):
+    """Best CPU figure: the sparse C / OpenMP restatement (oracle/gibbs_sparse.c, sufficient-statistic form, fp64)
+    on all host threads.  Runs whole sweeps on the full donor when one sweep fits the budget, else on a cell
+    sample (cost is linear in cells) -- says which."""
+    from oracle import c_oracle as CO
+    N, M, K, cov = WORKLOADS[workload]
+    cfg_mask = CO.config_masks(make_config(N, K))
+    threads = CO.threads()
+    probe_cells = min(M, 20000)
+    if counts is None:
+        # no GPU in this process: make the donor on the host with the same distributions
+        p, vi, a, d, _ = CO.synth(N, probe_cells, K, cov, cfg_mask, seed=SEED_DATA)
     else:
-        with get_context("spawn").Pool(procs) as pool:
-            per = pool.map(_cpu_chain, jobs)
-    rate_sample = sum(1.0 / s for s in per)                 # chain-iterations/s on the sample, all procs
-    return {"value": rate_sample * cells / M, "unit": "Gibbs iterations/s", "cores": procs, "kind": "port",
-            "sample": "%d chain(s) x %d sweeps of the dense R-shaped sampler on %d of %d cells (all %d variants, "
-                      "%d clones); linear-in-cells extrapolation to the full donor" %
-                      (procs, iters, cells, M, N, K),
-            "seconds_per_iteration_on_sample": float(np.mean(per))}
+        p, vi, a, d = counts
+        M = p.size - 1                     # this rank's cells
+        probe_cells = min(M, probe_cells)
+    sec, _, _ = CO.run(N, probe_cells, K, p[:probe_cells + 1], vi, a, d, cfg_mask, 2, seed=1)
+    per_cell = sec / 2 / probe_cells
+    Ms = M if per_cell * M * 3 <= budget_s else max(probe_cells, int(budget_s / 3 / per_cell))
+    if counts is None and Ms != probe_cells:
+        p, vi, a, d, _ = CO.synth(N, Ms, K, cov, cfg_mask, seed=SEED_DATA)
+    p = p[:Ms + 1]
+    T = max(2, min(20, int(budget_s / max(per_cell * Ms, 1e-9))))
+    sec, _, _ = CO.run(N, Ms, K, p, vi, a, d, cfg_mask, T, seed=1)
+    return {"value": T / sec * Ms / M, "unit": "Gibbs iterations/s", "cores": threads, "kind": "port",
+            "sample": "%d sweeps of the sparse C/OpenMP restatement (oracle/gibbs_sparse.c, fp64) on %d of %d cells "
+                      "(all %d variants, %d clones), %d threads%s" %
+                      (T, Ms, M, N, K, threads, "" if Ms == M else "; scaled linearly in cells to the full donor"),
+            "seconds_per_sweep_on_sample": sec / T}
 
 
 def run_reference(args):
@@ -293,27 +316,32 @@ def run_reference(args):
     if rank != 0:
         return
     N, M, K, cov = WORKLOADS[args.workload]
-    procs = os.cpu_count() or 1
     t0 = time.perf_counter()
-    per_step = []
-    cpu = None
+    vals, cpu = [], None
+    budget = max(5.0, 120.0 / max(1, args.steps + args.warmup))
     for s in range(args.warmup + args.steps):
-        c = cpu_baseline(args.workload, args.cpu_cells, args.cpu_iters, procs)
+        c = cpu_sparse_port(args.workload, budget_s=budget)
         if s >= args.warmup:
-            per_step.append(c["value"])
+            vals.append(c["value"])
             cpu = c
         if time.perf_counter() - t0 > 150:
             break
-    value = float(np.mean(per_step)) if per_step else cpu_baseline(args.workload, args.cpu_cells, 1, procs)["value"]
-    cpu = dict(cpu or {}, value=value)
+    if not vals:
+        cpu = cpu_sparse_port(args.workload, budget_s=5.0)
+        vals = [cpu["value"]]
+    value = float(np.mean(vals))
+    cpu = dict(cpu, value=value)
+    dense = cpu_dense_reference_shaped(args.workload)
     out = {"impl": "reference", "metric": "Gibbs iterations/sec", "value": value, "unit": "Gibbs iterations/s",
-           "n_gpus": args.gpus, "steps": len(per_step), "warmup": args.warmup,
+           "n_gpus": args.gpus, "steps": len(vals), "warmup": args.warmup,
            "ms_per_step": 1e3 / value if value else None, "higher_is_better": True, "scaling": "strong",
-           "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-           "config": {"workload": "%s: %d variants x %d cells x %d clones, %.0f%% coverage (reference algorithm "
-                                  "restated in NumPy; R is not installed; dense formulation cannot hold the "
-                                  "full donor, see cpu_baseline.sample)" % (args.workload, N, M, K, cov * 100)},
-           "cpu_baseline": cpu,
+           "vs_baseline": None, "dtype": "f64", "data": "synthetic (host generator with sim_read_count's distributions)",
+           "config": {"workload": "%s: %d variants x %d cells x %d clones, %.0f%% coverage, wise=variant, "
+                                  "relax_Config=TRUE, 1 chain.  R is not installed here: the reference ALGORITHM is "
+                                  "timed as the sparse C/OpenMP restatement on all host threads (the best CPU figure); "
+                                  "its dense R-shaped formulation is in dense_reference_shaped" %
+                                  (args.workload, N, M, K, cov * 100)},
+           "cpu_baseline": cpu, "dense_reference_shaped": dense,
            "e2e": {"value": value, "unit": "Gibbs iterations/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
     print(json.dumps(out))
 

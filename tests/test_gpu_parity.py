@@ -462,6 +462,44 @@ def test_full_size_properties(gpu_handle):
     assert abs(g - ll[it - 1]) <= 1e-9 * abs(g)
 
 
+@pytest.mark.parametrize("workload", ["C3", "C4s8"])
+def test_full_size_sweep_against_c_oracle(gpu_handle, workload):
+    """At BASELINE's shapes (C3: 2000 x 100 000 x 8; a 1/8 shard of C4: 10 000 x 125 000 x 16) one sweep of the CUDA
+    path is recomputed by the sparse C oracle from the same state (theta of trace row 1, input Config) and the
+    same Philox uniforms: every probability to 1e-9, every label (unless its uniform sits on a CDF boundary),
+    every Config flip and the logLik of the sweep."""
+    import bench
+    from oracle import c_oracle as CO
+    from oracle import philox
+    N, M, K, cov = bench.WORKLOADS[workload]
+    cfg = bench.make_config(N, K)
+    h = gpu_handle
+    h.synth_generate(N, M, K, cfg, cov, 31)
+    _, _, nnz, W = h.data_info()
+    p, vi, a, d = h.export_csc_u16()
+    seed = 12
+    h.gibbs_run(cfg, None, min_iter=3, max_iter=3, seed=seed, keep_prob_all=1, keep_assign_all=1)
+    t0, t1 = h.fetch("theta_traces")
+    prob_g = h.fetch("prob_all")[1].reshape(K, M).T
+    z_g = h.fetch("assign_all")[1] - 1
+    cfg_g = h.fetch("Config_all")[1].reshape(K, N).T
+    ll_g = h.fetch("logLik")[1]
+    u = philox.uniforms(seed, 0, 2, philox.STREAM_ASSIGN, np.arange(M))
+    prob_c, z_c, SA, SB = CO.sweep_cells(N, M, K, p, vi, a, d, CO.config_masks(cfg), t0[0], t1[0], np.full(K, 1 / K), u)
+    assert np.abs(prob_g - prob_c).max() <= 1e-9
+    bad = np.flatnonzero(z_g != z_c)
+    assert bad.size <= 2
+    for j in bad:                                    # only a uniform within 1e-6 of a CDF boundary may differ
+        cdf = np.cumsum(np.sort(prob_c[j])[::-1])
+        assert np.abs(cdf - u[j]).min() <= 1e-6
+    if bad.size == 0:
+        uc = philox.uniforms(seed, 0, 2, philox.STREAM_CONFIG, np.arange(N * K))
+        mask_new, S1, S2, S3, S4, ll_c, diff1 = CO.sweep_table(SA, SB, CO.config_masks(cfg), True, True, 0.1,
+                                                               t0[0], t1[0], uc, W)
+        assert np.array_equal(CO.masks_to_config(mask_new, K), cfg_g)
+        assert abs(ll_g - ll_c) <= 1e-9 * abs(ll_c)
+
+
 def test_error_paths(gpu_handle, example_donor):
     cb = _cb()
     A, D, Z = example_donor

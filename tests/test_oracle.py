@@ -148,3 +148,70 @@ def test_gibbs_statistical_sanity(example_donor):
     assert 0.3 < np.nanmean(g["theta1"]) < 0.6
     assert -1350 < g["logLik"][-1] < -1100
     assert 0.5 < (g["prob"].max(1) > 0.5).mean() < 0.85
+
+
+# ---- the sparse C restatement (oracle/gibbs_sparse.c) is pinned against the NumPy one ----
+
+def _csc(A, D):
+    A1, B1, W = O.preprocess(A, D)
+    Dn = A1 + B1
+    N, M = Dn.shape
+    cols = [np.flatnonzero(Dn[:, j] > 0) for j in range(M)]
+    p = np.concatenate([[0], np.cumsum([c.size for c in cols])]).astype(np.int64)
+    vi = np.concatenate(cols).astype(np.int32)
+    jj = np.repeat(np.arange(M), [c.size for c in cols])
+    return A1, B1, W, p, vi, A1[vi, jj].astype(np.uint16), Dn[vi, jj].astype(np.uint16)
+
+
+@pytest.mark.parametrize("wise", ["variant", "global"])
+def test_c_oracle_sweep_matches_numpy_oracle(example_donor, c2_donor, wise):
+    from oracle import c_oracle as CO
+    rng = np.random.default_rng(4)
+    for A, D, Z in (example_donor, c2_donor[:3]):
+        A1, B1, W, p, vi, a, d = _csc(A, D)
+        N, M = A1.shape
+        K = Z.shape[1]
+        cfg = (rng.random((N, K)) < 0.4).astype(float)
+        cfg[:, 0] = 0
+        th0 = 0.013
+        th1 = rng.uniform(0.2, 0.8, N) if wise == "variant" else np.array([0.41])
+        th1v = th1 if wise == "variant" else np.full(N, th1[0])
+        Psi = rng.dirichlet(np.ones(K) * 5)
+        u = rng.random(M)
+        prob_o, lab_o = O.sweep_tables(A1, B1, cfg, th0, th1v, Psi, u)
+        prob_c, z, SA, SB = CO.sweep_cells(N, M, K, p, vi, a, d, CO.config_masks(cfg), th0, th1, Psi, u)
+        assert np.abs(prob_c - prob_o).max() <= 1e-12
+        assert np.array_equal(z + 1, lab_o)                       # includes the all-tied uncovered cells (revsort)
+        Zm = np.zeros((M, K)); Zm[np.arange(M), z] = 1
+        assert np.array_equal(SA, (A1 @ Zm).astype(np.uint64)) and np.array_equal(SB, (B1 @ Zm).astype(np.uint64))
+        # table step vs the dense formulas of R/clone_id.R:525-535,546-562 and get_logLik (:734-752)
+        uc = rng.random(N * K)
+        for relax_rate, keep_base in ((0.13, True), (0.5, False)):
+            mask_new, S1, S2, S3, S4, ll, diff1 = CO.sweep_table(SA, SB, CO.config_masks(cfg), True, keep_base,
+                                                                 relax_rate, th0, th1, uc, W)
+            l0, l0c = np.log(th0), np.log(1 - th0)
+            l1, l1c = np.log(th1v)[:, None], np.log(1 - th1v)[:, None]
+            odd = SA * (l1 - l0) + SB * (l1c - l0c) + O._config_prior_oddlog(cfg, relax_rate, keep_base)
+            odd = np.clip(odd, -50, 50)
+            pflip = np.exp(odd) / (np.exp(odd) + 1)
+            new = O.r_rbinom1(pflip.T.ravel(), uc).reshape(K, N).T
+            assert np.array_equal(CO.masks_to_config(mask_new, K), new)
+            assert S1 == (SA * (1 - new)).sum() and S2 == (SB * (1 - new)).sum()
+            assert np.array_equal(S3, (SA * new).sum(1)) and np.array_equal(S4, (SB * new).sum(1))
+            assert diff1 == int((new != cfg)[:, 1:].sum())
+            ll_o = O.get_logLik(A1, B1, new, z + 1, th0, np.broadcast_to(th1v[:, None], A1.shape))
+            assert abs(ll - ll_o) <= 1e-9 * abs(ll_o)
+
+
+def test_c_oracle_runner_and_generator():
+    """The timing runner recovers the labels of a donor made by the host generator (same distributions as the
+    device generator): an end-to-end sanity check of the C restatement."""
+    from oracle import c_oracle as CO
+    import bench
+    N, M, K, cov = 400, 3000, 5, 0.15
+    cfg = bench.make_config(N, K, seed=2)
+    p, vi, a, d, lab = CO.synth(N, M, K, cov, CO.config_masks(cfg), seed=9)
+    assert p[-1] == vi.size and abs(p[-1] / (N * M) - cov) < 0.01 and np.all(a <= d) and d.min() >= 1
+    assert all(np.all(np.diff(vi[p[j]:p[j + 1]]) > 0) for j in range(0, M, 97))
+    sec, z, th1 = CO.run(N, M, K, p, vi, a, d, CO.config_masks(cfg), 30, seed=1)
+    assert sec > 0 and (z + 1 == lab).mean() > 0.95 and np.all((th1 > 0) & (th1 < 1))
