@@ -246,11 +246,10 @@ def _collect(h, chain, Av, Config, wise, relabel, verbose, keep_assign_all, ligh
     info = h.gibbs_info(chain)
     it, n_buin = info.n_iter, info.n_buin
     pc = info.percent_converged
-    if info.exact_trace:
-        if pc <= 95 or pc != pc:
-            warnings.warn("Only %s%% of parameters converged. Consider increasing `max_iter`." % pc)
-        elif verbose:
-            print("Converged in %d iterations." % it)
+    if pc <= 95 or pc != pc:
+        warnings.warn("Only %s%% of parameters converged. Consider increasing `max_iter`." % pc)
+    elif verbose:
+        print("Converged in %d iterations." % it)
     theta0, theta1_el = h.fetch("theta", chain)
     theta0_all, theta1_all = h.fetch("theta_traces", chain)
     relax_rate, relax_rate_all = h.fetch("relax_rate", chain)

@@ -816,6 +816,16 @@ int cdl_gibbs_run(cdl_handle h, const double* Config, int32_t K, const double* P
         auto finish_chain = [&](Chain& ch, SweepArgs& a, int64_t it_final, double frac) {
             const int64_t itf = it_final;
             if (exact) frac = geweke_fraction(h, ch, itf, gcounts);
+            else {
+                // streaming mode keeps no prob_all, so the reference's rule (Geweke Z of every prob_all column,
+                // R/clone_id.R:594-601) cannot be evaluated; the same Z test on the theta1 traces -- the model
+                // parameters the assignments follow from -- is reported instead (informational: streaming runs
+                // always do max_iter sweeps)
+                launch_geweke(ch.theta1_all.p, n_el, itf, gcounts.p, h->st);
+                unsigned long long cnt[2];
+                gcounts.download(cnt, 2, h->st);
+                frac = cnt[0] ? (double)cnt[1] / (double)cnt[0] : NAN;
+            }
             ch.info.n_iter = (int32_t)itf;
             ch.info.percent_converged = r_round3_percent(frac);
             const int64_t n_buin = exact ? (int64_t)std::ceil((double)itf * gp.buin_frac) : n_buin_planned;
@@ -829,12 +839,9 @@ int cdl_gibbs_run(cdl_handle h, const double* Config, int32_t K, const double* P
             if (exact) launch_col_means_d(ch.prob_all.p, M * K, r0, r1, ch.prob_mean.p, h->st);
             else {
                 // accumulator holds the sum over rows [n_buin_planned, T]
-                std::vector<double> acc((size_t)(M * K));
-                ch.prob_acc.download(acc.data(), acc.size(), h->st);
-                const double inv = 1.0 / (double)(r1 - r0);
-                for (double& v : acc) v *= inv;
-                ch.prob_mean.upload(acc.data(), acc.size(), h->st);
-                CDL_CUDA(cudaStreamSynchronize(h->st));
+                CDL_CUDA(cudaMemcpyAsync(ch.prob_mean.p, ch.prob_acc.p, sizeof(double) * (size_t)(M * K),
+                                         cudaMemcpyDeviceToDevice, h->st));
+                launch_scale(ch.prob_mean.p, M * K, 1.0 / (double)(r1 - r0), h->st);
             }
             ch.config_prob.alloc((size_t)(N * K));
             launch_col_means_u8(ch.config_all.p, N * K, r0, r1, ch.config_prob.p, h->st);
@@ -959,10 +966,9 @@ int cdl_fetch_prob(cdl_handle h, int32_t chain, double* out) {
     return guard(h, [&] {
         Chain& ch = get_chain(h, chain);
         const int64_t M = h->donor.M, K = h->K;
-        std::vector<double> t((size_t)(M * K));
-        ch.prob_mean.download(t.data(), t.size(), h->st);
-        for (int64_t j = 0; j < M; ++j)
-            for (int64_t k = 0; k < K; ++k) out[j + k * M] = t[(size_t)(j * K + k)];
+        DevBuf<double> t((size_t)(M * K));                           // [cell][clone] -> R's column-major M x K
+        launch_transpose_scale(ch.prob_mean.p, M, K, 1.0, t.p, h->st);
+        t.download(out, (size_t)(M * K), h->st);
     });
 }
 
@@ -988,10 +994,9 @@ int cdl_fetch_theta_traces(cdl_handle h, int32_t chain, double* theta0_all, doub
         if (theta0_all) ch.theta0_all.download(theta0_all, n, h->st);
         if (theta1_all) {
             // R shape n_iter x n_element column-major
-            std::vector<double> t(n * (size_t)h->n_el);
-            ch.theta1_all.download(t.data(), t.size(), h->st);
-            for (size_t r = 0; r < n; ++r)
-                for (size_t e = 0; e < (size_t)h->n_el; ++e) theta1_all[r + e * n] = t[r * (size_t)h->n_el + e];
+            DevBuf<double> t(n * (size_t)h->n_el);
+            launch_transpose_scale(ch.theta1_all.p, (int64_t)n, h->n_el, 1.0, t.p, h->st);
+            t.download(theta1_all, n * (size_t)h->n_el, h->st);
         }
     });
 }

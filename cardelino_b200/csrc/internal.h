@@ -172,6 +172,8 @@ void launch_el_theta(const Donor& d, const SweepArgs& a, ChainDev& c, cudaStream
 void launch_geweke(const double* prob_all, int64_t cols, int64_t n_rows, unsigned long long* counts2,
                    cudaStream_t st);  // counts2[0] = #non-NaN, counts2[1] = #|Z|<=2
 void launch_col_means_d(const double* X, int64_t cols, int64_t r0, int64_t r1, double* out, cudaStream_t st);
+void launch_transpose_scale(const double* in, int64_t R, int64_t C, double scale, double* out, cudaStream_t st);
+void launch_scale(double* x, int64_t n, double s, cudaStream_t st);
 void launch_col_means_u8(const uint8_t* X, int64_t cols, int64_t r0, int64_t r1, double* out, cudaStream_t st);
 void launch_prob_variant(const Donor& d, int wise, const double* theta0_all, const double* theta1_all,
                          int64_t n_el, int64_t r0, int64_t r1, double* out_dense, cudaStream_t st);   // wise 2 needs d.c_elem0

@@ -237,6 +237,51 @@ inline unsigned warp_grid(int64_t M, int threads) {
 
 }  // namespace
 
+namespace {
+// out[c * R + r] = in[r * C + c] (row-major R x C -> column-major R x C, i.e. R's layout), optionally scaled
+template <bool SWAP>
+__global__ void k_transpose_scale(const double* __restrict__ in, int64_t R, int64_t C, double scale,
+                                  double* __restrict__ out) {
+    __shared__ double tile[32][33];
+    const int64_t r0 = (int64_t)(SWAP ? blockIdx.y : blockIdx.x) * 32, c0 = (int64_t)(SWAP ? blockIdx.x : blockIdx.y) * 32;
+    for (int dy = threadIdx.y; dy < 32; dy += blockDim.y) {
+        const int64_t r = r0 + dy, c = c0 + threadIdx.x;
+        if (r < R && c < C) tile[dy][threadIdx.x] = in[r * C + c] * scale;
+    }
+    __syncthreads();
+    for (int dy = threadIdx.y; dy < 32; dy += blockDim.y) {
+        const int64_t c = c0 + dy, r = r0 + threadIdx.x;
+        if (r < R && c < C) out[c * R + r] = tile[threadIdx.x][dy];
+    }
+}
+
+__global__ void k_scale(double* __restrict__ x, int64_t n, double s) {
+    const int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+    if (i < n) x[i] *= s;
+}
+
+}  // namespace
+
+void launch_transpose_scale(const double* in, int64_t R, int64_t C, double scale, double* out, cudaStream_t st) {
+    if (R <= 0 || C <= 0) return;
+    const int64_t rb = (R + 31) / 32, cbk = (C + 31) / 32;      // the longer side goes on grid.x (no 65535 limit)
+    dim3 block(32, 8);
+    if (rb >= cbk) {
+        if (cbk > 65535) throw Error(5, "matrix too large for the transpose kernel");
+        k_transpose_scale<false><<<dim3((unsigned)rb, (unsigned)cbk), block, 0, st>>>(in, R, C, scale, out);
+    } else {
+        if (rb > 65535) throw Error(5, "matrix too large for the transpose kernel");
+        k_transpose_scale<true><<<dim3((unsigned)cbk, (unsigned)rb), block, 0, st>>>(in, R, C, scale, out);
+    }
+    CDL_CUDA(cudaGetLastError());
+}
+
+void launch_scale(double* x, int64_t n, double s, cudaStream_t st) {
+    if (n <= 0) return;
+    k_scale<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(x, n, s);
+    CDL_CUDA(cudaGetLastError());
+}
+
 void launch_geweke(const double* prob_all, int64_t cols, int64_t n_rows, unsigned long long* counts2,
                    cudaStream_t st) {
     CDL_CUDA(cudaMemsetAsync(counts2, 0, 2 * sizeof(unsigned long long), st));

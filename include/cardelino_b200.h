@@ -85,7 +85,7 @@ typedef struct cdl_gibbs_info {
     int32_t n_buin;              /* ceiling(it * buin_frac) (:604) */
     int32_t n_element;           /* 1, N or nnz (:406-416) */
     int32_t exact_trace;         /* 1 if prob_all was kept */
-    double  percent_converged;   /* (:595) */
+    double  percent_converged;   /* (:595); streaming mode (no prob_all): the same Geweke test on the theta1 traces */
     double  logLik_post;         /* (:656) */
     double  W_log;               /* (:388) */
     double  dic[6];              /* DIC, logLik_var, D_mean, D_post, DIC_Gelman, DIC_Spiegelhalter (:790-797) */
