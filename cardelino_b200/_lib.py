@@ -18,7 +18,7 @@ EXPORTS = [
     "cdl_fetch_prob", "cdl_fetch_config_prob", "cdl_fetch_theta", "cdl_fetch_theta_traces",
     "cdl_fetch_loglik_trace", "cdl_fetch_relax_rate", "cdl_fetch_prob_all", "cdl_fetch_config_all",
     "cdl_fetch_assign_all", "cdl_fetch_prob_variant", "cdl_fetch_element_index", "cdl_get_loglik",
-    "cdl_em_run", "cdl_bench_sweeps", "cdl_set_cells_layout", "cdl_set_exchange_mode", "cdl_exchange_is_peer",
+    "cdl_em_run", "cdl_bench_sweeps", "cdl_set_cells_layout", "cdl_set_exchange_mode", "cdl_exchange_is_peer", "cdl_incremental_full_passes",
 ]
 
 WISE = {"global": 0, "variant": 1, "element": 2}
@@ -39,7 +39,7 @@ class GibbsParams(C.Structure):
         ("max_iter", C.c_int32), ("buin_frac", C.c_double), ("wise", C.c_int32), ("n_chain", C.c_int32),
         ("seed", C.c_uint64), ("keep_assign_all", C.c_int32), ("keep_prob_all", C.c_int32),
         ("trace_budget_bytes", C.c_int64), ("check_every", C.c_int32), ("verbose", C.c_int32),
-        ("acc_fp32", C.c_int32),
+        ("acc_fp32", C.c_int32), ("incremental_stats", C.c_int32),
     ]
 
 
@@ -235,6 +235,11 @@ class Handle:
                                            C.byref(rp) if rp is not None else None))
         self._N, self._K = N, K
         return p
+
+    def incremental_full_passes(self, chain=0):
+        out = C.c_uint32()
+        self._check(self.lib.cdl_incremental_full_passes(self.h, C.c_int32(chain), C.byref(out)))
+        return out.value
 
     def gibbs_info(self, chain=0):
         info = GibbsInfo()

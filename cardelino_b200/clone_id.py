@@ -189,7 +189,7 @@ def clone_id_Gibbs(A, D, Config, Psi=None, relax_Config=True, relax_rate_fixed=N
                    keep_base_clone=True, prior0=(0.2, 99.8), prior1=(0.45, 0.55), min_iter=5000,
                    max_iter=20000, buin_frac=0.5, wise="variant", relabel=False, verbose=True,
                    seed=1, n_chain=1, replay=None, keep_assign_all=False, keep_prob_all=-1,
-                   handle=None, light=False, _loaded=False, _all_chains=False):
+                   handle=None, light=False, incremental_stats=False, _loaded=False, _all_chains=False):
     """R/clone_id.R:351-675.  Returns the reference's list (:662-673) as a dict.  Extra arguments: `seed`
     (Philox key; the reference uses R's global RNG), `n_chain` (chains run inside the library), `replay`
     (dict of injected draws, see cdl_replay)."""
@@ -223,7 +223,8 @@ def clone_id_Gibbs(A, D, Config, Psi=None, relax_Config=True, relax_rate_fixed=N
                 prior1_matrix=prior1_matrix, min_iter=int(min_iter), max_iter=int(max_iter),
                 buin_frac=float(buin_frac), wise=wise, n_chain=int(n_chain), seed=int(seed),
                 keep_assign_all=int(bool(keep_assign_all)),
-                keep_prob_all=1 if relabel else int(keep_prob_all), verbose=0)
+                keep_prob_all=1 if relabel else int(keep_prob_all), verbose=0,
+                incremental_stats=int(bool(incremental_stats)))
     outs = [_collect(h, c, Av, Config, wise, relabel, verbose, keep_assign_all, light) for c in range(n_chain)]
     return outs if _all_chains else outs[0]
 

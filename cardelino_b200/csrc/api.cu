@@ -73,7 +73,9 @@ struct Chain {
     DevBuf<uint32_t> mask;
     DevBuf<uint8_t> z, config_all, assign_all;
     DevBuf<unsigned long long> sab, part_u;
-    DevBuf<unsigned int> ticket, work, sell_tickets, stats_work;
+    DevBuf<unsigned int> ticket, work, sell_tickets, stats_work, chg_ctl;
+    DevBuf<uint32_t> chg_list;
+    DevBuf<uint8_t> chg_old;
     DevBuf<double> sell_scratch;
     DevBuf<double2> tab_g;
     // summaries
@@ -349,8 +351,10 @@ bool p2p_ensure(cdl_handle h, size_t elems) {
     return true;
 }
 
-void one_sweep(cdl_handle h, Chain& ch, SweepArgs& a, uint32_t it, const cdl_replay* rp_dev, int64_t n_el) {
+void one_sweep(cdl_handle h, Chain& ch, SweepArgs& a, uint32_t it, const cdl_replay* rp_dev, int64_t n_el,
+               uint32_t rng_advance = 0) {
     a.it = it;
+    a.rng_it = it + rng_advance;
     const cdl_gibbs_params& gp = h->gp;
     a.learn_relax_next = (a.relax && !a.relax_fixed_set && ((double)(it + 1) > 0.1 * gp.min_iter + 5.0)) ? 1 : 0;
     if (rp_dev) {
@@ -386,7 +390,8 @@ void one_sweep(cdl_handle h, Chain& ch, SweepArgs& a, uint32_t it, const cdl_rep
         h->launches += 4;   // + k_signal
     } else {
         a.p2p = nullptr;
-        launch_stats(h->donor, a, ch.dev, h->sm_count, h->st);
+        if (a.incremental) { launch_stats_incremental(h->donor, a, ch.dev, h->sm_count, h->st); h->launches += 2; }
+        else launch_stats(h->donor, a, ch.dev, h->sm_count, h->st);
         allreduce_u64(h, ch.dev.sab, (size_t)(a.N * a.K));
         launch_table(h->donor, a, ch.dev, h->st);
         h->launches += 3;   // k_cells / k_cells_sell, k_stats, k_table (+ memset nodes)
@@ -718,6 +723,8 @@ int cdl_gibbs_run(cdl_handle h, const double* Config, int32_t K, const double* P
         a.W_log = allreduce_scalar_d(h, d.W_log);
         a.key = PhiloxKey{(uint32_t)(gp.seed & 0xffffffffu), (uint32_t)(gp.seed >> 32)};
         a.T = T;
+        // incremental statistics: single GPU, per-variant tables (the element path keeps fp64 sums)
+        a.incremental = (gp.incremental_stats && h->world == 1 && !element) ? 1 : 0;
 
         // replay arrays -> device
         DevBuf<double> r_ua, r_uc, r_t0, r_t1, r_rr;
@@ -793,6 +800,15 @@ int cdl_gibbs_run(cdl_handle h, const double* Config, int32_t K, const double* P
             ch.dev.el_l1 = ch.el_l1.p; ch.dev.el_l1c = ch.el_l1c.p; ch.dev.sd1 = ch.sd1.p;
             ch.dev.work = ch.work.p;
             ch.dev.stats_work = ch.stats_work.p;
+            ch.chg_ctl.alloc(4); ch.chg_ctl.zero(h->st);
+            ch.dev.chg_ctl = ch.chg_ctl.p; ch.dev.chg_list = nullptr; ch.dev.chg_old = nullptr;
+            if (a.incremental) {
+                ch.chg_list.alloc((size_t)M); ch.chg_old.alloc((size_t)M);
+                ch.dev.chg_list = ch.chg_list.p; ch.dev.chg_old = ch.chg_old.p;
+                const unsigned int ctl0[4] = {0u, 1u, 1u, 0u};          // the first sweep takes the full pass
+                ch.chg_ctl.upload(ctl0, 4, h->st);
+                CDL_CUDA(cudaStreamSynchronize(h->st));
+            }
             ch.dev.sell_scratch = nullptr; ch.dev.sell_tickets = nullptr;
             if (h->use_sell && d.s_slices < 64 * (int64_t)h->sm_count) {
                 const int KPs = K <= 4 ? 4 : (K <= 8 ? 8 : (K <= 16 ? 16 : 32));
@@ -804,6 +820,7 @@ int cdl_gibbs_run(cdl_handle h, const double* Config, int32_t K, const double* P
             a.chain = (uint32_t)c;
             // initial draws (row 1)
             a.it = 1;
+            a.rng_it = 1;
             a.learn_relax_next = (a.relax && !a.relax_fixed_set && (2.0 > 0.1 * gp.min_iter + 5.0)) ? 1 : 0;
             if (rp) {
                 a.rp_theta0 = rp->theta0; a.rp_theta1 = rp->theta1;
@@ -960,6 +977,15 @@ int cdl_gibbs_run(cdl_handle h, const double* Config, int32_t K, const double* P
 
 int cdl_gibbs_info_get(cdl_handle h, int32_t chain, cdl_gibbs_info* out) {
     return guard(h, [&] { *out = get_chain(h, chain).info; });
+}
+
+int cdl_incremental_full_passes(cdl_handle h, int32_t chain, uint32_t* out) {
+    return guard(h, [&] {
+        Chain& ch = get_chain(h, chain);
+        unsigned int ctl[4] = {0, 0, 0, 0};
+        ch.chg_ctl.download(ctl, 4, h->st);
+        *out = ctl[3];
+    });
 }
 
 int cdl_fetch_prob(cdl_handle h, int32_t chain, double* out) {
@@ -1177,10 +1203,11 @@ int cdl_bench_sweeps(cdl_handle h, int32_t warmup, int32_t n, float* ms_total, f
         CDL_CUDA(cudaEventCreate(&e0));
         CDL_CUDA(cudaEventCreate(&e1));
         // warm-up and timed sweeps go down the stream back to back; the start event sits between them
-        for (int w = 0; w < warmup; ++w) one_sweep(h, ch, a, it, nullptr, h->n_el);
+        uint32_t adv = 0;                        // fresh Philox streams for every bench sweep (the trace row is reused)
+        for (int w = 0; w < warmup; ++w) one_sweep(h, ch, a, it, nullptr, h->n_el, ++adv);
         const int64_t l0 = h->launches;
         CDL_CUDA(cudaEventRecord(e0, h->st));
-        for (int q = 0; q < n; ++q) one_sweep(h, ch, a, it, nullptr, h->n_el);
+        for (int q = 0; q < n; ++q) one_sweep(h, ch, a, it, nullptr, h->n_el, ++adv);
         CDL_CUDA(cudaEventRecord(e1, h->st));
         CDL_CUDA(cudaEventSynchronize(e1));
         float tot = 0;
@@ -1194,6 +1221,7 @@ int cdl_bench_sweeps(cdl_handle h, int32_t warmup, int32_t n, float* ms_total, f
             for (auto& e : ev) CDL_CUDA(cudaEventCreate(&e));
             for (int q = 0; q < n; ++q) {
                 a.it = it;
+                a.rng_it = it + (++adv);
                 a.learn_relax_next = (a.relax && !a.relax_fixed_set && ((double)(it + 1) > 0.1 * h->gp.min_iter + 5.0)) ? 1 : 0;
                 CDL_CUDA(cudaEventRecord(ev[0], h->st));
                 if (h->use_sell) launch_cells_sell(h->donor, a, ch.dev, h->sm_count, h->st);
@@ -1208,7 +1236,8 @@ int cdl_bench_sweeps(cdl_handle h, int32_t warmup, int32_t n, float* ms_total, f
                     launch_signal(q, h->st);
                 } else {
                     a.p2p = nullptr;
-                    launch_stats(h->donor, a, ch.dev, h->sm_count, h->st);
+                    if (a.incremental) launch_stats_incremental(h->donor, a, ch.dev, h->sm_count, h->st);
+                    else launch_stats(h->donor, a, ch.dev, h->sm_count, h->st);
                     allreduce_u64(h, ch.dev.sab, (size_t)(a.N * a.K));
                 }
                 CDL_CUDA(cudaEventRecord(ev[2], h->st));

@@ -31,6 +31,9 @@ struct CellsParams {
     uint8_t* z;
     uint8_t* assign_row;       // [M] 1-based labels or nullptr
     const double* rp_u;        // replay uniforms for this iteration or nullptr
+    uint32_t* chg_list;        // incremental statistics: cells whose label changes are appended here (or nullptr)
+    uint8_t* chg_old;
+    unsigned int* chg_count;
     PhiloxKey key;
     uint32_t chain, it;
     int tab_in_smem;
@@ -237,6 +240,30 @@ __device__ __forceinline__ int lane_draw(const double (&pr)[KP], int K, double u
         sel = perm[jj];
     }
     return sel;
+}
+
+// label write-back; with incremental statistics the cells whose label changed are appended to a list (one
+// atomic per warp)
+__device__ __forceinline__ void store_label(const CellsParams& C, bool writer, int64_t cell, int sel) {
+    if (C.chg_list) {
+        const uint8_t old = writer ? C.z[cell] : (uint8_t)sel;
+        const bool changed = writer && old != (uint8_t)sel;
+        const unsigned m = __ballot_sync(0xffffffffu, changed);
+        if (m) {
+            const int lane = threadIdx.x & 31;
+            unsigned base = 0;
+            if (lane == __ffs(m) - 1) base = atomicAdd(C.chg_count, (unsigned)__popc(m));
+            base = __shfl_sync(0xffffffffu, base, __ffs(m) - 1);
+            if (changed) {
+                const unsigned idx = base + (unsigned)__popc(m & ((1u << lane) - 1u));
+                if ((int64_t)idx < C.M) { C.chg_list[idx] = (uint32_t)cell; C.chg_old[idx] = old; }
+            }
+        }
+    }
+    if (writer) {
+        C.z[cell] = (uint8_t)sel;
+        if (C.assign_row) C.assign_row[cell] = (uint8_t)(sel + 1);
+    }
 }
 
 }  // namespace

@@ -263,10 +263,7 @@ __global__ void __launch_bounds__(SELL_THREADS, 1) k_cells_sell(const SellParams
             while (jj < K - 1 && !(u <= pa[jj])) ++jj;
             sel = perm[jj];
         }
-        if (valid) {
-            C.z[jl] = (uint8_t)sel;
-            if (C.assign_row) C.assign_row[jl] = (uint8_t)(sel + 1);
-        }
+        store_label(C, valid, (int64_t)jl, sel);
     }
 }
 
@@ -491,7 +488,8 @@ void launch_cells_sell(const Donor& d, const SweepArgs& a, ChainDev& c, int sm_c
     C.z = c.z;
     C.assign_row = c.assign_all ? c.assign_all + row * d.M : nullptr;
     C.rp_u = a.rp_u_assign;
-    C.key = a.key; C.chain = a.chain; C.it = a.it;
+    C.key = a.key; C.chain = a.chain; C.it = a.rng_it;
+    C.chg_list = a.incremental ? c.chg_list : nullptr; C.chg_old = c.chg_old; C.chg_count = c.chg_ctl;
     P.slice_off = d.s_off; P.perm = d.s_perm;
     P.v8 = nullptr; P.a8 = (const uint4*)d.s_a; P.b8 = (const uint4*)d.s_b;
     P.n_slices = d.s_slices;

@@ -187,10 +187,7 @@ __global__ void __launch_bounds__(CELLS_THREADS, (KP <= 8 ? 2 : 1)) k_cells(cons
                 sel = (unsigned)perm[jj];
             }
         }
-        if (valid && lig == 0) {
-            P.z[j] = (uint8_t)sel;
-            if (P.assign_row) P.assign_row[j] = (uint8_t)(sel + 1);
-        }
+        store_label(P, valid && lig == 0, j, (int)sel);
     }
 }
 
@@ -215,6 +212,7 @@ struct StatsParams {
     int64_t N, M;
     int K;
     int n_cb;             // cell blocks
+    const unsigned int* run_flag;   // incremental mode: the full pass runs only if *run_flag != 0 (else nullptr)
     const int* plan;      // [grid + 2 * n_cb]: home block of each CTA, first CTA and CTA count of each block
     int chunks_per_warp;  // 1: one static range per warp; > 1: ranges are pulled from the block's counter
     unsigned int* work;   // [n_cb] chunk counters (zeroed before the launch; used when chunks_per_warp > 1)
@@ -282,6 +280,7 @@ __device__ __forceinline__ void stats_flush(uint32_t* __restrict__ bins, int lan
 // the kernel is bound by the latency of the shared-memory update chain as much as by HBM.
 template <int KP>
 __global__ void __launch_bounds__(STATS_THREADS, 2) k_stats_stream(const StatsParams P) {
+    if (P.run_flag && *P.run_flag == 0) return;      // the incremental update already produced this sweep's table
     extern __shared__ __align__(16) unsigned char smem_raw[];
     uint32_t* s_bins = reinterpret_cast<uint32_t*>(smem_raw);                  // [WARPS][KP][32]
     uint8_t* s_z = smem_raw + sizeof(uint32_t) * STATS_WARPS * KP * 32;        // [cells of the staged block]
@@ -424,6 +423,7 @@ __global__ void __launch_bounds__(STATS_THREADS, 2) k_stats_stream(const StatsPa
 // others, helping wherever units are left.
 template <int KP>
 __global__ void __launch_bounds__(STATS_THREADS, 2) k_stats_units(const StatsParams P) {
+    if (P.run_flag && *P.run_flag == 0) return;      // the incremental update already produced this sweep's table
     extern __shared__ __align__(16) unsigned char smem_raw[];
     uint32_t* s_bins = reinterpret_cast<uint32_t*>(smem_raw);                  // [WARPS][KP][32]
     uint8_t* s_z = smem_raw + sizeof(uint32_t) * STATS_WARPS * KP * 32;        // [cells of the staged block]
@@ -505,6 +505,55 @@ __global__ void __launch_bounds__(STATS_THREADS, 2) k_stats_units(const StatsPar
     }
 }
 
+// ---- incremental statistics (opt-in) ---------------------------------------------------------------
+// SA / SB are integer sums over the cells of each label, so when few labels changed in a sweep the table of the
+// previous sweep can be corrected instead of recomputed: for every changed cell, move its row's counts from the
+// old label's column to the new one.  Exact (integers), so the chain is bit-identical to the full pass.  A
+// converged chain on an informative donor changes a handful of labels per sweep; early sweeps, or donors whose
+// cells stay uncertain, exceed the threshold and take the full pass (k_stats_* with run_flag set).
+struct IncrParams {
+    const uint32_t* rowgrp; const void* vidx; const uint16_t* ca; const uint16_t* cb; int vidx32;
+    const uint8_t* z; const uint32_t* chg_list; const uint8_t* chg_old;
+    unsigned int* ctl;            // [0] changed count, [1] need full pass (out), [2] force full pass, [3] full passes
+    unsigned long long* sab;
+    int64_t M, NK;
+    int K;
+    unsigned int threshold;
+};
+
+__global__ void __launch_bounds__(256) k_stats_incr(const IncrParams P) {
+    const unsigned int count = P.ctl[0];
+    const bool full = P.ctl[2] != 0 || count > P.threshold;
+    if (blockIdx.x == 0 && threadIdx.x == 0) P.ctl[1] = full ? 1u : 0u;
+    if (full) return;
+    const int lane = threadIdx.x & 31;
+    const int64_t warp = (blockIdx.x * (int64_t)blockDim.x + threadIdx.x) >> 5;
+    const int64_t nwarps = ((int64_t)gridDim.x * blockDim.x) >> 5;
+    for (int64_t q = warp; q < (int64_t)count; q += nwarps) {
+        const int64_t j = P.chg_list[q];
+        const int zo = P.chg_old[q], zn = P.z[j];
+        const int64_t e0 = (int64_t)P.rowgrp[j] * GROUP, e1 = (int64_t)P.rowgrp[j + 1] * GROUP;
+        for (int64_t e = e0 + lane; e < e1; e += 32) {
+            const unsigned long long a = P.ca[e], b = P.cb[e];
+            if ((a | b) == 0) continue;
+            const int64_t v = P.vidx32 ? reinterpret_cast<const uint32_t*>(P.vidx)[e]
+                                       : reinterpret_cast<const uint16_t*>(P.vidx)[e];
+            const unsigned long long w = a | (b << 32);
+            atomicAdd(&P.sab[v * P.K + zn], w);
+            atomicAdd(&P.sab[v * P.K + zo], 0ull - w);     // the packed halves borrow and repay: net exact
+        }
+    }
+}
+
+// between the incremental update and the full pass: clear the table if the full pass is going to run, and
+// re-arm the control words for the next sweep
+__global__ void k_stats_prepare_full(unsigned int* ctl, unsigned long long* sab, int64_t NK) {
+    const bool full = ctl[1] != 0;
+    const int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+    if (full && i < NK) sab[i] = 0ull;
+    if (i == 0) { ctl[0] = 0u; ctl[2] = 0u; if (full) ctl[3] += 1u; }
+}
+
 // ------------------------------------------------------------------------------------------------
 struct TableParams {
     int64_t N;
@@ -523,6 +572,7 @@ struct TableParams {
     double* theta0_all; double* theta1_all; double* loglik_all; double* relax_all; uint8_t* config_all;
     int64_t T;
     uint32_t it;               // 1-based row being filled
+    uint32_t rng_it;           // iteration in the Philox keys
     PhiloxKey key; uint32_t chain;
     const double* rp_u_config; const double* rp_theta0; const double* rp_theta1; const double* rp_relax_next;
     double* part_d; unsigned long long* part_u; unsigned int* ticket;
@@ -621,7 +671,7 @@ __global__ void __launch_bounds__(TABLE_THREADS) k_table(const TableParams P) {
             const double p = ex / (ex + 1.0);
             const uint32_t idx = (uint32_t)(i + (int64_t)k * P.N);
             const double u = P.rp_u_config ? P.rp_u_config[idx]
-                                           : philox_uniform(P.key, P.chain, P.it, STREAM_CONFIG, idx);
+                                           : philox_uniform(P.key, P.chain, P.rng_it, STREAM_CONFIG, idx);
             bit = (uint32_t)rbinom1(p, u);
         }
         // Config_all row (:535); with relax off the row holds Config itself (the reference stops
@@ -687,7 +737,7 @@ __global__ void __launch_bounds__(TABLE_THREADS) k_table(const TableParams P) {
     {
         const int j = threadIdx.x;
         double shape = -1.0;
-        uint32_t stream = 0, idx = 0, it = P.it;
+        uint32_t stream = 0, idx = 0, it = P.rng_it;
         if (j < 2 * VPB) {
             const int64_t iv = (int64_t)blockIdx.x * VPB + (j >> 1);
             if (P.wise == 1 && iv < P.N && !P.rp_theta1) {
@@ -705,7 +755,7 @@ __global__ void __launch_bounds__(TABLE_THREADS) k_table(const TableParams P) {
                 const double d1 = (double)s_tot[4];
                 shape = (q == 2) ? P.relax_prior[0] + d1
                                  : P.relax_prior[1] + (double)P.N * (double)(P.K - 1) - d1;
-                stream = STREAM_RELAX; it = P.it + 1;
+                stream = STREAM_RELAX; it = P.rng_it + 1;
             } else if (q >= 4 && P.wise == 0 && !P.rp_theta1) {
                 const double pa = P.prior1_mat ? P.prior1_mat[0] : P.prior1[0];
                 const double pb = P.prior1_mat ? P.prior1_mat[1] : P.prior1[1];
@@ -898,7 +948,8 @@ void launch_cells(const Donor& d, const SweepArgs& a, ChainDev& c, int sm_count,
     P.z = c.z;
     P.assign_row = c.assign_all ? c.assign_all + row * d.M : nullptr;
     P.rp_u = a.rp_u_assign;
-    P.key = a.key; P.chain = a.chain; P.it = a.it;
+    P.key = a.key; P.chain = a.chain; P.it = a.rng_it;
+    P.chg_list = a.incremental ? c.chg_list : nullptr; P.chg_old = c.chg_old; P.chg_count = c.chg_ctl;
     const size_t smem = (size_t)cells_smem_bytes(d.N, a.K);
     const bool smem_tab = smem <= 200 * 1024;
     P.tab_in_smem = smem_tab;
@@ -974,9 +1025,24 @@ std::vector<int> stats_plan(const std::vector<int64_t>& groups_per_cb, int ctas)
     return plan;
 }
 
+void launch_stats_incremental(const Donor& d, const SweepArgs& a, ChainDev& c, int sm_count, cudaStream_t st) {
+    IncrParams P{};
+    P.rowgrp = d.c_rowgrp; P.vidx = d.c_vidx; P.ca = d.c_a; P.cb = d.c_b; P.vidx32 = d.vidx32 ? 1 : 0;
+    P.z = c.z; P.chg_list = c.chg_list; P.chg_old = c.chg_old; P.ctl = c.chg_ctl; P.sab = c.sab;
+    P.M = d.M; P.NK = d.N * a.K; P.K = a.K;
+    P.threshold = (unsigned int)std::max<int64_t>(1, d.M / 32);      // ~3 % of the cells
+    k_stats_incr<<<(unsigned)(sm_count * 4), 256, 0, st>>>(P);
+    CDL_CUDA(cudaGetLastError());
+    k_stats_prepare_full<<<(unsigned)((P.NK + 255) / 256), 256, 0, st>>>(c.chg_ctl, c.sab, P.NK);
+    CDL_CUDA(cudaGetLastError());
+    launch_stats(d, a, c, sm_count, st);             // exits at once unless the full pass is needed
+}
+
 void launch_stats(const Donor& d, const SweepArgs& a, ChainDev& c, int sm_count, cudaStream_t st) {
-    CDL_CUDA(cudaMemsetAsync(c.sab, 0, sizeof(unsigned long long) * (size_t)(d.N * a.K), st));
+    if (!a.incremental)
+        CDL_CUDA(cudaMemsetAsync(c.sab, 0, sizeof(unsigned long long) * (size_t)(d.N * a.K), st));
     StatsParams P{};
+    P.run_flag = a.incremental ? c.chg_ctl + 1 : nullptr;
     P.seggrp = d.v_seggrp; P.flush = d.v_flush; P.vc = d.v_cell; P.va = d.v_a; P.vb = d.v_b; P.z = c.z; P.sab = c.sab;
     P.N = d.N; P.M = d.M; P.K = a.K; P.n_cb = d.n_cb;
     const int KP = pad_k(a.K);
@@ -1051,7 +1117,7 @@ void launch_table(const Donor& d, const SweepArgs& a, ChainDev& c, cudaStream_t 
     P.W_log = a.W_log;
     P.theta0_all = c.theta0_all; P.theta1_all = c.theta1_all; P.loglik_all = c.loglik_all;
     P.relax_all = c.relax_all; P.config_all = c.config_all;
-    P.T = a.T; P.it = a.it; P.key = a.key; P.chain = a.chain;
+    P.T = a.T; P.it = a.it; P.rng_it = a.rng_it; P.key = a.key; P.chain = a.chain;
     P.rp_u_config = a.rp_u_config; P.rp_theta0 = a.rp_theta0; P.rp_theta1 = a.rp_theta1;
     P.rp_relax_next = a.rp_relax_next;
     P.part_d = c.part_d; P.part_u = c.part_u; P.ticket = c.ticket;

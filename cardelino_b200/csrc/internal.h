@@ -106,6 +106,10 @@ struct ChainDev {
     double2* tab_g;      // (du, dv) table in global memory when it does not fit shared memory, else nullptr
     double* sell_scratch;        // [s_slices][4][32][KP] partial logits of split slices (small shards) or nullptr
     unsigned int* sell_tickets;  // [s_slices]
+    // incremental statistics (opt-in): cells whose label changed in this sweep, and control words
+    uint32_t* chg_list;          // [M] local cell ids
+    uint8_t* chg_old;            // [M] their previous labels
+    unsigned int* chg_ctl;       // [4]: changed count, need-full-pass flag, force-full flag, full passes done
     unsigned int* work;  // dynamic work-item counter of k_cells_sell
     unsigned int* stats_work;    // [n_cb] dynamic unit counters of k_stats
 };
@@ -146,6 +150,8 @@ struct SweepArgs {
     const uint32_t* cfg0;       // [N] input Config bit masks
     double W_log;
     PhiloxKey key; uint32_t chain; uint32_t it;   // it = 1-based trace row being filled
+    uint32_t rng_it;                              // iteration in the Philox keys (== it except in the bench hook)
+    int incremental;                              // update SA/SB from the changed cells when they are few
     int64_t T;                                    // trace rows allocated
     // replay (device pointers to row `it-1`), nullptr = own draws
     const double* rp_u_assign; const double* rp_u_config;
@@ -160,6 +166,7 @@ void launch_init_chain(const SweepArgs& a, ChainDev& c, cudaStream_t st);
 void launch_cells(const Donor& d, const SweepArgs& a, ChainDev& c, int sm_count, cudaStream_t st);
 void launch_cells_sell(const Donor& d, const SweepArgs& a, ChainDev& c, int sm_count, cudaStream_t st);
 void launch_stats(const Donor& d, const SweepArgs& a, ChainDev& c, int sm_count, cudaStream_t st);
+void launch_stats_incremental(const Donor& d, const SweepArgs& a, ChainDev& c, int sm_count, cudaStream_t st);
 void launch_table(const Donor& d, const SweepArgs& a, ChainDev& c, cudaStream_t st);
 void launch_signal(const P2PState& q, cudaStream_t st);
 // wise = element (element.cu)

@@ -64,6 +64,9 @@ typedef struct cdl_gibbs_params {
     int32_t check_every;         /* convergence check period, reference value 100 (:580) */
     int32_t verbose;
     int32_t acc_fp32;            /* reserved, must be 0 (fp64 accumulation) */
+    int32_t incremental_stats;   /* 1: when at most ~3 % of the cells changed label in a sweep, correct the previous
+                                    sweep's SA/SB table from those cells instead of re-reading every count (exact:
+                                    integer sums, bit-identical chains); single GPU, wise = global / variant */
 } cdl_gibbs_params;
 
 /* Optional injected draws ("replay mode", north_star correctness check 2).  Any pointer may be NULL,
@@ -152,6 +155,8 @@ void cdl_gibbs_defaults(cdl_gibbs_params* p);
 int cdl_gibbs_run(cdl_handle h, const double* Config, int32_t K, const double* Psi,
                   const cdl_gibbs_params* params, const cdl_replay* replay /* may be NULL */);
 int cdl_gibbs_info_get(cdl_handle h, int32_t chain, cdl_gibbs_info* out);
+/* incremental_stats = 1: how many sweeps of the chain (bench sweeps included) took the full statistic pass */
+int cdl_incremental_full_passes(cdl_handle h, int32_t chain, uint32_t* out);
 /* Fetch fields of the reference return list (:662-673); `chain` selects the chain.  All column-major
  * doubles with R's shapes, EXCEPT the three big traces (prob_all, Config_all, assign_all), which are
  * returned ROW-major (n_iter rows, R's column order within a row: cell j + clone k * M, variant

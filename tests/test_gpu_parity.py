@@ -247,6 +247,40 @@ def test_element_wise_matches_oracle(gpu_handle, example_donor, kw):
     assert 0.2 < g["theta1_all"][0].mean() < 0.7
 
 
+def test_incremental_statistics_are_exact(gpu_handle, example_donor):
+    """incremental_stats corrects the previous sweep's SA/SB table from the cells whose label changed (integer
+    sums): chains are bit-identical to the full pass.  example_donor: most cells stay uncertain, so the ~3 %
+    threshold sends nearly every sweep down the full pass; an informative synthetic donor: after a few sweeps only
+    a handful of labels move and the incremental path carries the chain."""
+    cb = _cb()
+    A, D, Z = example_donor
+    kw = dict(min_iter=40, max_iter=40, seed=8, keep_assign_all=True, handle=gpu_handle, verbose=False)
+    a = cb.clone_id_Gibbs(A, D, Z, **kw)
+    b = cb.clone_id_Gibbs(A, D, Z, incremental_stats=True, **kw)
+    for f in ("prob_all", "assign_all", "Config_all", "theta1_all", "logLik"):
+        assert np.array_equal(a[f], b[f]), f
+    import bench
+    for layout, (N, M, K, cov) in (("rows", (2000, 9000, 6, 0.15)), ("slices", (2000, 40000, 6, 0.15))):
+        cfg = bench.make_config(N, K, seed=7)
+        h = gpu_handle
+        h.set_cells_layout(layout)
+        h.synth_generate(N, M, K, cfg, cov, 55)
+        out = {}
+        T = 30
+        for inc in (0, 1):
+            h.gibbs_run(cfg, None, min_iter=T, max_iter=T, seed=3, keep_prob_all=0, keep_assign_all=1,
+                        incremental_stats=inc)
+            out[inc] = (h.fetch("assign_all"), h.fetch("Config_all"), h.fetch("theta_traces"), h.fetch("logLik"))
+        h.set_cells_layout("auto")
+        full = h.incremental_full_passes()
+        assert np.array_equal(out[0][0], out[1][0]) and np.array_equal(out[0][1], out[1][1])
+        assert np.array_equal(out[0][2][1], out[1][2][1]) and np.array_equal(out[0][3], out[1][3])
+        changed = (out[0][0][2:] != out[0][0][1:-1]).sum(1)           # labels that moved, sweeps 3..T
+        expect_full = 1 + int((changed > M // 32).sum())             # sweep 2 is forced, then by the threshold
+        assert full == expect_full, (full, expect_full, changed)
+        assert full < T - 1, changed                                  # the incremental path really ran
+
+
 def test_replay_mode(gpu_handle, example_donor):
     """Correctness check 2 of the north star: inject a recorded run's uniforms and theta draws; the
     assignments and Config flips must be reproduced."""
