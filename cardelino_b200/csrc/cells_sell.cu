@@ -508,7 +508,7 @@ void launch_cells_sell(const Donor& d, const SweepArgs& a, ChainDev& c, int sm_c
     const size_t smem = (size_t)d.N * (sizeof(double2) + (packed ? 0 : sizeof(uint32_t)));
     const bool smem_tab = smem <= 216 * 1024;
     C.tab_in_smem = smem_tab;
-    CDL_CUDA(cudaMemsetAsync(c.work, 0, sizeof(unsigned int), st));
+    // c.work is zero on entry: k_table's last block re-arms it (and the chain starts with it zeroed)
     if (!smem_tab) {
         if (!c.tab_g) throw Error(4, "global weight table not allocated");
         k_build_tab_sell<<<(unsigned)((d.N + 255) / 256), 256, 0, st>>>(d.N, C.n_tab, packed ? 1 : 0, c.l1, c.l1c,

@@ -564,6 +564,10 @@ struct TableParams {
     const uint32_t* cfg0;
     uint32_t* mask;
     const unsigned long long* sab;
+    unsigned long long* sab_next;   // table the NEXT sweep's k_stats accumulates into: cleared here, element by
+                                    // element, once this sweep's value has been read (saves a memset per sweep);
+                                    // nullptr with incremental statistics, which carry the table over
+    unsigned int* sell_work;        // k_cells_sell's work counter, re-armed by the last block
     const double* sd1;         // wise = element: SD[i,k] = sum_{j: z_j = k} A ln th1_ij + B ln(1 - th1_ij), else nullptr
     double* scal;
     double* l1;
@@ -657,6 +661,7 @@ __global__ void __launch_bounds__(TABLE_THREADS) k_table(const TableParams P) {
         const uint32_t c0 = P.cfg0[i];
         unsigned long long pk = P.sab[i * P.K + k];
         for (int q = 0; q < P.n_peer; ++q) pk += ld_peer_u64(P.peer_sab[q] + i * P.K + k);
+        if (P.sab_next) P.sab_next[i * P.K + k] = 0ull;
         const double SA = (double)(uint32_t)pk, SB = (double)(uint32_t)(pk >> 32);
         const double sd = element ? P.sd1[i * P.K + k] : 0.0;       // per-entry theta1: the theta1 part, summed
         const uint32_t cbit = (c0 >> k) & 1u;
@@ -728,6 +733,7 @@ __global__ void __launch_bounds__(TABLE_THREADS) k_table(const TableParams P) {
         tl = block_sum_d(tl, sm_d);
         if (threadIdx.x == 0) {
             *P.ticket = 0;
+            if (P.sell_work) *P.sell_work = 0u;
             P.loglik_all[(int64_t)P.it - 1] = tl + P.W_log;
             s_tot[0] = t1; s_tot[1] = t2; s_tot[2] = t3; s_tot[3] = t4; s_tot[4] = td;
         }
@@ -1039,8 +1045,7 @@ void launch_stats_incremental(const Donor& d, const SweepArgs& a, ChainDev& c, i
 }
 
 void launch_stats(const Donor& d, const SweepArgs& a, ChainDev& c, int sm_count, cudaStream_t st) {
-    if (!a.incremental)
-        CDL_CUDA(cudaMemsetAsync(c.sab, 0, sizeof(unsigned long long) * (size_t)(d.N * a.K), st));
+    // c.sab is zero on entry: k_table clears it while it reads it (and the chain starts with a zeroed table)
     StatsParams P{};
     P.run_flag = a.incremental ? c.chg_ctl + 1 : nullptr;
     P.seggrp = d.v_seggrp; P.flush = d.v_flush; P.vc = d.v_cell; P.va = d.v_a; P.vb = d.v_b; P.z = c.z; P.sab = c.sab;
@@ -1121,6 +1126,8 @@ void launch_table(const Donor& d, const SweepArgs& a, ChainDev& c, cudaStream_t 
     P.rp_u_config = a.rp_u_config; P.rp_theta0 = a.rp_theta0; P.rp_theta1 = a.rp_theta1;
     P.rp_relax_next = a.rp_relax_next;
     P.part_d = c.part_d; P.part_u = c.part_u; P.ticket = c.ticket;
+    P.sell_work = c.work;
+    P.sab_next = (a.incremental || a.wise == 2) ? nullptr : c.sab;
     P.n_peer = 0;
     if (a.p2p && a.p2p->n_peer > 0) {
         const P2PState& q = *a.p2p;
@@ -1129,6 +1136,7 @@ void launch_table(const Donor& d, const SweepArgs& a, ChainDev& c, cudaStream_t 
             P.peer_sab[r] = q.peer_arena[r] + (size_t)(q.epoch & 1ull) * q.table_elems;
             P.peer_rank[r] = q.peer_rank[r];
         }
+        P.sab_next = q.arena + (size_t)((q.epoch + 1ull) & 1ull) * q.table_elems;   // not read by any peer any more
         P.my_flags = q.my_flags;
         P.epoch = q.epoch;
         P.p2p_error = q.error;
