@@ -39,7 +39,7 @@ class GibbsParams(C.Structure):
         ("max_iter", C.c_int32), ("buin_frac", C.c_double), ("wise", C.c_int32), ("n_chain", C.c_int32),
         ("seed", C.c_uint64), ("keep_assign_all", C.c_int32), ("keep_prob_all", C.c_int32),
         ("trace_budget_bytes", C.c_int64), ("check_every", C.c_int32), ("verbose", C.c_int32),
-        ("acc_fp32", C.c_int32), ("incremental_stats", C.c_int32),
+        ("acc_fp32", C.c_int32), ("chain_offset", C.c_int32), ("incremental_stats", C.c_int32),
     ]
 
 

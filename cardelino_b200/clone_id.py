@@ -189,7 +189,8 @@ def clone_id_Gibbs(A, D, Config, Psi=None, relax_Config=True, relax_rate_fixed=N
                    keep_base_clone=True, prior0=(0.2, 99.8), prior1=(0.45, 0.55), min_iter=5000,
                    max_iter=20000, buin_frac=0.5, wise="variant", relabel=False, verbose=True,
                    seed=1, n_chain=1, replay=None, keep_assign_all=False, keep_prob_all=-1,
-                   handle=None, light=False, incremental_stats=False, _loaded=False, _all_chains=False):
+                   handle=None, light=False, incremental_stats=False, chain_offset=0, _loaded=False,
+                   _all_chains=False):
     """R/clone_id.R:351-675.  Returns the reference's list (:662-673) as a dict.  Extra arguments: `seed`
     (Philox key; the reference uses R's global RNG), `n_chain` (chains run inside the library), `replay`
     (dict of injected draws, see cdl_replay)."""
@@ -224,7 +225,7 @@ def clone_id_Gibbs(A, D, Config, Psi=None, relax_Config=True, relax_rate_fixed=N
                 buin_frac=float(buin_frac), wise=wise, n_chain=int(n_chain), seed=int(seed),
                 keep_assign_all=int(bool(keep_assign_all)),
                 keep_prob_all=1 if relabel else int(keep_prob_all), verbose=0,
-                incremental_stats=int(bool(incremental_stats)))
+                incremental_stats=int(bool(incremental_stats)), chain_offset=int(chain_offset))
     outs = [_collect(h, c, Av, Config, wise, relabel, verbose, keep_assign_all, light) for c in range(n_chain)]
     return outs if _all_chains else outs[0]
 
@@ -300,6 +301,26 @@ def _collect(h, chain, Av, Config, wise, relabel, verbose, keep_assign_all, ligh
     return out
 
 
+def merge_chains(outs):
+    """Chain merge of R/clone_id.R:165-181: match every chain's clone columns to chain 1 with colMatch(force=TRUE),
+    then average prob, relax_rate and Config_prob; every other field is chain 1's.  `outs` are per-chain results
+    (dicts with at least prob, relax_rate, Config_prob) -- from one GPU or gathered from several."""
+    out = dict(outs[0])
+    out["n_chain"] = 1
+    n_chain = len(outs)
+    for ii in range(1, n_chain):
+        out["n_chain"] += 1
+        idx = colMatch(out["prob"], outs[ii]["prob"], force=True)
+        out["prob"] = out["prob"] + outs[ii]["prob"][:, idx]
+        out["relax_rate"] = out["relax_rate"] + outs[ii]["relax_rate"]
+        out["Config_prob"] = out["Config_prob"] + outs[ii]["Config_prob"][:, idx]
+    if n_chain > 1:
+        out["prob"] = out["prob"] / n_chain
+        out["relax_rate"] = out["relax_rate"] / n_chain
+        out["Config_prob"] = out["Config_prob"] / n_chain
+    return out
+
+
 def clone_id(A, D, Config=None, n_clone=None, Psi=None, relax_Config=True, relax_rate_fixed=None,
              inference="sampling", n_chain=1, n_proc=1, verbose=True, handle=None, **kwargs):
     """R/clone_id.R:78-186.  `n_proc` is accepted for signature compatibility; chains run inside the
@@ -350,18 +371,7 @@ def clone_id(A, D, Config=None, n_clone=None, Psi=None, relax_Config=True, relax
     else:
         outs = clone_id_Gibbs(Av, Dv, Cv, Psi=Psi, relax_Config=relax_Config, relax_rate_fixed=relax_rate_fixed,
                               verbose=verbose, n_chain=n_chain, handle=handle, _all_chains=True, **kwargs)
-        out = outs[0]
-        out["n_chain"] = 1
-        for ii in range(1, n_chain):                                 # chain merge, R/clone_id.R:165-181
-            out["n_chain"] += 1
-            idx = colMatch(out["prob"], outs[ii]["prob"], force=True)
-            out["prob"] = out["prob"] + outs[ii]["prob"][:, idx]
-            out["relax_rate"] = out["relax_rate"] + outs[ii]["relax_rate"]
-            out["Config_prob"] = out["Config_prob"] + outs[ii]["Config_prob"][:, idx]
-        if n_chain > 1:
-            out["prob"] = out["prob"] / n_chain
-            out["relax_rate"] = out["relax_rate"] / n_chain
-            out["Config_prob"] = out["Config_prob"] / n_chain
+        out = merge_chains(outs)
     out["cell_names"] = cell_names
     out["clone_names"] = c_cols
     return out

@@ -675,6 +675,8 @@ int cdl_gibbs_run(cdl_handle h, const double* Config, int32_t K, const double* P
         if (gp.relax_Config && gp.relax_rate_fixed_set && (gp.relax_rate_fixed > 1 || gp.relax_rate_fixed < 0))
             throw Error(CDL_ERR_INVALID, "relax_rate_fixed needs to be NULL or in [0, 1].");
         if (gp.n_chain < 1) throw Error(CDL_ERR_INVALID, "n_chain must be >= 1");
+        if (gp.chain_offset < 0 || gp.chain_offset + gp.n_chain > (1 << 23))
+            throw Error(CDL_ERR_INVALID, "chain_offset + n_chain must stay below 2^23 (Philox stream word)");
         if (replay && gp.n_chain != 1) throw Error(CDL_ERR_INVALID, "replay mode runs a single chain");
         if (replay && replay->n_rows < gp.max_iter) throw Error(CDL_ERR_INVALID, "replay arrays shorter than max_iter");
         if (gp.acc_fp32) throw Error(CDL_ERR_UNSUPPORTED, "acc_fp32 is reserved");
@@ -817,7 +819,7 @@ int cdl_gibbs_run(cdl_handle h, const double* Config, int32_t K, const double* P
                 ch.dev.sell_scratch = ch.sell_scratch.p; ch.dev.sell_tickets = ch.sell_tickets.p;
             }
 
-            a.chain = (uint32_t)c;
+            a.chain = (uint32_t)(gp.chain_offset + c);
             // initial draws (row 1)
             a.it = 1;
             a.rng_it = 1;

@@ -73,3 +73,36 @@ def allreduce_sum(arr):
     t = torch.from_numpy(np.ascontiguousarray(arr)).to(dev)
     dist.all_reduce(t)
     return t.cpu().numpy()
+
+
+def chain_groups(n_chain, world):
+    """Chains dealt to ranks in contiguous groups: [(first chain, count)] per rank (counts differ by at most 1)."""
+    edges = [(n_chain * r) // world for r in range(world + 1)]
+    return [(edges[r], edges[r + 1] - edges[r]) for r in range(world)]
+
+
+def clone_id_chain_groups(A, D, Config, n_chain, run_chains=None, **kwargs):
+    """Independent chains placed one group per GPU (BASELINE config 5; the reference forks one process per chain,
+    R/clone_id.R:127-154): every rank holds the whole donor, runs its group of chains with globally unique chain
+    numbers (Philox keys), the per-chain prob / Config_prob / relax_rate are gathered and merged exactly like
+    clone_id() merges them (R/clone_id.R:165-181).  No communication while sampling.  Returns the merged result on
+    every rank.  `run_chains(first, count)` -> list of per-chain dicts replaces the GPU call in tests."""
+    import torch.distributed as dist
+    import importlib
+    _ci = importlib.import_module(__package__ + ".clone_id")     # the module (the package re-exports the function)
+    rank, world = dist.get_rank(), dist.get_world_size()
+    first, count = chain_groups(n_chain, world)[rank]
+    if run_chains is None:
+        def run_chains(first, count):
+            if count == 0:
+                return []
+            return _ci.clone_id_Gibbs(A, D, Config, n_chain=count, chain_offset=first, _all_chains=True, **kwargs)
+    mine = run_chains(first, count)
+    keep = ("prob", "Config_prob", "relax_rate", "theta0", "n_iter", "percent_converged", "logLik_post")
+    slim = [{k: o[k] for k in keep if k in o} for o in mine]
+    gathered = [None] * world
+    dist.all_gather_object(gathered, slim)
+    outs = [o for part in gathered for o in part]
+    merged = _ci.merge_chains(outs)
+    merged["chains"] = outs
+    return merged

@@ -64,6 +64,8 @@ typedef struct cdl_gibbs_params {
     int32_t check_every;         /* convergence check period, reference value 100 (:580) */
     int32_t verbose;
     int32_t acc_fp32;            /* reserved, must be 0 (fp64 accumulation) */
+    int32_t chain_offset;        /* chains are numbered chain_offset .. chain_offset + n_chain - 1 in the Philox keys, so
+                                    chain groups placed on different GPUs / processes draw independent streams */
     int32_t incremental_stats;   /* 1: when at most ~3 % of the cells changed label in a sweep, correct the previous
                                     sweep's SA/SB table from those cells instead of re-reading every count (exact:
                                     integer sums, bit-identical chains); single GPU, wise = global / variant */

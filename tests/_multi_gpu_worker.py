@@ -59,6 +59,23 @@ def main():
                 ok = False
                 msg.append("%s/logLik differs" % mode)
         print(json.dumps({"ok": ok, "world": world, "messages": msg}))
+    # ---- independent chains, one group per GPU (BASELINE config 5): the merged result equals the one of the same
+    # chains (same Philox chain numbers) run in a single process ----
+    d = np.load(os.path.join(ROOT, "tests", "golden", "example_donor.npz"))
+    A, Dm, Z = d["A"], d["D"], d["Z"]
+    hc = cb.Handle(local)
+    kw = dict(min_iter=80, max_iter=80, seed=6, relax_Config=False, verbose=False, keep_prob_all=1)
+    res = D.clone_id_chain_groups(A, Dm, Z, n_chain=4, handle=hc, **kw)
+    if rank == 0:
+        one = cb.clone_id_Gibbs(A, Dm, Z, n_chain=4, handle=hc, _all_chains=True, **kw)
+        import importlib
+        ref = importlib.import_module("cardelino_b200.clone_id").merge_chains(one)
+        same = res["n_chain"] == 4 and np.array_equal(res["prob"], ref["prob"]) and \
+            all(np.array_equal(a["prob"], b["prob"]) for a, b in zip(res["chains"], one))
+        if not same:
+            ok = False
+            msg.append("chain groups differ from the single-process chains")
+        print(json.dumps({"ok": ok, "world": world, "messages": msg}))
     dist.barrier()
     dist.destroy_process_group()
     if rank == 0 and not ok:

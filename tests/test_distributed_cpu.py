@@ -65,3 +65,46 @@ def test_cell_sharding_world2(tmp_path):
     assert np.allclose(r["prob"], prob, rtol=0, atol=1e-13)   # BLAS blocking differs with the shard shape
     assert abs(r["wsum"] - W) < 1e-9
     assert np.array_equal(r["uid"], np.arange(128, dtype=np.uint8))
+
+
+def _chain_worker(rank, world, port, out):
+    import sys
+    sys.path.insert(0, ROOT)
+    import torch.distributed as dist
+    from cardelino_b200 import distributed as D
+    from oracle import cardelino_oracle as O
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    d = np.load(os.path.join(ROOT, "tests", "golden", "example_donor.npz"))
+    A, Dm, Z = d["A"], d["D"], d["Z"]
+
+    def run_chains(first, count):      # the oracle stands in for the GPU library on this CPU-only box
+        return [O.clone_id_Gibbs(A, Dm, Z, min_iter=60, max_iter=60, relax_Config=False, draws=O.NumpyDraws(500 + c))
+                for c in range(first, first + count)]
+
+    res = D.clone_id_chain_groups(A, Dm, Z, n_chain=3, run_chains=run_chains)
+    if rank == 0:
+        np.savez(out, prob=res["prob"], n_chain=res["n_chain"], relax=res["relax_rate"], cfg=res["Config_prob"])
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+def test_chain_groups_world2(tmp_path):
+    """Chains dealt to two ranks (2 + 1), gathered and merged like R/clone_id.R:165-181: the same result as merging
+    the three chains in one process."""
+    from cardelino_b200 import distributed as D
+    import importlib
+    CI = importlib.import_module("cardelino_b200.clone_id")
+    from oracle import cardelino_oracle as O
+    assert D.chain_groups(64, 8) == [(8 * r, 8) for r in range(8)] and D.chain_groups(3, 2) == [(0, 1), (1, 2)]
+    out = str(tmp_path / "chains.npz")
+    mp.spawn(_chain_worker, args=(2, 29517, out), nprocs=2, join=True)
+    r = np.load(out)
+    d = np.load(os.path.join(ROOT, "tests", "golden", "example_donor.npz"))
+    A, Dm, Z = d["A"], d["D"], d["Z"]
+    outs = [O.clone_id_Gibbs(A, Dm, Z, min_iter=60, max_iter=60, relax_Config=False, draws=O.NumpyDraws(500 + c))
+            for c in range(3)]
+    ref = CI.merge_chains(outs)
+    assert int(r["n_chain"]) == 3 and np.allclose(r["prob"], ref["prob"], atol=1e-15)
+    assert np.allclose(r["cfg"], ref["Config_prob"]) and abs(float(r["relax"]) - ref["relax_rate"]) < 1e-15
