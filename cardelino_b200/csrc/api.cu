@@ -722,6 +722,13 @@ int cdl_gibbs_run(cdl_handle h, const double* Config, int32_t K, const double* P
         a.relax_fixed = gp.relax_rate_fixed; a.relax_fixed_set = gp.relax_rate_fixed_set ? 1 : 0;
         fill_logpsi(Psi, K, a.logPsi);
         a.cfg0 = h->cfg0.p;
+        {
+            // base clone (column 1 of Config, all zero in a clonal tree): with keep_base_clone or without relaxation
+            // its column never changes, so no variant ever contributes to its logit
+            bool col0_zero = true;
+            for (uint32_t m : masks) if (m & 1u) { col0_zero = false; break; }
+            a.skip0 = (col0_zero && (!gp.relax_Config || gp.keep_base_clone)) ? 1 : 0;
+        }
         a.W_log = allreduce_scalar_d(h, d.W_log);
         a.key = PhiloxKey{(uint32_t)(gp.seed & 0xffffffffu), (uint32_t)(gp.seed >> 32)};
         a.T = T;

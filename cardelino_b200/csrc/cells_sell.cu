@@ -61,7 +61,7 @@ __device__ __forceinline__ void masked_add8(double (&acc)[KP], double del, uint3
     }
 }
 
-template <int KP, typename VIdx, bool SMEM, bool PACKED>
+template <int KP, typename VIdx, bool SMEM, bool PACKED, bool SKIP0>
 __device__ __forceinline__ void sell_group(double (&acc)[KP], const Grp<VIdx>& q, uint32_t tab_sa, uint32_t msk_sa,
                                            const double2* __restrict__ tab_g, const uint32_t* __restrict__ msk_g) {
 #pragma unroll
@@ -87,7 +87,10 @@ __device__ __forceinline__ void sell_group(double (&acc)[KP], const Grp<VIdx>& q
             // R2P (seven predicates per instruction); testing the low words of du / dv in place makes it
             // emit one LOP3 per clone instead
             const uint32_t m = __byte_perm((uint32_t)__double2loint(du), (uint32_t)__double2loint(dv), 0x7740);
-            masked_add8<0, (KP < 8 ? KP : 8), KP>(acc, del, m);
+            // SKIP0: the base clone's Config column is zero and cannot flip (keep_base_clone), so its logit gets
+            // no contribution at all -- one masked add fewer per entry
+            if (SKIP0) masked_add8<1, (KP < 8 ? KP : 8) - 1, KP>(acc, del, m >> 1);
+            else masked_add8<0, (KP < 8 ? KP : 8), KP>(acc, del, m);
             if (KP > 8) masked_add8<8, KP - 8, KP>(acc, del, m >> 8);
         } else {
             uint32_t m;
@@ -103,7 +106,7 @@ __device__ __forceinline__ void sell_group(double (&acc)[KP], const Grp<VIdx>& q
     }
 }
 
-template <int KP, typename VIdx, bool SMEM, int SELL_THREADS, int SELL_DEPTH, bool SPLIT>
+template <int KP, typename VIdx, bool SMEM, int SELL_THREADS, int SELL_DEPTH, bool SPLIT, bool SKIP0>
 __global__ void __launch_bounds__(SELL_THREADS, 1) k_cells_sell(const SellParams P) {
     constexpr bool PACKED = KP <= 16;
     extern __shared__ __align__(16) unsigned char smem_raw[];
@@ -168,7 +171,7 @@ __global__ void __launch_bounds__(SELL_THREADS, 1) k_cells_sell(const SellParams
                 n[h].load(C.vidx, P.a8, P.b8, min(g + SELL_DEPTH + h, g1 - 1) * 32 + lane);
 #pragma unroll
             for (int h = 0; h < SELL_DEPTH; ++h)
-                if (h == 0 || g + h < g1) sell_group<KP, VIdx, SMEM, PACKED>(acc, q[h], tab_sa, msk_sa, tab_g, msk_g);
+                if (h == 0 || g + h < g1) sell_group<KP, VIdx, SMEM, PACKED, SKIP0>(acc, q[h], tab_sa, msk_sa, tab_g, msk_g);
 #pragma unroll
             for (int h = 0; h < SELL_DEPTH; ++h) q[h] = n[h];
         }
@@ -205,9 +208,10 @@ __global__ void __launch_bounds__(SELL_THREADS, 1) k_cells_sell(const SellParams
             if (k < K) { acc[k] = exp(acc[k] - mx); sm += acc[k]; }
             else acc[k] = 0.0;
         }
+        const double inv_sm = 1.0 / sm;            // one division per cell; each probability is within an ulp of e / sm
 #pragma unroll
         for (int k = 0; k < KP; ++k)
-            if (k < K) acc[k] = acc[k] / sm;
+            if (k < K) acc[k] = acc[k] * inv_sm;
         if (valid) {
             if (C.prob_row) {
                 double* o = C.prob_row + (int64_t)jl * K;
@@ -385,27 +389,29 @@ inline int sell_warps(int64_t n_items, int grid, int max_warps) {
     return (int)w;
 }
 
-template <int KP, typename VIdx, int THREADS, int DEPTH>
+template <int KP, typename VIdx, int THREADS, int DEPTH, bool SKIP0>
 void launch_sell_t(const SellParams& P, bool smem_tab, size_t smem, int grid, cudaStream_t st) {
     const int threads = 32 * sell_warps(P.n_slices * P.parts, grid, THREADS / 32);
     if (smem_tab) {
-        auto kern = P.parts > 1 ? k_cells_sell<KP, VIdx, true, THREADS, DEPTH, true>
-                                : k_cells_sell<KP, VIdx, true, THREADS, DEPTH, false>;
+        auto kern = P.parts > 1 ? k_cells_sell<KP, VIdx, true, THREADS, DEPTH, true, false>
+                                : k_cells_sell<KP, VIdx, true, THREADS, DEPTH, false, SKIP0>;
         CDL_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         kern<<<grid, threads, smem, st>>>(P);
     } else if (P.parts > 1) {
-        k_cells_sell<KP, VIdx, false, THREADS, DEPTH, true><<<grid, threads, 0, st>>>(P);
+        k_cells_sell<KP, VIdx, false, THREADS, DEPTH, true, false><<<grid, threads, 0, st>>>(P);
     } else {
-        k_cells_sell<KP, VIdx, false, THREADS, DEPTH, false><<<grid, threads, 0, st>>>(P);
+        k_cells_sell<KP, VIdx, false, THREADS, DEPTH, false, false><<<grid, threads, 0, st>>>(P);
     }
 }
 
 template <int KP>
-void launch_sell_v(const Donor& d, const SellParams& P, bool smem_tab, size_t smem, int grid, int shape,
+void launch_sell_v(const Donor& d, const SellParams& P, bool smem_tab, size_t smem, int grid, int shape, bool skip0,
                    cudaStream_t st) {
-    if (d.vidx32) { launch_sell_t<KP, uint32_t, 512, 2>(P, smem_tab, smem, grid, st); return; }
-    if (shape == 1) launch_sell_t<KP, uint16_t, 768, 1>(P, smem_tab, smem, grid, st);
-    else launch_sell_t<KP, uint16_t, 512, 2>(P, smem_tab, smem, grid, st);
+    if (d.vidx32) { launch_sell_t<KP, uint32_t, 512, 2, false>(P, smem_tab, smem, grid, st); return; }
+    // the base-clone shortcut is compiled for the shape large donors run in (K <= 16: the mask rides in the weights)
+    if (shape == 1 && skip0 && KP <= 16) launch_sell_t<KP, uint16_t, 768, 1, true>(P, smem_tab, smem, grid, st);
+    else if (shape == 1) launch_sell_t<KP, uint16_t, 768, 1, false>(P, smem_tab, smem, grid, st);
+    else launch_sell_t<KP, uint16_t, 512, 2, false>(P, smem_tab, smem, grid, st);
 }
 
 }  // namespace
@@ -527,10 +533,10 @@ void launch_cells_sell(const Donor& d, const SweepArgs& a, ChainDev& c, int sm_c
     const int64_t max_useful = (d.s_slices + threads / 32 - 1) / (threads / 32);
     if (grid > max_useful) grid = std::max<int64_t>(max_useful, 1);
     switch (KP) {
-        case 4: launch_sell_v<4>(d, P, smem_tab, smem, (int)grid, shape, st); break;
-        case 8: launch_sell_v<8>(d, P, smem_tab, smem, (int)grid, shape, st); break;
-        case 16: launch_sell_v<16>(d, P, smem_tab, smem, (int)grid, shape, st); break;
-        default: launch_sell_v<32>(d, P, smem_tab, smem, (int)grid, shape, st); break;
+        case 4: launch_sell_v<4>(d, P, smem_tab, smem, (int)grid, shape, a.skip0 != 0, st); break;
+        case 8: launch_sell_v<8>(d, P, smem_tab, smem, (int)grid, shape, a.skip0 != 0, st); break;
+        case 16: launch_sell_v<16>(d, P, smem_tab, smem, (int)grid, shape, a.skip0 != 0, st); break;
+        default: launch_sell_v<32>(d, P, smem_tab, smem, (int)grid, shape, false, st); break;
     }
     CDL_CUDA(cudaGetLastError());
 }

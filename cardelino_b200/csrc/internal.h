@@ -151,6 +151,7 @@ struct SweepArgs {
     double W_log;
     PhiloxKey key; uint32_t chain; uint32_t it;   // it = 1-based trace row being filled
     uint32_t rng_it;                              // iteration in the Philox keys (== it except in the bench hook)
+    int skip0;                                    // clone 1's Config column is all zero and cannot flip
     int incremental;                              // update SA/SB from the changed cells when they are few
     int64_t T;                                    // trace rows allocated
     // replay (device pointers to row `it-1`), nullptr = own draws
