@@ -22,7 +22,7 @@ EXPORTS = [
 ]
 
 WISE = {"global": 0, "variant": 1, "element": 2}
-CELLS_LAYOUT = {"auto": 0, "rows": 1, "slices": 2}
+CELLS_LAYOUT = {"auto": 0, "rows": 1, "slices": 2, "small": 3}
 
 
 class CdlError(RuntimeError):

@@ -7,7 +7,7 @@ from concurrent.futures import ThreadPoolExecutor
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 OUT = os.path.join(HERE, "libcardelino_b200.so")
-SOURCES = ["api.cu", "formats.cu", "gibbs.cu", "cells_sell.cu", "element.cu", "post.cu", "synth.cu"]
+SOURCES = ["api.cu", "formats.cu", "gibbs.cu", "cells_sell.cu", "element.cu", "small.cu", "post.cu", "synth.cu"]
 NVCC = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
 FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
          "-Xcompiler", "-fPIC", "-Xptxas", "-v"]
@@ -44,7 +44,7 @@ def build(force=False, verbose=False):
             raise RuntimeError("nvcc failed for %s:\n%s" % (s, r.stdout + r.stderr))
         return s
 
-    with ThreadPoolExecutor(max_workers=7) as ex:
+    with ThreadPoolExecutor(max_workers=8) as ex:
         for s in ex.map(compile_one, jobs):
             if verbose:
                 print("compiled", s)

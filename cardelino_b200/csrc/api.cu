@@ -603,7 +603,7 @@ int cdl_set_shard(cdl_handle h, int64_t cell_offset, int64_t M_total) {
 
 int cdl_set_cells_layout(cdl_handle h, int32_t layout) {
     return guard(h, [&] {
-        if (layout != CDL_CELLS_AUTO && layout != CDL_CELLS_ROWS && layout != CDL_CELLS_SLICES)
+        if (layout != CDL_CELLS_AUTO && layout != CDL_CELLS_ROWS && layout != CDL_CELLS_SLICES && layout != CDL_CELLS_SMALL)
             throw Error(CDL_ERR_INVALID, "unknown cells layout");
         h->cells_layout = layout;
     });
@@ -899,7 +899,61 @@ int cdl_gibbs_run(cdl_handle h, const double* Config, int32_t K, const double* P
                                        (double)T * (double)n_el * 8.0;
         const bool concurrent = gp.n_chain > 1 && h->world == 1 && !rp &&
                                 per_chain_bytes * gp.n_chain <= (double)gp.trace_budget_bytes;
-        if (!concurrent) {
+        // small donors: every chain is one CTA of one grid, check_every sweeps per launch (small.cu)
+        const bool small = (h->cells_layout == CDL_CELLS_SMALL ||
+                            (h->cells_layout == CDL_CELLS_AUTO && d.M_total < 16384)) &&
+                           h->world == 1 && !rp && !element && !a.incremental && small_path_fits(d, K, gp.wise) &&
+                           per_chain_bytes * gp.n_chain <= (double)gp.trace_budget_bytes;
+        if (h->cells_layout == CDL_CELLS_SMALL && !small)
+            throw Error(CDL_ERR_UNSUPPORTED, "the small-donor path does not apply (size, replay, sharding, element or incremental mode)");
+        if (small) {
+            std::vector<std::unique_ptr<Chain>> run;
+            std::vector<SweepArgs> args((size_t)gp.n_chain, a);
+            std::vector<ChainDev> devs((size_t)gp.n_chain);
+            for (int c = 0; c < gp.n_chain; ++c) {
+                run.push_back(start_chain(c, args[(size_t)c]));
+                devs[(size_t)c] = run.back()->dev;
+                devs[(size_t)c].prob_acc = exact ? nullptr : run.back()->prob_acc.p;   // the kernel gates it by iteration
+            }
+            DevBuf<ChainDev> devs_d((size_t)gp.n_chain);
+            DevBuf<int> active_d((size_t)gp.n_chain);
+            devs_d.upload(devs.data(), devs.size(), h->st);
+            std::vector<int> active((size_t)gp.n_chain, 1);
+            std::vector<int64_t> it_final((size_t)gp.n_chain, T);
+            std::vector<double> fr((size_t)gp.n_chain, NAN);
+            int n_active = gp.n_chain;
+            int64_t it = 2;
+            while (it <= T && n_active > 0) {
+                // up to the next point at which the reference checks convergence (:580), at most 1000 sweeps a launch
+                int64_t end = T;
+                if (exact) {
+                    int64_t chk = ((std::max<int64_t>(it, gp.min_iter) + check_every - 1) / check_every) * check_every;
+                    end = std::min<int64_t>(T, chk);
+                }
+                end = std::min<int64_t>(end, it + 999);
+                active_d.upload(active.data(), active.size(), h->st);
+                cdl_small_run r{};
+                r.n_chain = gp.n_chain; r.chain0 = gp.chain_offset; r.min_iter = gp.min_iter; r.exact = exact ? 1 : 0;
+                r.n_buin_planned = n_buin_planned; r.it_begin = (uint32_t)it; r.it_end = (uint32_t)end;
+                r.chains_dev = devs_d.p; r.active_dev = active_d.p;
+                launch_small_chains(d, a, r, h->st);
+                h->launches += 1;
+                if (exact && end >= gp.min_iter && end % check_every == 0) {
+                    for (int c = 0; c < gp.n_chain; ++c) {
+                        if (!active[(size_t)c]) continue;
+                        fr[(size_t)c] = geweke_fraction(h, *run[(size_t)c], end, gcounts);
+                        if (gp.verbose) std::printf("%g%% converged.\n", r_round3_percent(fr[(size_t)c]));
+                        if (fr[(size_t)c] > 0.995) { it_final[(size_t)c] = end; active[(size_t)c] = 0; --n_active; }
+                    }
+                }
+                it = end + 1;
+            }
+            CDL_CUDA(cudaStreamSynchronize(h->st));
+            for (int c = 0; c < gp.n_chain; ++c) {
+                finish_chain(*run[(size_t)c], args[(size_t)c], it_final[(size_t)c], fr[(size_t)c]);
+                h->chains.push_back(std::move(run[(size_t)c]));
+            }
+        } else if (!concurrent) {
             for (int c = 0; c < gp.n_chain; ++c) {
                 std::unique_ptr<Chain> chp = start_chain(c, a);
                 Chain& ch = *chp;

@@ -170,6 +170,16 @@ void launch_stats(const Donor& d, const SweepArgs& a, ChainDev& c, int sm_count,
 void launch_stats_incremental(const Donor& d, const SweepArgs& a, ChainDev& c, int sm_count, cudaStream_t st);
 void launch_table(const Donor& d, const SweepArgs& a, ChainDev& c, cudaStream_t st);
 void launch_signal(const P2PState& q, cudaStream_t st);
+// small donors: whole sweeps of all chains in one launch (small.cu)
+struct cdl_small_run {
+    int n_chain, chain0, min_iter, exact;
+    int64_t n_buin_planned;
+    uint32_t it_begin, it_end;
+    const ChainDev* chains_dev;
+    const int* active_dev;
+};
+bool small_path_fits(const Donor& d, int K, int wise);
+void launch_small_chains(const Donor& d, const SweepArgs& a, const cdl_small_run& r, cudaStream_t st);
 // wise = element (element.cu)
 void launch_el_init(const Donor& d, const SweepArgs& a, ChainDev& c, cudaStream_t st);
 void launch_el_cells(const Donor& d, const SweepArgs& a, ChainDev& c, cudaStream_t st);

@@ -133,8 +133,10 @@ int cdl_set_shard(cdl_handle h, int64_t cell_offset, int64_t M_total);
 
 /* Which cell kernel the Gibbs sweep uses: ROWS = several lanes per cell on the row layout (small donors),
  * SLICES = one lane per cell on the slice-major layout (large donors), AUTO = SLICES when the whole donor
- * has >= 16384 cells.  Results agree to rounding (the per-cell summation order differs). */
-enum { CDL_CELLS_AUTO = 0, CDL_CELLS_ROWS = 1, CDL_CELLS_SLICES = 2 };
+ * has >= 16384 cells.  SMALL = a small donor's whole sweep in one CTA, many sweeps per launch, one CTA per chain
+ * (single GPU, no replay; AUTO takes it whenever the donor fits: <= 65536 cells, <= 2^18 covered entries, N*K <=
+ * 16384).  Results agree to rounding (the per-cell summation order differs). */
+enum { CDL_CELLS_AUTO = 0, CDL_CELLS_ROWS = 1, CDL_CELLS_SLICES = 2, CDL_CELLS_SMALL = 3 };
 int cdl_set_cells_layout(cdl_handle h, int32_t layout);
 
 /* ---- multi-GPU (cells sharded over ranks; one all-reduce of the N x K statistic table per sweep) ----

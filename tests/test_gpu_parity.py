@@ -124,6 +124,48 @@ def test_gibbs_c2_four_chains(gpu_handle, c2_donor):
 
 
 @pytest.fixture()
+def rows_handle(gpu_handle):
+    """The session handle forced onto the three-kernel sweep with the row-split cell kernel (small donors take the
+    single-CTA path of small.cu by default), restored afterwards."""
+    gpu_handle.set_cells_layout("rows")
+    yield gpu_handle
+    gpu_handle.set_cells_layout("auto")
+
+
+@pytest.mark.parametrize("kw", [dict(), dict(wise="global", relax_rate_fixed=0.3), dict(relax_Config=False),
+                                dict(Psi=np.array([0.1, 0.2, 0.3, 0.4]), keep_base_clone=False)])
+def test_three_kernel_path_stepwise(rows_handle, example_donor, kw):
+    A, D, Z = example_donor
+    _verify(_cb(), rows_handle, A, D, Z, T=40, **kw)
+
+
+@pytest.mark.parametrize("K", [3, 12, 20])
+def test_three_kernel_path_denovo(rows_handle, example_donor, K):
+    A, D, _ = example_donor
+    _verify(_cb(), rows_handle, A, D, np.zeros((34, K)), T=25, relax_rate_fixed=0.5)
+
+
+def test_small_path_equals_three_kernel_path(gpu_handle, c2_donor):
+    """Same Philox keys, same Beta sampler: the single-CTA sweep and the three-kernel sweep produce the same chain
+    (labels, Config flips, theta draws; probabilities to rounding), four chains at once."""
+    cb = _cb()
+    A, D, Z, _ = c2_donor
+    out = {}
+    for layout in ("small", "rows"):
+        gpu_handle.set_cells_layout(layout)
+        out[layout] = cb.clone_id_Gibbs(A, D, Z, min_iter=100, max_iter=300, seed=5, n_chain=4, keep_assign_all=True,
+                                        handle=gpu_handle, verbose=False, _all_chains=True)
+    gpu_handle.set_cells_layout("auto")
+    for a, b in zip(out["small"], out["rows"]):
+        assert a["n_iter"] == b["n_iter"]
+        assert np.array_equal(a["assign_all"], b["assign_all"]) and np.array_equal(a["Config_all"], b["Config_all"])
+        assert np.abs(a["prob_all"] - b["prob_all"]).max() <= 1e-12
+        assert np.allclose(a["theta1_all"], b["theta1_all"], rtol=1e-13, atol=0)
+        assert np.allclose(a["logLik"], b["logLik"], rtol=1e-12, atol=0)
+        assert np.abs(a["prob"] - b["prob"]).max() <= 1e-12 and a["percent_converged"] == b["percent_converged"]
+
+
+@pytest.fixture()
 def slices_handle(gpu_handle):
     """The session handle forced onto the slice-major cell kernel (one lane per cell), restored afterwards."""
     gpu_handle.set_cells_layout("slices")
@@ -255,8 +297,10 @@ def test_incremental_statistics_are_exact(gpu_handle, example_donor):
     cb = _cb()
     A, D, Z = example_donor
     kw = dict(min_iter=40, max_iter=40, seed=8, keep_assign_all=True, handle=gpu_handle, verbose=False)
+    gpu_handle.set_cells_layout("rows")          # both runs on the three-kernel sweep (the incremental update lives there)
     a = cb.clone_id_Gibbs(A, D, Z, **kw)
     b = cb.clone_id_Gibbs(A, D, Z, incremental_stats=True, **kw)
+    gpu_handle.set_cells_layout("auto")
     for f in ("prob_all", "assign_all", "Config_all", "theta1_all", "logLik"):
         assert np.array_equal(a[f], b[f]), f
     import bench
