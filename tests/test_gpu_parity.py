@@ -578,6 +578,37 @@ def test_full_size_sweep_against_c_oracle(gpu_handle, workload):
         assert abs(ll_g - ll_c) <= 1e-9 * abs(ll_c)
 
 
+@pytest.mark.parametrize("layout", ["auto", "rows", "slices"])
+def test_edge_shapes(gpu_handle, layout):
+    """Ragged and degenerate inputs on every cell kernel: cells without any covered variant, a variant nobody
+    covers, a single cell, a single variant, K = 2 and K = 32, depth-1 entries only."""
+    cb = _cb()
+    rng = np.random.default_rng(3)
+    gpu_handle.set_cells_layout(layout)
+    try:
+        for N, M, K in ((1, 40, 2), (7, 1, 3), (9, 70, 32), (40, 33, 2)):
+            D = rng.integers(0, 4, (N, M)).astype(float)
+            D[:, ::5] = 0                                   # every fifth cell has no data at all
+            if N > 2:
+                D[2, :] = 0                                 # a variant without any coverage
+            A = rng.binomial(D.astype(int), 0.3).astype(float)
+            D[D == 0] = np.nan
+            A[np.isnan(D)] = np.nan
+            cfg = (rng.random((N, K)) < 0.4).astype(float)
+            cfg[:, 0] = 0
+            if np.isnan(D).all():
+                continue
+            T = 12
+            res = cb.clone_id_Gibbs(A, D, cfg, min_iter=T, max_iter=T, seed=5, keep_assign_all=True,
+                                    handle=gpu_handle, verbose=False)
+            v = O.verify_gibbs_trace(A, D, cfg, res, min_iter=T, seed=5)
+            assert v["max_dprob"] <= 1e-9 and v["hard"] == 0 and v["config_hard"] == 0, (N, M, K, v)
+            assert v["max_dloglik_rel"] <= REL or abs(res["logLik"][-1]) < 1e-9, (N, M, K, v)
+            assert np.allclose(res["prob"].sum(1), 1)
+    finally:
+        gpu_handle.set_cells_layout("auto")
+
+
 def test_error_paths(gpu_handle, example_donor):
     cb = _cb()
     A, D, Z = example_donor
