@@ -116,7 +116,7 @@ SEXP b200_gibbs(SEXP ptr, SEXP Config, SEXP Psi, SEXP params) {
         const int T = info.n_iter, ne = info.n_element;
         const char* fields[] = {"theta0", "theta1_elements", "theta0_all", "theta1_all", "logLik", "prob_all_t", "prob",
                                 "prob_variant", "relax_rate", "Config_prob", "Config_all_t", "relax_rate_all", "DIC",
-                                "n_iter", "percent_converged", ""};
+                                "n_iter", "percent_converged", "element", ""};
         SEXP out = PROTECT(Rf_mkNamed(VECSXP, fields));
         SEXP theta0 = PROTECT(Rf_allocVector(REALSXP, 1));
         SEXP th1 = PROTECT(Rf_allocVector(REALSXP, ne));
@@ -142,11 +142,18 @@ SEXP b200_gibbs(SEXP ptr, SEXP Config, SEXP Psi, SEXP params) {
         check(h, cdl_fetch_config_all(h, c, REAL(call)));
         SEXP dic = PROTECT(Rf_allocVector(REALSXP, 6));
         memcpy(REAL(dic), info.dic, sizeof(double) * 6);
+        /* wise = "element": 1-based positions of the covered entries, which(!is.na(D)) (R/clone_id.R:413-415) */
+        SEXP element = PROTECT(Rf_allocVector(REALSXP, p.wise == CDL_WISE_ELEMENT ? (R_xlen_t)nnz : 0));
+        if (p.wise == CDL_WISE_ELEMENT) {
+            int64_t* el = (int64_t*)R_alloc((size_t)nnz, sizeof(int64_t));
+            check(h, cdl_fetch_element_index(h, el));
+            for (int64_t q = 0; q < nnz; ++q) REAL(element)[q] = (double)(el[q] + 1);
+        }
         SEXP objs[] = {theta0, th1, t0all, t1all, ll, pall, prob, pv, rr, cprob, call, rrall, dic,
-                       PROTECT(Rf_ScalarInteger(T)), PROTECT(Rf_ScalarReal(info.percent_converged))};
-        for (int q = 0; q < 15; ++q) SET_VECTOR_ELT(out, q, objs[q]);
+                       PROTECT(Rf_ScalarInteger(T)), PROTECT(Rf_ScalarReal(info.percent_converged)), element};
+        for (int q = 0; q < 16; ++q) SET_VECTOR_ELT(out, q, objs[q]);
         SET_VECTOR_ELT(chains, c, out);
-        UNPROTECT(16);
+        UNPROTECT(17);
         R_CheckUserInterrupt();
     }
     UNPROTECT(1);

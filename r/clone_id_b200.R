@@ -59,7 +59,8 @@ clone_id_Gibbs <- function(A, D, Config, Psi = NULL,
                     "Consider increasing `max_iter`.", call. = FALSE)
         } else print(paste("Converged in", it, "iterations."))
         theta1 <- matrix(NA, N, M)
-        theta1[seq_len(N * M)] <- ch$theta1_elements             # recycling, R/clone_id.R:469,653
+        element <- if (wise == "element") ch$element else seq_len(N * M)     # idx_mat, R/clone_id.R:406-416
+        theta1[element] <- ch$theta1_elements                    # recycling, R/clone_id.R:469,653
         prob <- ch$prob; rownames(prob) <- colnames(A); colnames(prob) <- colnames(Config)
         Config_prob <- Config; Config_prob[, ] <- ch$Config_prob
         pv <- ch$prob_variant; dimnames(pv) <- dimnames(A)
@@ -67,7 +68,7 @@ clone_id_Gibbs <- function(A, D, Config, Psi = NULL,
         cat(paste("DIC:", round(dic$DIC, 2), "D_mean:", round(dic$D_mean, 2), "D_post:", round(dic$D_post, 2),
                   "logLik_var:", round(dic$logLik_var, 2), "\n"))
         list(theta0 = ch$theta0, theta1 = theta1, theta0_all = ch$theta0_all, theta1_all = ch$theta1_all,
-             element = seq_len(N * M), logLik = ch$logLik, prob_all = t(ch$prob_all_t), prob = prob,
+             element = element, logLik = ch$logLik, prob_all = t(ch$prob_all_t), prob = prob,
              prob_variant = pv, relax_rate = ch$relax_rate, Config_prob = Config_prob,
              Config_all = t(ch$Config_all_t), relax_rate_all = ch$relax_rate_all, DIC = dic)
     }

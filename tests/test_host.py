@@ -121,3 +121,14 @@ def test_bench_reference_arm_line():
     line = json.loads(r.stdout.strip().splitlines()[-1])
     assert line["impl"] == "reference" and line["value"] > 0 and line["cpu_baseline"]["kind"] == "port"
     assert line["e2e"]["h2d_bytes_per_step"] == 0
+
+
+def test_r_shim_compiles_against_stub_headers():
+    """The .Call shim cannot be built here (no R), but it must at least be valid C against the C ABI header: compile
+    it with -fsyntax-only -Wall -Werror against stand-in declarations of the R API entry points it uses."""
+    import subprocess
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    r = subprocess.run(["gcc", "-fsyntax-only", "-Wall", "-Werror", "-I", os.path.join(root, "tests", "r_stub"),
+                        "-I", os.path.join(root, "include"), os.path.join(root, "r", "cardelino_b200_shim.c")],
+                       capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr
