@@ -409,7 +409,9 @@ void launch_sell_v(const Donor& d, const SellParams& P, bool smem_tab, size_t sm
                    cudaStream_t st) {
     if (d.vidx32) { launch_sell_t<KP, uint32_t, 512, 2, false>(P, smem_tab, smem, grid, st); return; }
     // the base-clone shortcut is compiled for the shape large donors run in (K <= 16: the mask rides in the weights)
-    if (shape == 1 && skip0 && KP <= 16) launch_sell_t<KP, uint16_t, 768, 1, true>(P, smem_tab, smem, grid, st);
+    if (shape == 3 && skip0 && KP == 16) launch_sell_t<16, uint16_t, 640, 2, true>(P, smem_tab, smem, grid, st);
+    else if (shape == 4 && skip0 && KP == 16) launch_sell_t<16, uint16_t, 896, 1, true>(P, smem_tab, smem, grid, st);
+    else if (shape == 1 && skip0 && KP <= 16) launch_sell_t<KP, uint16_t, 768, 1, true>(P, smem_tab, smem, grid, st);
     else if (shape == 1) launch_sell_t<KP, uint16_t, 768, 1, false>(P, smem_tab, smem, grid, st);
     else launch_sell_t<KP, uint16_t, 512, 2, false>(P, smem_tab, smem, grid, st);
 }
@@ -529,7 +531,7 @@ void launch_cells_sell(const Donor& d, const SweepArgs& a, ChainDev& c, int sm_c
     if (sell_warps(d.s_slices * P.parts, sm_count, 24) <= 16) shape = 0;
     if (const char* e = getenv("CDL_SELL_SHAPE")) shape = atoi(e);
     int64_t grid = sm_count;
-    const int threads = d.vidx32 ? 512 : (shape == 1 ? 768 : 512);
+    const int threads = d.vidx32 ? 512 : (shape == 1 ? 768 : (shape == 3 ? 640 : (shape == 4 ? 896 : 512)));
     const int64_t max_useful = (d.s_slices + threads / 32 - 1) / (threads / 32);
     if (grid > max_useful) grid = std::max<int64_t>(max_useful, 1);
     switch (KP) {
