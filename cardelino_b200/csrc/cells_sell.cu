@@ -409,8 +409,8 @@ void launch_sell_v(const Donor& d, const SellParams& P, bool smem_tab, size_t sm
                    cudaStream_t st) {
     if (d.vidx32) { launch_sell_t<KP, uint32_t, 512, 2, false>(P, smem_tab, smem, grid, st); return; }
     // the base-clone shortcut is compiled for the shape large donors run in (K <= 16: the mask rides in the weights)
-    if (shape == 3 && skip0 && KP == 16) launch_sell_t<16, uint16_t, 640, 2, true>(P, smem_tab, smem, grid, st);
-    else if (shape == 4 && skip0 && KP == 16) launch_sell_t<16, uint16_t, 896, 1, true>(P, smem_tab, smem, grid, st);
+    // (K = 16 with the base-clone shortcut: 28 warps at 72 registers measured 1.5 % faster than 24 at 80)
+    if (shape == 1 && skip0 && KP == 16) launch_sell_t<16, uint16_t, 896, 1, true>(P, smem_tab, smem, grid, st);
     else if (shape == 1 && skip0 && KP <= 16) launch_sell_t<KP, uint16_t, 768, 1, true>(P, smem_tab, smem, grid, st);
     else if (shape == 1) launch_sell_t<KP, uint16_t, 768, 1, false>(P, smem_tab, smem, grid, st);
     else launch_sell_t<KP, uint16_t, 512, 2, false>(P, smem_tab, smem, grid, st);
@@ -525,13 +525,14 @@ void launch_cells_sell(const Donor& d, const SweepArgs& a, ChainDev& c, int sm_c
     }
     // 24 warps per SM with one group slot of look-ahead beat 16 warps with two (the kernel is bound by the
     // fp64 pipe and needs the extra warps to keep it fed); CDL_SELL_SHAPE overrides for experiments
-    // On a small shard that cannot fill 16 warps per SM anyway the extra warps buy nothing: take the
-    // 16-warp shape, whose two slots of look-ahead hide the HBM latency that few warps cannot.
+    // On a shard so small that even one round of slices cannot fill 16 warps per SM the extra warps buy nothing:
+    // take the 16-warp shape, whose two slots of look-ahead hide the HBM latency that few warps cannot.  (A 1/8
+    // shard of C4 has 27 slices per SM: one round of 27 warps, 0.122 ms, beats two rounds of 14, 0.134 ms.)
     int shape = 1;
-    if (sell_warps(d.s_slices * P.parts, sm_count, 24) <= 16) shape = 0;
+    if (sell_warps(d.s_slices * P.parts, sm_count, (KP == 16 && a.skip0) ? 28 : 24) <= 16) shape = 0;
     if (const char* e = getenv("CDL_SELL_SHAPE")) shape = atoi(e);
     int64_t grid = sm_count;
-    const int threads = d.vidx32 ? 512 : (shape == 1 ? 768 : (shape == 3 ? 640 : (shape == 4 ? 896 : 512)));
+    const int threads = d.vidx32 ? 512 : (shape == 1 ? ((KP == 16 && a.skip0) ? 896 : 768) : 512);
     const int64_t max_useful = (d.s_slices + threads / 32 - 1) / (threads / 32);
     if (grid > max_useful) grid = std::max<int64_t>(max_useful, 1);
     switch (KP) {
