@@ -26,6 +26,8 @@ WORKLOADS = {
     "C4": (10000, 1000000, 16, 0.05),     # BASELINE.json configs[3], the metric's configuration
     "C3": (2000, 100000, 8, 0.19),        # configs[2] (sim_read_count-shaped 19 % coverage)
     "C4s8": (10000, 125000, 16, 0.05),    # one rank's share of C4 at 8 GPUs (tuning aid)
+    "K32": (5000, 200000, 32, 0.05),      # widest clone count (separate mask table, 32 masked adds per entry)
+    "N70k": (70000, 100000, 8, 0.01),     # more than 65536 variants: uint32 variant ids, weight table in global memory
     "tiny": (200, 4000, 4, 0.2),
 }
 SEED_DATA = 20261019 + 4
