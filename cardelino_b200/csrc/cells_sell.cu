@@ -110,6 +110,7 @@ template <int KP, typename VIdx, bool SMEM, int SELL_THREADS, int SELL_DEPTH, bo
 __global__ void __launch_bounds__(SELL_THREADS, 1) k_cells_sell(const SellParams P) {
     constexpr bool PACKED = KP <= 16;
     extern __shared__ __align__(16) unsigned char smem_raw[];
+    pdl_enter();
     const CellsParams& C = P.c;
     uint32_t tab_sa = 0, msk_sa = 0;
     const double2* tab_g = nullptr;
@@ -396,11 +397,11 @@ void launch_sell_t(const SellParams& P, bool smem_tab, size_t smem, int grid, cu
         auto kern = P.parts > 1 ? k_cells_sell<KP, VIdx, true, THREADS, DEPTH, true, false>
                                 : k_cells_sell<KP, VIdx, true, THREADS, DEPTH, false, SKIP0>;
         CDL_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        kern<<<grid, threads, smem, st>>>(P);
+        launch_dep(kern, dim3(grid), dim3(threads), smem, st, P);
     } else if (P.parts > 1) {
-        k_cells_sell<KP, VIdx, false, THREADS, DEPTH, true, false><<<grid, threads, 0, st>>>(P);
+        launch_dep(k_cells_sell<KP, VIdx, false, THREADS, DEPTH, true, false>, dim3(grid), dim3(threads), 0, st, P);
     } else {
-        k_cells_sell<KP, VIdx, false, THREADS, DEPTH, false, false><<<grid, threads, 0, st>>>(P);
+        launch_dep(k_cells_sell<KP, VIdx, false, THREADS, DEPTH, false, false>, dim3(grid), dim3(threads), 0, st, P);
     }
 }
 

@@ -280,6 +280,7 @@ __device__ __forceinline__ void stats_flush(uint32_t* __restrict__ bins, int lan
 // the kernel is bound by the latency of the shared-memory update chain as much as by HBM.
 template <int KP>
 __global__ void __launch_bounds__(STATS_THREADS, 2) k_stats_stream(const StatsParams P) {
+    pdl_enter();
     if (P.run_flag && *P.run_flag == 0) return;      // the incremental update already produced this sweep's table
     extern __shared__ __align__(16) unsigned char smem_raw[];
     uint32_t* s_bins = reinterpret_cast<uint32_t*>(smem_raw);                  // [WARPS][KP][32]
@@ -423,6 +424,7 @@ __global__ void __launch_bounds__(STATS_THREADS, 2) k_stats_stream(const StatsPa
 // others, helping wherever units are left.
 template <int KP>
 __global__ void __launch_bounds__(STATS_THREADS, 2) k_stats_units(const StatsParams P) {
+    pdl_enter();
     if (P.run_flag && *P.run_flag == 0) return;      // the incremental update already produced this sweep's table
     extern __shared__ __align__(16) unsigned char smem_raw[];
     uint32_t* s_bins = reinterpret_cast<uint32_t*>(smem_raw);                  // [WARPS][KP][32]
@@ -630,6 +632,7 @@ __global__ void __launch_bounds__(TABLE_THREADS) k_table(const TableParams P) {
     __shared__ unsigned long long s_s3[VPB], s_s4[VPB], s_tot[5];
     __shared__ double s_gam[NJOB];
     __shared__ bool is_last;
+    pdl_enter();
     const int k = threadIdx.x & (KP - 1);
     const int v = threadIdx.x / KP;
     const int64_t i = (int64_t)blockIdx.x * VPB + v;
@@ -819,6 +822,7 @@ struct SignalParams {
     unsigned long long epoch;
 };
 __global__ void k_signal(const SignalParams P) {
+    pdl_enter();
     if ((int)threadIdx.x < P.n_peer) {
         __threadfence_system();
         st_release_sys_u64(P.peer_flags[threadIdx.x] + P.my_rank, P.epoch);
@@ -908,12 +912,17 @@ template <int KP>
 void launch_stats_t(const StatsParams& P, unsigned grid, size_t smem, bool units, cudaStream_t st) {
     auto kern = units ? k_stats_units<KP> : k_stats_stream<KP>;
     CDL_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    kern<<<grid, STATS_THREADS, smem, st>>>(P);
+    launch_dep(kern, dim3(grid), dim3(STATS_THREADS), smem, st, P);
 }
 
 int pad_k(int K) { return K <= 4 ? 4 : (K <= 8 ? 8 : (K <= 16 ? 16 : 32)); }
 
 }  // namespace
+
+bool pdl_enabled() {
+    static const bool on = [] { const char* e = getenv("CDL_PDL"); return !(e && e[0] == '0'); }();
+    return on;
+}
 
 int cells_smem_bytes(int64_t N, int K) {
     (void)K;
@@ -1104,7 +1113,7 @@ void launch_signal(const P2PState& q, cudaStream_t st) {
     SignalParams P{};
     P.n_peer = q.n_peer; P.my_rank = q.my_rank; P.epoch = q.epoch;
     for (int r = 0; r < q.n_peer; ++r) P.peer_flags[r] = q.peer_flags[r];
-    k_signal<<<1, 32, 0, st>>>(P);
+    launch_dep(k_signal, dim3(1), dim3(32), 0, st, P);
     CDL_CUDA(cudaGetLastError());
 }
 
@@ -1145,10 +1154,10 @@ void launch_table(const Donor& d, const SweepArgs& a, ChainDev& c, cudaStream_t 
     const int vpb = TABLE_THREADS / KP;
     const unsigned grid = (unsigned)((d.N + vpb - 1) / vpb);
     switch (KP) {
-        case 4: k_table<4><<<grid, TABLE_THREADS, 0, st>>>(P); break;
-        case 8: k_table<8><<<grid, TABLE_THREADS, 0, st>>>(P); break;
-        case 16: k_table<16><<<grid, TABLE_THREADS, 0, st>>>(P); break;
-        default: k_table<32><<<grid, TABLE_THREADS, 0, st>>>(P); break;
+        case 4: launch_dep(k_table<4>, dim3(grid), dim3(TABLE_THREADS), 0, st, P); break;
+        case 8: launch_dep(k_table<8>, dim3(grid), dim3(TABLE_THREADS), 0, st, P); break;
+        case 16: launch_dep(k_table<16>, dim3(grid), dim3(TABLE_THREADS), 0, st, P); break;
+        default: launch_dep(k_table<32>, dim3(grid), dim3(TABLE_THREADS), 0, st, P); break;
     }
     CDL_CUDA(cudaGetLastError());
 }

@@ -26,6 +26,23 @@ struct Error : std::runtime_error {
                                       __FILE__ + ":" + std::to_string(__LINE__) + ")");             \
     } while (0)
 
+// Launch of a sweep kernel with programmatic stream serialization (programmatic dependent launch): the CTAs of
+// kernel n+1 are placed on the SMs while kernel n drains and block in pdl_enter() (common.cuh) until kernel n has
+// completed and its writes are visible, which takes the launch latency and CTA start-up out of the gap between
+// the three kernels of a sweep.  Every kernel launched this way calls pdl_enter() before its first global access.
+// CDL_PDL=0 in the environment launches them the ordinary way.
+bool pdl_enabled();
+template <typename P>
+inline void launch_dep(void (*kern)(const P), dim3 grid, dim3 block, size_t smem, cudaStream_t st, const P& p) {
+    cudaLaunchConfig_t cfg{};
+    cfg.gridDim = grid; cfg.blockDim = block; cfg.dynamicSmemBytes = smem; cfg.stream = st;
+    cudaLaunchAttribute at[1];
+    at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    at[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = at; cfg.numAttrs = pdl_enabled() ? 1 : 0;
+    CDL_CUDA(cudaLaunchKernelEx(&cfg, kern, p));
+}
+
 // Device-resident donor: the same counts in two layouts.
 //  (A) cell-major, each cell's entries padded to a multiple of GROUP with (variant 0, a 0, b 0):
 //      c_rowgrp[M+1] group offsets; c_vidx (uint16 if N <= 65536 else uint32), c_a, c_b.
