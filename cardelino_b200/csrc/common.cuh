@@ -161,10 +161,9 @@ __device__ __forceinline__ unsigned long long warp_sum_u64(unsigned long long v)
 // First statement of every kernel launched with launch_dep() (internal.h): let the next kernel's CTAs be scheduled
 // as soon as there is room for them, then wait until the previous kernel has completed and flushed its writes.
 // Both are no-ops in a kernel launched the ordinary way.
-__device__ __forceinline__ void pdl_enter() {
-    asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
-    asm volatile("griddepcontrol.wait;" ::: "memory");
-}
+__device__ __forceinline__ void pdl_trigger() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+__device__ __forceinline__ void pdl_enter() { pdl_trigger(); pdl_wait(); }
 
 __device__ __forceinline__ double u16_to_double(uint32_t a) {
     return __hiloint2double(0x43300000, (int)a) - 4503599627370496.0;

@@ -280,8 +280,7 @@ __device__ __forceinline__ void stats_flush(uint32_t* __restrict__ bins, int lan
 // the kernel is bound by the latency of the shared-memory update chain as much as by HBM.
 template <int KP>
 __global__ void __launch_bounds__(STATS_THREADS, 2) k_stats_stream(const StatsParams P) {
-    pdl_enter();
-    if (P.run_flag && *P.run_flag == 0) return;      // the incremental update already produced this sweep's table
+    pdl_trigger();
     extern __shared__ __align__(16) unsigned char smem_raw[];
     uint32_t* s_bins = reinterpret_cast<uint32_t*>(smem_raw);                  // [WARPS][KP][32]
     uint8_t* s_z = smem_raw + sizeof(uint32_t) * STATS_WARPS * KP * 32;        // [cells of the staged block]
@@ -304,37 +303,26 @@ __global__ void __launch_bounds__(STATS_THREADS, 2) k_stats_stream(const StatsPa
     } else {
         cb = (int)blockIdx.x; cb_step = G; r = w; R = STATS_WARPS;
     }
+    // Everything up to pdl_wait() reads only the donor's layout (never written after the load), so under a
+    // programmatic dependent launch it runs while the cell kernel is still draining: the warp's range, the
+    // search for its first segment and the loads of its first 32 groups.
+    bool waited = false;
     for (; cb < P.n_cb; cb += cb_step) {
-        __syncthreads();                       // all warps are done with the previous block's labels
-        {
-            const int64_t c0 = (int64_t)cb * CELL_BLOCK;
-            const int ncell = (int)min((int64_t)CELL_BLOCK, P.M - c0);
-            const int nvec = ncell >> 4;
-            const uint4* src = reinterpret_cast<const uint4*>(P.z + c0);
-            uint4* dst = reinterpret_cast<uint4*>(s_z);
-            for (int t = threadIdx.x; t < nvec; t += blockDim.x) dst[t] = src[t];
-            for (int t = (nvec << 4) + threadIdx.x; t < ncell; t += blockDim.x) s_z[t] = P.z[c0 + t];
-        }
-        __syncthreads();
         const uint32_t* sg = P.seggrp + (int64_t)cb * P.N;       // sg[0..N]: group offsets of the block's segments
         const uint16_t* fl = P.flush + (int64_t)cb * P.N;
         const int64_t G0 = sg[0], G1 = sg[P.N];
-        const int64_t n_chunks = R * P.chunks_per_warp;
-        for (int64_t pass = 0;; ++pass) {
-        // a large block is cut into a few chunks per warp that are pulled from the block's counter (the warps of
-        // a slower SM take fewer); a small one into exactly one static range per warp (no atomics at all)
-        int64_t ck = r;
-        if (P.chunks_per_warp > 1) {
-            unsigned int u = 0;
-            if (lane == 0) u = atomicAdd(P.work + cb, 1u);
-            ck = (int64_t)__shfl_sync(0xffffffffu, u, 0);
-        } else if (pass > 0) break;
-        if (ck >= n_chunks) break;
-        const int64_t lo = G0 + ((G1 - G0) * ck) / n_chunks, hi = G0 + ((G1 - G0) * (ck + 1)) / n_chunks;
-        if (lo >= hi) continue;
-        // segment that holds group `lo`: largest i with sg[i] <= lo (32-ary search, the lanes probe in parallel)
-        int64_t i = 0;
-        {
+        // one static contiguous range of the block's groups per warp
+        const int64_t lo = G0 + ((G1 - G0) * r) / R, hi = G0 + ((G1 - G0) * (r + 1)) / R;
+        const bool has = lo < hi;
+        int64_t i = 0, win = 0, cur = lo, send = hi;
+        uint32_t wend = 0, wfl = 0;
+        int flush_every = 0;
+        uint4 cw = make_uint4(0, 0, 0, 0), aw = cw, bw = cw;
+        auto seg_end_of = [&](int64_t seg) -> int64_t {
+            return (int64_t)__shfl_sync(0xffffffffu, wend, (int)(seg - win));
+        };
+        if (has) {
+            // segment that holds group `lo`: largest i with sg[i] <= lo (32-ary search, the lanes probe in parallel)
             int64_t span = P.N;                 // answer in [i, i + span)
             while (span > 1) {
                 const int64_t stepw = (span + 31) / 32;
@@ -346,24 +334,37 @@ __global__ void __launch_bounds__(STATS_THREADS, 2) k_stats_stream(const StatsPa
                 span = min(stepw, i + span - ni);
                 i = ni;
             }
-        }
-        // boundary window: lane l holds sg[win + 1 + l] (end of segment win + l) and fl[win + l]
-        int64_t win = i;
-        uint32_t wend = sg[min(win + 1 + lane, P.N)];
-        uint32_t wfl = fl[min(win + lane, P.N - 1)];
-        auto seg_end_of = [&](int64_t seg) -> int64_t {
-            return (int64_t)__shfl_sync(0xffffffffu, wend, (int)(seg - win));
-        };
-        int64_t cur = lo;
-        int64_t send = min(seg_end_of(i), hi);
-        while (send <= cur) {                  // cannot happen for i found above, but keep the invariant explicit
-            ++i;
-            if (i - win >= 32) { win = i; wend = sg[min(win + 1 + lane, P.N)]; wfl = fl[min(win + lane, P.N - 1)]; }
+            // boundary window: lane l holds sg[win + 1 + l] (end of segment win + l) and fl[win + l]
+            win = i;
+            wend = sg[min(win + 1 + lane, P.N)];
+            wfl = fl[min(win + lane, P.N - 1)];
             send = min(seg_end_of(i), hi);
+            while (send <= cur) {              // cannot happen for i found above, but keep the invariant explicit
+                ++i;
+                if (i - win >= 32) { win = i; wend = sg[min(win + 1 + lane, P.N)]; wfl = fl[min(win + lane, P.N - 1)]; }
+                send = min(seg_end_of(i), hi);
+            }
+            flush_every = (int)__shfl_sync(0xffffffffu, wfl, (int)(i - win));
+            const int64_t gi = min(cur + lane, send - 1);
+            cw = ld_stream(c8 + gi); aw = ld_stream(a8 + gi); bw = ld_stream(b8 + gi);
         }
-        int flush_every = (int)__shfl_sync(0xffffffffu, wfl, (int)(i - win));
-        int64_t gi = min(cur + lane, send - 1);
-        uint4 cw = ld_stream(c8 + gi), aw = ld_stream(a8 + gi), bw = ld_stream(b8 + gi);
+        if (!waited) {
+            pdl_wait();
+            waited = true;
+            if (P.run_flag && *P.run_flag == 0) return;   // the incremental update already produced this sweep's table
+        }
+        __syncthreads();                       // all warps are done with the previous block's labels
+        {
+            const int64_t c0 = (int64_t)cb * CELL_BLOCK;
+            const int ncell = (int)min((int64_t)CELL_BLOCK, P.M - c0);
+            const int nvec = ncell >> 4;
+            const uint4* src = reinterpret_cast<const uint4*>(P.z + c0);
+            uint4* dst = reinterpret_cast<uint4*>(s_z);
+            for (int t = threadIdx.x; t < nvec; t += blockDim.x) dst[t] = src[t];
+            for (int t = (nvec << 4) + threadIdx.x; t < ncell; t += blockDim.x) s_z[t] = P.z[c0 + t];
+        }
+        __syncthreads();
+        if (!has) continue;
         int since = 0;
         while (cur < hi) {
             // where the NEXT iteration starts: the next 32 groups of this segment, or the start of the next
@@ -385,7 +386,7 @@ __global__ void __launch_bounds__(STATS_THREADS, 2) k_stats_stream(const StatsPa
             }
             uint4 cn = cw, an = aw, bn = bw;
             if (nbase < hi) {
-                gi = min(nbase + lane, nsend - 1);
+                const int64_t gi = min(nbase + lane, nsend - 1);
                 cn = ld_stream(c8 + gi); an = ld_stream(a8 + gi); bn = ld_stream(b8 + gi);
             }
             unsigned long long* sab_row = P.sab + i * P.K;
@@ -412,8 +413,8 @@ __global__ void __launch_bounds__(STATS_THREADS, 2) k_stats_stream(const StatsPa
             cw = cn; aw = an; bw = bn;
             cur = nbase; send = nsend; i = ni; flush_every = nfl;
         }
-        }   // chunks
     }
+    if (!waited) pdl_wait();
 }
 
 // The same statistics for LARGE shards (many segments per warp): the warps pull whole variant segments (or
