@@ -110,8 +110,40 @@ template <int KP, typename VIdx, bool SMEM, int SELL_THREADS, int SELL_DEPTH, bo
 __global__ void __launch_bounds__(SELL_THREADS, 1) k_cells_sell(const SellParams P) {
     constexpr bool PACKED = KP <= 16;
     extern __shared__ __align__(16) unsigned char smem_raw[];
-    pdl_enter();
+    pdl_trigger();
     const CellsParams& C = P.c;
+    const int lane = threadIdx.x & 31;
+    // Work items (slices, or 1/parts of one) are dealt dynamically, except each warp's FIRST one, which is its
+    // own index: its header and first group slots are donor layout only, so under a programmatic dependent
+    // launch they are fetched here, while the table kernel is still running.
+    const unsigned int n_static = gridDim.x * (blockDim.x >> 5);
+    unsigned int s_u = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    int64_t s = 0, g0 = 0, g1 = 0;
+    int part = 0;
+    uint32_t jl = 0xffffffffu;
+    Grp<VIdx> q[SELL_DEPTH];
+    // header of item s_u and its first SELL_DEPTH group slots (the look-ahead index is clamped to the slice's last
+    // slot so the loads need no predicate: a few redundant loads per slice); false when the items are used up
+    auto item_begin = [&]() -> bool {
+        const int parts = SPLIT ? P.parts : 1;
+        s = (int64_t)(s_u / (unsigned int)parts);
+        part = (int)(s_u - (unsigned int)s * (unsigned int)parts);
+        if (s >= P.n_slices) return false;
+        g0 = P.slice_off[s]; g1 = P.slice_off[s + 1];
+        if (SPLIT && parts > 1) {
+            const int64_t len = g1 - g0;
+            g1 = g0 + (len * (part + 1)) / parts;
+            g0 = g0 + (len * part) / parts;
+        }
+        jl = P.perm[s * 32 + lane];
+        if (g0 < g1) {
+#pragma unroll
+            for (int h = 0; h < SELL_DEPTH; ++h) q[h].load(C.vidx, P.a8, P.b8, min(g0 + h, g1 - 1) * 32 + lane);
+        }
+        return true;
+    };
+    bool have = item_begin();
+    pdl_wait();
     uint32_t tab_sa = 0, msk_sa = 0;
     const double2* tab_g = nullptr;
     const uint32_t* msk_g = C.mask;
@@ -137,34 +169,19 @@ __global__ void __launch_bounds__(SELL_THREADS, 1) k_cells_sell(const SellParams
     } else {
         tab_g = reinterpret_cast<const double2*>(C.l1);   // pre-built (packed when K <= 16) table in global memory
     }
-    const int lane = threadIdx.x & 31;
     const int K = C.K;
-    for (;;) {
-        unsigned int s_u = 0;
-        if (lane == 0) s_u = atomicAdd(P.work, 1u);
-        s_u = __shfl_sync(0xffffffffu, s_u, 0);
+    auto advance = [&]() {
+        unsigned int u = 0;
+        if (lane == 0) u = atomicAdd(P.work, 1u);
+        s_u = __shfl_sync(0xffffffffu, u, 0) + n_static;
+        have = item_begin();
+    };
+    for (; have; advance()) {
         const int parts = SPLIT ? P.parts : 1;
-        const int64_t s = (int64_t)(s_u / (unsigned int)parts);
-        const int part = (int)(s_u - (unsigned int)s * (unsigned int)parts);
-        if (s >= P.n_slices) break;
-        int64_t g0 = P.slice_off[s], g1 = P.slice_off[s + 1];
-        if (SPLIT && parts > 1) {
-            const int64_t len = g1 - g0;
-            g1 = g0 + (len * (part + 1)) / parts;
-            g0 = g0 + (len * part) / parts;
-        }
-        const uint32_t jl = P.perm[s * 32 + lane];
         const bool valid = jl != 0xffffffffu;
         double acc[KP];
 #pragma unroll
-        for (int q = 0; q < KP; ++q) acc[q] = 0.0;
-        // SELL_DEPTH group slots per lane are loaded ahead of the ones being accumulated; the look-ahead index
-        // is clamped to the slice's last slot so the loads need no predicate (a few redundant loads per slice)
-        Grp<VIdx> q[SELL_DEPTH];
-        if (g0 < g1) {
-#pragma unroll
-            for (int h = 0; h < SELL_DEPTH; ++h) q[h].load(C.vidx, P.a8, P.b8, min(g0 + h, g1 - 1) * 32 + lane);
-        }
+        for (int q_ = 0; q_ < KP; ++q_) acc[q_] = 0.0;
         for (int64_t g = g0; g < g1; g += SELL_DEPTH) {
             Grp<VIdx> n[SELL_DEPTH];
 #pragma unroll
