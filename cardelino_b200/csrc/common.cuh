@@ -157,7 +157,6 @@ __device__ __forceinline__ unsigned long long warp_sum_u64(unsigned long long v)
     for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
     return v;
 }
-// exact u16 -> double without the (slow) I2F.F64 path: 2^52 + a has `a` in the low mantissa bits
 // First statement of every kernel launched with launch_dep() (internal.h): let the next kernel's CTAs be scheduled
 // as soon as there is room for them, then wait until the previous kernel has completed and flushed its writes.
 // Both are no-ops in a kernel launched the ordinary way.
@@ -165,6 +164,7 @@ __device__ __forceinline__ void pdl_trigger() { asm volatile("griddepcontrol.lau
 __device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
 __device__ __forceinline__ void pdl_enter() { pdl_trigger(); pdl_wait(); }
 
+// exact u16 -> double without the (slow) I2F.F64 path: 2^52 + a has `a` in the low mantissa bits
 __device__ __forceinline__ double u16_to_double(uint32_t a) {
     return __hiloint2double(0x43300000, (int)a) - 4503599627370496.0;
 }

@@ -593,25 +593,30 @@ struct TableParams {
     unsigned int* p2p_error;                  // set to 1 if a peer's flag did not arrive in time
 };
 
-__device__ __forceinline__ unsigned long long block_sum_u64(unsigned long long v, unsigned long long* sm) {
-    v = warp_sum_u64(v);
-    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+// Block totals of k_table's six per-thread terms.  On return sm_u[q * 32] (q = 0..4) and sm_d[0] hold them; every
+// thread has passed one barrier after the warp partials were stored and one before they were overwritten.
+__device__ __forceinline__ void table_block_sums(unsigned long long a0, unsigned long long a1, unsigned long long a2,
+                                                 unsigned long long a3, unsigned long long a4, double d,
+                                                 unsigned long long* sm_u, double* sm_d) {
+    a0 = warp_sum_u64(a0); a1 = warp_sum_u64(a1); a2 = warp_sum_u64(a2); a3 = warp_sum_u64(a3); a4 = warp_sum_u64(a4);
+    d = warp_sum_d(d);
+    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5, nw = (int)(blockDim.x >> 5);
+    __syncthreads();                       // earlier readers of sm_u / sm_d are done
+    if (lane == 0) {
+        sm_u[w] = a0; sm_u[32 + w] = a1; sm_u[64 + w] = a2; sm_u[96 + w] = a3; sm_u[128 + w] = a4;
+        sm_d[w] = d;
+    }
     __syncthreads();
-    if (lane == 0) sm[w] = v;
-    __syncthreads();
-    unsigned long long r = 0;
-    for (int q = 0; q < (int)(blockDim.x >> 5); ++q) r += sm[q];
-    return r;
-}
-__device__ __forceinline__ double block_sum_d(double v, double* sm) {
-    v = warp_sum_d(v);
-    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
-    __syncthreads();
-    if (lane == 0) sm[w] = v;
-    __syncthreads();
-    double r = 0;
-    for (int q = 0; q < (int)(blockDim.x >> 5); ++q) r += sm[q];
-    return r;
+    if (threadIdx.x < 5) {
+        unsigned long long r = 0;
+        for (int q = 0; q < nw; ++q) r += sm_u[threadIdx.x * 32 + q];
+        sm_u[threadIdx.x * 32] = r;
+    } else if (threadIdx.x == 5) {
+        double r = 0.0;
+        for (int q = 0; q < nw; ++q) r += sm_d[q];          // warps in order, as everywhere: fixed rounding
+        sm_d[0] = r;
+    }
+    if (threadIdx.x < 32) __syncwarp();
 }
 
 // One thread per (variant, clone) element; the KP lanes of a variant sit in one warp.
@@ -628,8 +633,8 @@ __global__ void __launch_bounds__(TABLE_THREADS) k_table(const TableParams P) {
     constexpr int VPB = TABLE_THREADS / KP;          // variants per block
     constexpr int NJOB = 2 * VPB + 6;
     static_assert(NJOB <= TABLE_THREADS, "one Gamma job per thread");
-    __shared__ unsigned long long sm_u[TABLE_THREADS / 32];
-    __shared__ double sm_d[TABLE_THREADS / 32];
+    __shared__ unsigned long long sm_u[5 * 32];
+    __shared__ double sm_d[32];
     __shared__ unsigned long long s_s3[VPB], s_s4[VPB], s_tot[5];
     __shared__ double s_gam[NJOB];
     __shared__ bool is_last;
@@ -708,17 +713,20 @@ __global__ void __launch_bounds__(TABLE_THREADS) k_table(const TableParams P) {
         s_s3[v] = v3; s_s4[v] = v4;
         if (i < P.N) P.mask[i] = bitk;
     }
-    const unsigned long long b1 = block_sum_u64(S1, sm_u), b2 = block_sum_u64(S2, sm_u);
-    const unsigned long long b3 = block_sum_u64(S3, sm_u), b4 = block_sum_u64(S4, sm_u);
-    const unsigned long long bd = block_sum_u64(diff1, sm_u);
-    const double bl = block_sum_d(ll, sm_d);          // (the block sums synchronise: s_s3 / s_s4 are visible)
-    if (threadIdx.x == 0) {
-        unsigned long long* pu = P.part_u + (size_t)blockIdx.x * 8;
-        pu[0] = b1; pu[1] = b2; pu[2] = b3; pu[3] = b4; pu[4] = bd;
-        P.part_d[blockIdx.x] = bl;
+    // block totals of the five integer sums and the logLik term: warp butterflies, then thread q adds component
+    // q over the warps in order (one barrier; the double sum keeps a fixed order)
+    table_block_sums(S1, S2, S3, S4, diff1, ll, sm_u, sm_d);          // (the barrier makes s_s3 / s_s4 visible)
+    if (threadIdx.x < 6) {
+        if (threadIdx.x < 5) P.part_u[(size_t)blockIdx.x * 8 + threadIdx.x] = sm_u[threadIdx.x * 32];
+        else P.part_d[blockIdx.x] = sm_d[0];
         __threadfence();
-        const unsigned int tk = atomicAdd(P.ticket, 1u);
-        is_last = (tk == gridDim.x - 1);
+    }
+    if (threadIdx.x < 32) {
+        __syncwarp();
+        if (threadIdx.x == 0) {
+            const unsigned int tk = atomicAdd(P.ticket, 1u);
+            is_last = (tk == gridDim.x - 1);
+        }
     }
     __syncthreads();
     const bool last = is_last;                        // block-uniform
@@ -732,14 +740,12 @@ __global__ void __launch_bounds__(TABLE_THREADS) k_table(const TableParams P) {
             t1 += pu[0]; t2 += pu[1]; t3 += pu[2]; t4 += pu[3]; td += pu[4];
             tl += ((const volatile double*)P.part_d)[b];
         }
-        t1 = block_sum_u64(t1, sm_u); t2 = block_sum_u64(t2, sm_u); t3 = block_sum_u64(t3, sm_u);
-        t4 = block_sum_u64(t4, sm_u); td = block_sum_u64(td, sm_u);
-        tl = block_sum_d(tl, sm_d);
+        table_block_sums(t1, t2, t3, t4, td, tl, sm_u, sm_d);
+        if (threadIdx.x < 5) s_tot[threadIdx.x] = sm_u[threadIdx.x * 32];
+        if (threadIdx.x == 5) P.loglik_all[(int64_t)P.it - 1] = sm_d[0] + P.W_log;
         if (threadIdx.x == 0) {
             *P.ticket = 0;
             if (P.sell_work) *P.sell_work = 0u;
-            P.loglik_all[(int64_t)P.it - 1] = tl + P.W_log;
-            s_tot[0] = t1; s_tot[1] = t2; s_tot[2] = t3; s_tot[3] = t4; s_tot[4] = td;
         }
         __syncthreads();
     }
