@@ -571,6 +571,8 @@ struct TableParams {
                                     // element, once this sweep's value has been read (saves a memset per sweep);
                                     // nullptr with incremental statistics, which carry the table over
     unsigned int* sell_work;        // k_cells_sell's work counter, re-armed by the last block
+    unsigned int* stats_work;       // k_stats_units' per-cell-block unit counters [n_cb], re-armed likewise
+    int n_cb;
     const double* sd1;         // wise = element: SD[i,k] = sum_{j: z_j = k} A ln th1_ij + B ln(1 - th1_ij), else nullptr
     double* scal;
     double* l1;
@@ -669,7 +671,14 @@ __global__ void __launch_bounds__(TABLE_THREADS) k_table(const TableParams P) {
         const double du = l1 - l0, dv = l1c - l0c;
         const uint32_t c0 = P.cfg0[i];
         unsigned long long pk = P.sab[i * P.K + k];
-        for (int q = 0; q < P.n_peer; ++q) pk += ld_peer_u64(P.peer_sab[q] + i * P.K + k);
+        if (P.n_peer > 0) {
+            // all peers' loads in flight together: one NVLink round trip, not one per peer
+            unsigned long long pv[MAX_PEERS];
+#pragma unroll
+            for (int q = 0; q < MAX_PEERS; ++q) pv[q] = q < P.n_peer ? ld_peer_u64(P.peer_sab[q] + i * P.K + k) : 0ull;
+#pragma unroll
+            for (int q = 0; q < MAX_PEERS; ++q) pk += pv[q];
+        }
         if (P.sab_next) P.sab_next[i * P.K + k] = 0ull;
         const double SA = (double)(uint32_t)pk, SB = (double)(uint32_t)(pk >> 32);
         const double sd = element ? P.sd1[i * P.K + k] : 0.0;       // per-entry theta1: the theta1 part, summed
@@ -747,6 +756,8 @@ __global__ void __launch_bounds__(TABLE_THREADS) k_table(const TableParams P) {
             *P.ticket = 0;
             if (P.sell_work) *P.sell_work = 0u;
         }
+        if (P.stats_work)
+            for (int b = threadIdx.x; b < P.n_cb; b += blockDim.x) P.stats_work[b] = 0u;
         __syncthreads();
     }
     // ---- phase B: one Gamma job per thread ----
@@ -1104,7 +1115,7 @@ void launch_stats(const Donor& d, const SweepArgs& a, ChainDev& c, int sm_count,
         const int64_t avg_groups = std::max<int64_t>(1, d.v_groups / std::max<int64_t>(segs, 1));
         parts = std::min<int64_t>(parts, std::max<int64_t>(1, avg_groups / 64));
         P.chunks_per_warp = (int)std::max<int64_t>(1, std::min<int64_t>(parts, 64));
-        CDL_CUDA(cudaMemsetAsync(c.stats_work, 0, sizeof(unsigned int) * (size_t)d.n_cb, st));
+        // c.stats_work is zero on entry: k_table's last block re-arms it (and the chain starts with it zeroed)
     }
     const unsigned grid = (unsigned)ctas;
     switch (KP) {
@@ -1143,6 +1154,7 @@ void launch_table(const Donor& d, const SweepArgs& a, ChainDev& c, cudaStream_t 
     P.rp_relax_next = a.rp_relax_next;
     P.part_d = c.part_d; P.part_u = c.part_u; P.ticket = c.ticket;
     P.sell_work = c.work;
+    P.stats_work = c.stats_work; P.n_cb = (int)d.n_cb;
     P.sab_next = (a.incremental || a.wise == 2) ? nullptr : c.sab;
     P.n_peer = 0;
     if (a.p2p && a.p2p->n_peer > 0) {
