@@ -117,7 +117,9 @@ __global__ void __launch_bounds__(SELL_THREADS, 1) k_cells_sell(const SellParams
     // own index: its header and first group slots are donor layout only, so under a programmatic dependent
     // launch they are fetched here, while the table kernel is still running.
     const unsigned int n_static = gridDim.x * (blockDim.x >> 5);
-    unsigned int s_u = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    // (strided by the grid, not blocked by CTA: slices are sorted by length inside 4096-cell windows, and on a shard
+    // that is done in one round a CTA holding 28 neighbours would be all-long or all-short)
+    unsigned int s_u = (threadIdx.x >> 5) * gridDim.x + blockIdx.x;
     int64_t s = 0, g0 = 0, g1 = 0;
     int part = 0;
     uint32_t jl = 0xffffffffu;
