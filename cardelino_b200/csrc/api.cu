@@ -8,6 +8,7 @@
 #include <cmath>
 #include <cstdio>
 #include <cstring>
+#include <map>
 #include <memory>
 #include <vector>
 
@@ -70,6 +71,7 @@ struct Chain {
     ChainDev dev{};
     DevBuf<double> scal, l1, l1c, theta0_all, theta1_all, loglik_all, relax_all, prob_all, prob_acc, part_d;
     DevBuf<double> el_l1, el_l1c, sd1;
+    DevBuf<double> prob_sq;              // running sum of squares beside prob_acc (streaming Geweke windows)
     DevBuf<uint32_t> mask;
     DevBuf<uint8_t> z, config_all, assign_all;
     DevBuf<unsigned long long> sab, part_u;
@@ -763,6 +765,44 @@ int cdl_gibbs_run(cdl_handle h, const double* Config, int32_t K, const double* P
         const int64_t n_buin_planned = (int64_t)std::ceil((double)T * gp.buin_frac);
         DevBuf<unsigned long long> gcounts(2);
 
+        // Streaming mode with the reference's stop rule.  Without prob_all the Geweke test (:580-601) and the
+        // burn-in that depends on the final iteration (:604-606,645) are evaluated from RUNNING column sums of
+        // prob and prob^2 (kept by the cell kernel from row 2 on) and snapshots of them at the rows where a
+        // window of some later check begins: floor(.1 n), ceil(.5 n) - 1 and ceil(buin_frac n) - 1 for every
+        // check row n.  That is 2-3 snapshots per check instead of n rows; used when a stop before max_iter is
+        // possible, the snapshots that are alive together fit the trace budget, and the run takes the plain
+        // one-chain-at-a-time branch (wise = global / variant).
+        struct Snap { DevBuf<double> s1, s2; int64_t last_use = 0; bool need_s2 = false; };
+        std::map<int64_t, Snap> snaps;          // by row count r (rows 1..r summed); r <= 1 needs no buffer
+        std::vector<int64_t> win_checks;
+        auto rowsA = [](int64_t n) { return (int64_t)std::floor(0.1 * (double)n); };
+        auto rowsB = [](int64_t n) { return (int64_t)std::ceil(0.5 * (double)n) - 1; };
+        auto rowsU = [&](int64_t n) { return (int64_t)std::ceil((double)n * gp.buin_frac) - 1; };
+        bool win = !exact && !element && gp.min_iter < T;
+        if (win) {
+            for (int64_t n = ((gp.min_iter + check_every - 1) / check_every) * check_every; n <= T; n += check_every)
+                win_checks.push_back(n);
+            if (win_checks.empty() || win_checks.back() != T) win_checks.push_back(T);
+            for (int64_t n : win_checks) {
+                const int64_t r3[3] = {rowsA(n), rowsB(n), rowsU(n)};
+                for (int q = 0; q < 3; ++q) {
+                    if (r3[q] <= 1) continue;
+                    Snap& sn = snaps[r3[q]];
+                    sn.last_use = std::max(sn.last_use, n);
+                    if (q < 2) sn.need_s2 = true;
+                }
+            }
+            // most buffers alive at once: snapshot r lives from row r to its last check
+            double peak = 0.0;
+            for (const auto& kv : snaps) {
+                double live = 0.0;
+                for (const auto& kw : snaps)
+                    if (kw.first <= kv.first && kw.second.last_use >= kv.first) live += kw.second.need_s2 ? 2.0 : 1.0;
+                peak = std::max(peak, live);
+            }
+            if ((peak + 2.0) * (double)M * (double)K * 8.0 > (double)gp.trace_budget_bytes) { win = false; snaps.clear(); }
+        }
+
         // ---- a chain's life in three steps, each on whatever stream h->st currently is ----
         auto start_chain = [&](int c, SweepArgs& a) -> std::unique_ptr<Chain> {
             std::unique_ptr<Chain> chp(new Chain());
@@ -789,6 +829,7 @@ int cdl_gibbs_run(cdl_handle h, const double* Config, int32_t K, const double* P
             ch.config_all.alloc((size_t)(T * N * K)); ch.config_all.zero(h->st);
             if (exact) { ch.prob_all.alloc((size_t)(T * M * K)); ch.prob_all.zero(h->st); }
             else { ch.prob_acc.alloc((size_t)(M * K)); ch.prob_acc.zero(h->st); }
+            if (win) { ch.prob_sq.alloc((size_t)(M * K)); ch.prob_sq.zero(h->st); }
             if (gp.keep_assign_all) { ch.assign_all.alloc((size_t)(T * M)); ch.assign_all.zero(h->st); }
             const size_t tgrid = (size_t)((N + 7) / 8) + 1;     // k_table blocks: 256 / KP variants each, KP <= 32
             ch.part_d.alloc(tgrid * 4); ch.part_u.alloc(tgrid * 8);
@@ -803,7 +844,7 @@ int cdl_gibbs_run(cdl_handle h, const double* Config, int32_t K, const double* P
             ch.dev.config_all = ch.config_all.p;
             ch.dev.prob_all = exact ? ch.prob_all.p : nullptr;
             ch.dev.assign_all = gp.keep_assign_all ? ch.assign_all.p : nullptr;
-            ch.dev.prob_acc = nullptr;
+            ch.dev.prob_acc = nullptr; ch.dev.prob_sq = nullptr;
             ch.dev.part_d = ch.part_d.p; ch.dev.part_u = ch.part_u.p; ch.dev.ticket = ch.ticket.p;
             ch.dev.tab_g = ch.tab_g.p;
             ch.dev.el_l1 = ch.el_l1.p; ch.dev.el_l1c = ch.el_l1c.p; ch.dev.sd1 = ch.sd1.p;
@@ -839,9 +880,11 @@ int cdl_gibbs_run(cdl_handle h, const double* Config, int32_t K, const double* P
             if (element) launch_el_init(h->donor, a, ch.dev, h->st);
             return chp;
         };
+        const double* win_burn_s1 = nullptr;    // windows mode: snapshot at row ceil(it * buin_frac) - 1 of the final it
         auto finish_chain = [&](Chain& ch, SweepArgs& a, int64_t it_final, double frac) {
             const int64_t itf = it_final;
             if (exact) frac = geweke_fraction(h, ch, itf, gcounts);
+            else if (win) { /* frac is the windowed test at itf, from the run loop */ }
             else {
                 // streaming mode keeps no prob_all, so the reference's rule (Geweke Z of every prob_all column,
                 // R/clone_id.R:594-601) cannot be evaluated; the same Z test on the theta1 traces -- the model
@@ -854,7 +897,7 @@ int cdl_gibbs_run(cdl_handle h, const double* Config, int32_t K, const double* P
             }
             ch.info.n_iter = (int32_t)itf;
             ch.info.percent_converged = r_round3_percent(frac);
-            const int64_t n_buin = exact ? (int64_t)std::ceil((double)itf * gp.buin_frac) : n_buin_planned;
+            const int64_t n_buin = (exact || win) ? (int64_t)std::ceil((double)itf * gp.buin_frac) : n_buin_planned;
             ch.info.n_buin = (int32_t)n_buin;
             ch.info.n_element = (int32_t)n_el;
             ch.info.exact_trace = exact ? 1 : 0;
@@ -863,6 +906,7 @@ int cdl_gibbs_run(cdl_handle h, const double* Config, int32_t K, const double* P
             // posterior means (:645-653)
             ch.prob_mean.alloc((size_t)(M * K));
             if (exact) launch_col_means_d(ch.prob_all.p, M * K, r0, r1, ch.prob_mean.p, h->st);
+            else if (win) launch_window_mean(ch.prob_acc.p, win_burn_s1, M * K, 1.0 / (double)(r1 - r0), ch.prob_mean.p, h->st);
             else {
                 // accumulator holds the sum over rows [n_buin_planned, T]
                 CDL_CUDA(cudaMemcpyAsync(ch.prob_mean.p, ch.prob_acc.p, sizeof(double) * (size_t)(M * K),
@@ -897,13 +941,15 @@ int cdl_gibbs_run(cdl_handle h, const double* Config, int32_t K, const double* P
         // runs keep one chain at a time on the library's stream.
         const double per_chain_bytes = (exact ? trace_bytes : 0.0) + (double)T * (double)(N * K) +
                                        (double)T * (double)n_el * 8.0;
-        const bool concurrent = gp.n_chain > 1 && h->world == 1 && !rp &&
-                                per_chain_bytes * gp.n_chain <= (double)gp.trace_budget_bytes;
+        const bool concurrent_ok = gp.n_chain > 1 && h->world == 1 && !rp &&
+                                   per_chain_bytes * gp.n_chain <= (double)gp.trace_budget_bytes;
         // small donors: every chain is one CTA of one grid, check_every sweeps per launch (small.cu)
         const bool small = (h->cells_layout == CDL_CELLS_SMALL ||
                             (h->cells_layout == CDL_CELLS_AUTO && d.M_total < 16384)) &&
                            h->world == 1 && !rp && !element && !a.incremental && small_path_fits(d, K, gp.wise) &&
                            per_chain_bytes * gp.n_chain <= (double)gp.trace_budget_bytes;
+        if (small) { win = false; snaps.clear(); }
+        const bool concurrent = concurrent_ok && !win;     // the windowed stop rule runs one chain at a time
         if (h->cells_layout == CDL_CELLS_SMALL && !small)
             throw Error(CDL_ERR_UNSUPPORTED, "the small-donor path does not apply (size, replay, sharding, element or incremental mode)");
         if (small) {
@@ -959,13 +1005,52 @@ int cdl_gibbs_run(cdl_handle h, const double* Config, int32_t K, const double* P
                 Chain& ch = *chp;
                 int64_t it_final = T;
                 double frac = NAN;
+                if (win && c > 0)       // every chain walks the same snapshot schedule
+                    for (auto& kv : snaps) { kv.second.s1.release(); kv.second.s2.release(); }
+                size_t next_check = 0;
+                win_burn_s1 = nullptr;
                 for (int64_t it = 2; it <= T; ++it) {
-                    ch.dev.prob_acc = (!exact && it >= n_buin_planned) ? ch.prob_acc.p : nullptr;
+                    if (win) { ch.dev.prob_acc = ch.prob_acc.p; ch.dev.prob_sq = ch.prob_sq.p; }
+                    else ch.dev.prob_acc = (!exact && it >= n_buin_planned) ? ch.prob_acc.p : nullptr;
                     one_sweep(h, ch, a, (uint32_t)it, rp, n_el);
                     if (exact && it >= gp.min_iter && it % check_every == 0) {
                         frac = geweke_fraction(h, ch, it, gcounts);
                         if (gp.verbose) std::printf("%g%% converged.\n", r_round3_percent(frac));
                         if (frac > 0.995) { it_final = it; break; }
+                    }
+                    if (!win) continue;
+                    auto sn = snaps.find(it);
+                    if (sn != snaps.end()) {           // the sums over rows 1..it, kept for a later window
+                        const size_t nb = sizeof(double) * (size_t)(M * K);
+                        sn->second.s1.alloc((size_t)(M * K));
+                        CDL_CUDA(cudaMemcpyAsync(sn->second.s1.p, ch.prob_acc.p, nb, cudaMemcpyDeviceToDevice, h->st));
+                        if (sn->second.need_s2) {
+                            sn->second.s2.alloc((size_t)(M * K));
+                            CDL_CUDA(cudaMemcpyAsync(sn->second.s2.p, ch.prob_sq.p, nb, cudaMemcpyDeviceToDevice, h->st));
+                        }
+                    }
+                    if (next_check < win_checks.size() && it == win_checks[next_check]) {
+                        ++next_check;
+                        auto buf = [&](int64_t r, bool sq) -> const double* {
+                            if (r <= 1) return nullptr;
+                            const Snap& q = snaps.at(r);
+                            return sq ? q.s2.p : q.s1.p;
+                        };
+                        launch_geweke_sums(buf(rowsA(it), false), buf(rowsA(it), true), buf(rowsB(it), false),
+                                           buf(rowsB(it), true), ch.prob_acc.p, ch.prob_sq.p, M * K, it, gcounts.p, h->st);
+                        if (h->world > 1) allreduce_u64(h, gcounts.p, 2);
+                        unsigned long long cnt[2];
+                        gcounts.download(cnt, 2, h->st);
+                        frac = cnt[0] ? (double)cnt[1] / (double)cnt[0] : NAN;
+                        const bool rule = it >= gp.min_iter && it % check_every == 0;     // (:580); else the final row
+                        if (rule && gp.verbose) std::printf("%g%% converged.\n", r_round3_percent(frac));
+                        if ((rule && frac > 0.995) || it == T) {
+                            it_final = it;
+                            win_burn_s1 = buf(rowsU(it), false);
+                            break;
+                        }
+                        for (auto& kv : snaps)         // snapshots no later check needs
+                            if (kv.second.last_use <= it) { kv.second.s1.release(); kv.second.s2.release(); }
                     }
                 }
                 finish_chain(ch, a, it_final, frac);
@@ -1261,7 +1346,7 @@ int cdl_bench_sweeps(cdl_handle h, int32_t warmup, int32_t n, float* ms_total, f
         SweepArgs a = h->sweep;
         a.chain = 0;
         const uint32_t it = (uint32_t)h->T;     // keep overwriting the last trace row
-        ch.dev.prob_acc = nullptr;
+        ch.dev.prob_acc = nullptr; ch.dev.prob_sq = nullptr;
         cudaEvent_t e0, e1;
         CDL_CUDA(cudaEventCreate(&e0));
         CDL_CUDA(cudaEventCreate(&e1));

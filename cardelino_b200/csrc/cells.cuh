@@ -28,6 +28,7 @@ struct CellsParams {
     double logPsi[KMAX];
     double* prob_row;          // [M*K] trace row to fill (device layout [cell][clone]) or nullptr
     double* prob_acc;          // [M*K] accumulator or nullptr
+    double* prob_sq;           // [M*K] accumulator of squares (streaming Geweke windows) or nullptr
     uint8_t* z;
     uint8_t* assign_row;       // [M] 1-based labels or nullptr
     const double* rp_u;        // replay uniforms for this iteration or nullptr

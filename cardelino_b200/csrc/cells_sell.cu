@@ -243,6 +243,11 @@ __global__ void __launch_bounds__(SELL_THREADS, 1) k_cells_sell(const SellParams
 #pragma unroll
                 for (int k = 0; k < KP; ++k) if (k < K) o[k] += acc[k];
             }
+            if (C.prob_sq) {
+                double* o = C.prob_sq + (int64_t)jl * K;
+#pragma unroll
+                for (int k = 0; k < KP; ++k) if (k < K) o[k] += acc[k] * acc[k];
+            }
         }
         // ---- sample(seq_len(K), 1, prob = pr): walk the DESCENDING-sorted CDF with one uniform (:493) ----
         double u = 0.5;
@@ -513,6 +518,7 @@ void launch_cells_sell(const Donor& d, const SweepArgs& a, ChainDev& c, int sm_c
     const int64_t row = (int64_t)a.it - 1;
     C.prob_row = c.prob_all ? c.prob_all + row * d.M * a.K : nullptr;
     C.prob_acc = c.prob_acc;
+    C.prob_sq = c.prob_sq;
     C.z = c.z;
     C.assign_row = c.assign_all ? c.assign_all + row * d.M : nullptr;
     C.rp_u = a.rp_u_assign;

@@ -137,6 +137,7 @@ __global__ void __launch_bounds__(CELLS_THREADS, (KP <= 8 ? 2 : 1)) k_cells(cons
         if (valid && rep && k < K) {
             if (P.prob_row) P.prob_row[j * K + k] = pr;
             if (P.prob_acc) P.prob_acc[j * K + k] += pr;
+            if (P.prob_sq) P.prob_sq[j * K + k] += pr * pr;
         }
         // ---- sample(seq_len(K), 1, prob = pr): walk the DESCENDING-sorted CDF with one uniform ----
         const uint32_t gcell = (uint32_t)(P.cell_offset + j);
@@ -978,6 +979,7 @@ void launch_cells(const Donor& d, const SweepArgs& a, ChainDev& c, int sm_count,
     const int64_t row = (int64_t)a.it - 1;
     P.prob_row = c.prob_all ? c.prob_all + row * d.M * a.K : nullptr;
     P.prob_acc = c.prob_acc;
+    P.prob_sq = c.prob_sq;
     P.z = c.z;
     P.assign_row = c.assign_all ? c.assign_all + row * d.M : nullptr;
     P.rp_u = a.rp_u_assign;

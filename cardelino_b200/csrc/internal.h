@@ -113,6 +113,7 @@ struct ChainDev {
     double* prob_all;    // [T * M*K] device layout [t][cell][clone]  (exact mode) or nullptr
     uint8_t* assign_all; // [T * M] 1-based labels or nullptr
     double* prob_acc;    // [M*K] streaming accumulator (compact mode) or nullptr
+    double* prob_sq;     // [M*K] running sum of squares beside it (streaming Geweke windows) or nullptr
     // reduction scratch
     double* part_d;      // [grid * 4]
     unsigned long long* part_u; // [grid * 8]
@@ -206,6 +207,9 @@ void launch_el_theta(const Donor& d, const SweepArgs& a, ChainDev& c, cudaStream
 // post-processing
 void launch_geweke(const double* prob_all, int64_t cols, int64_t n_rows, unsigned long long* counts2,
                    cudaStream_t st);  // counts2[0] = #non-NaN, counts2[1] = #|Z|<=2
+void launch_geweke_sums(const double* s1a, const double* s2a, const double* s1b, const double* s2b, const double* s1n,
+                        const double* s2n, int64_t cols, int64_t n_rows, unsigned long long* counts2, cudaStream_t st);
+void launch_window_mean(const double* s1n, const double* s1u, int64_t n, double inv, double* out, cudaStream_t st);
 void launch_col_means_d(const double* X, int64_t cols, int64_t r0, int64_t r1, double* out, cudaStream_t st);
 void launch_transpose_scale(const double* in, int64_t R, int64_t C, double scale, double* out, cudaStream_t st);
 void launch_scale(double* x, int64_t n, double s, cudaStream_t st);

@@ -255,6 +255,43 @@ __global__ void k_transpose_scale(const double* __restrict__ in, int64_t R, int6
     }
 }
 
+// The same Z test (R/clone_id.R:688-715) from RUNNING column sums instead of the stored trace: s1 / s2 are the
+// sums of x and x^2 over rows 1..r, snapshotted at r = a = floor(.1 n) (window A), r = b = ceil(.5 n) - 1 (the
+// rows before window B) and current at r = n.  A null snapshot stands for r <= 1 (row 1 of prob_all is all zero).
+// One-pass variances (clamped at 0) differ from the two-pass ones of k_geweke by rounding only, relative to the
+// column's mean square.
+__global__ void k_geweke_sums(const double* __restrict__ s1a, const double* __restrict__ s2a,
+                              const double* __restrict__ s1b, const double* __restrict__ s2b,
+                              const double* __restrict__ s1n, const double* __restrict__ s2n, int64_t cols, int64_t n,
+                              unsigned long long* counts) {
+    const int64_t c = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+    unsigned ok = 0, conv = 0;
+    if (c < cols) {
+        const double nA = floor(0.1 * (double)n);
+        const double nB = (double)n - (ceil(0.5 * (double)n) - 1.0);
+        const double a1 = s1a ? s1a[c] : 0.0, a2 = s2a ? s2a[c] : 0.0;
+        const double b1 = s1n[c] - (s1b ? s1b[c] : 0.0), b2 = s2n[c] - (s2b ? s2b[c] : 0.0);
+        const double mA = a1 / nA, mB = b1 / nB;
+        const double vA = fmax(a2 - nA * mA * mA, 0.0) / (nA - 1.0);
+        const double vB = fmax(b2 - nB * mB * mB, 0.0) / (nA - 1.0);     // nrow(A) - 1, as the reference has it
+        const double Z = (mA - mB) / sqrt(vA + vB + 1e-50);
+        if (!isnan(Z)) { ok = 1; conv = fabs(Z) <= 2.0; }
+    }
+    const unsigned okw = __popc(__ballot_sync(0xffffffffu, ok));
+    const unsigned cvw = __popc(__ballot_sync(0xffffffffu, conv));
+    if ((threadIdx.x & 31) == 0) {
+        if (okw) atomicAdd(&counts[0], (unsigned long long)okw);
+        if (cvw) atomicAdd(&counts[1], (unsigned long long)cvw);
+    }
+}
+
+// out = (s1n - s1u) * inv: column means over the rows after snapshot u
+__global__ void k_window_mean(const double* __restrict__ s1n, const double* __restrict__ s1u, int64_t n, double inv,
+                              double* __restrict__ out) {
+    const int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+    if (i < n) out[i] = (s1n[i] - (s1u ? s1u[i] : 0.0)) * inv;
+}
+
 __global__ void k_scale(double* __restrict__ x, int64_t n, double s) {
     const int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
     if (i < n) x[i] *= s;
@@ -286,6 +323,19 @@ void launch_geweke(const double* prob_all, int64_t cols, int64_t n_rows, unsigne
                    cudaStream_t st) {
     CDL_CUDA(cudaMemsetAsync(counts2, 0, 2 * sizeof(unsigned long long), st));
     k_geweke<<<(unsigned)((cols + 255) / 256), 256, 0, st>>>(prob_all, cols, n_rows, counts2);
+    CDL_CUDA(cudaGetLastError());
+}
+
+void launch_geweke_sums(const double* s1a, const double* s2a, const double* s1b, const double* s2b, const double* s1n,
+                        const double* s2n, int64_t cols, int64_t n_rows, unsigned long long* counts2, cudaStream_t st) {
+    CDL_CUDA(cudaMemsetAsync(counts2, 0, 2 * sizeof(unsigned long long), st));
+    k_geweke_sums<<<(unsigned)((cols + 255) / 256), 256, 0, st>>>(s1a, s2a, s1b, s2b, s1n, s2n, cols, n_rows, counts2);
+    CDL_CUDA(cudaGetLastError());
+}
+
+void launch_window_mean(const double* s1n, const double* s1u, int64_t n, double inv, double* out, cudaStream_t st) {
+    if (n <= 0) return;
+    k_window_mean<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(s1n, s1u, n, inv, out);
     CDL_CUDA(cudaGetLastError());
 }
 

@@ -434,6 +434,32 @@ def test_converged_posterior_matches_oracle_chains(gpu_handle, c2_donor, example
     assert abs(g["theta0"] - np.mean([o["theta0"] for o in os_])) < 2e-3
 
 
+@pytest.mark.parametrize("layout,buin_frac", [("rows", 0.5), ("slices", 0.3)])
+def test_streaming_stop_rule_matches_exact(gpu_handle, c2_donor, layout, buin_frac):
+    """Streaming mode (no prob_all) applies the reference's Geweke stop rule and its burn-in, which depends on
+    the final iteration (R/clone_id.R:580-606,645), from running column sums and window snapshots: same stop
+    iteration, burn-in and posterior means as the exact mode that keeps the whole trace."""
+    cb = _cb()
+    A, D, Z, _ = c2_donor
+    gpu_handle.set_cells_layout(layout)
+    try:
+        out = {}
+        for keep in (1, 0):
+            out[keep] = cb.clone_id_Gibbs(A, D, Z, min_iter=300, max_iter=2500, seed=11, buin_frac=buin_frac,
+                                          handle=gpu_handle, verbose=False, keep_prob_all=keep)
+    finally:
+        gpu_handle.set_cells_layout("auto")
+    ex, st = out[1], out[0]
+    assert ex["exact_trace"] and not st["exact_trace"]
+    assert st["n_iter"] == ex["n_iter"] and st["n_buin"] == ex["n_buin"]
+    assert ex["n_iter"] < 2500, "pick parameters with which the exact run stops early"
+    assert abs(st["percent_converged"] - ex["percent_converged"]) <= 0.2
+    assert np.abs(st["prob"] - ex["prob"]).max() < 1e-9          # difference of running sums vs mean of the rows
+    assert np.array_equal(st["Config_prob"], ex["Config_prob"])
+    assert st["theta0"] == ex["theta0"] and st["relax_rate"] == ex["relax_rate"]
+    assert np.isclose(st["logLik_post"], ex["logLik_post"], rtol=1e-9)
+
+
 def test_device_beta_sampler_distribution(gpu_handle):
     """The on-device Beta draws (Marsaglia-Tsang gammas on Philox streams) replace R's rbeta (Cheng BB/BC):
     same distribution, different stream.  Kolmogorov-Smirnov against scipy for small, moderate and large
