@@ -57,9 +57,11 @@ typedef struct cdl_gibbs_params {
     int32_t n_chain;             /* chains run inside the library (replaces doMC fork, :127-163) */
     uint64_t seed;               /* Philox key; chain c uses (seed, c) */
     int32_t keep_assign_all;     /* also record assign_all (R allocates it at :429 but does not return it) */
-    int32_t keep_prob_all;       /* 1: exact mode, keep prob_all on device (needed for the reference's
-                                    Geweke rule and relabel); 0: streaming accumulators only;
-                                    -1: decide from trace_budget_bytes */
+    int32_t keep_prob_all;       /* 1: exact mode, keep prob_all on device (needed for relabel and for fetching
+                                    the trace); 0: streaming mode: running column sums of prob and prob^2 plus
+                                    snapshots at the rows where a Geweke window or the burn-in of a later check
+                                    starts, which give the reference's stop rule (:580-601) and final-iteration
+                                    burn-in (:604,645) without the trace; -1: decide from trace_budget_bytes */
     int64_t trace_budget_bytes;  /* upper bound for on-device traces when keep_prob_all == -1 */
     int32_t check_every;         /* convergence check period, reference value 100 (:580) */
     int32_t verbose;
@@ -90,7 +92,9 @@ typedef struct cdl_gibbs_info {
     int32_t n_buin;              /* ceiling(it * buin_frac) (:604) */
     int32_t n_element;           /* 1, N or nnz (:406-416) */
     int32_t exact_trace;         /* 1 if prob_all was kept */
-    double  percent_converged;   /* (:595); streaming mode (no prob_all): the same Geweke test on the theta1 traces */
+    double  percent_converged;   /* (:595); streaming mode: the same test from running sums when a stop before
+                                    max_iter is possible (min_iter < max_iter, snapshots within the trace budget),
+                                    else the Geweke test on the theta1 traces */
     double  logLik_post;         /* (:656) */
     double  W_log;               /* (:388) */
     double  dic[6];              /* DIC, logLik_var, D_mean, D_post, DIC_Gelman, DIC_Spiegelhalter (:790-797) */
