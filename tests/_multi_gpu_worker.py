@@ -59,6 +59,30 @@ def main():
                 ok = False
                 msg.append("%s/logLik differs" % mode)
         print(json.dumps({"ok": ok, "world": world, "messages": msg}))
+    # ---- the stop rule on a sharded chain: the Geweke counts are summed over the ranks, so every rank stops at the
+    # iteration the unsharded chain stops at -- with the whole trace (exact mode) and from the running sums and
+    # window snapshots of streaming mode ----
+    stop = {}
+    for keep in (1, 0):
+        h.gibbs_run(cfg, None, min_iter=100, max_iter=600, seed=8, keep_prob_all=keep)
+        info = h.gibbs_info(0)
+        stop[keep] = (int(info.n_iter), int(info.n_buin), float(info.percent_converged), h.fetch("prob"))
+    if rank == 0:
+        for keep in (1, 0):
+            full.gibbs_run(cfg, None, min_iter=100, max_iter=600, seed=8, keep_prob_all=keep)
+            fi = full.gibbs_info(0)
+            n_it, n_bu, pc, prob = stop[keep]
+            if (n_it, n_bu) != (int(fi.n_iter), int(fi.n_buin)) or abs(pc - float(fi.percent_converged)) > 0.2:
+                ok = False
+                msg.append("stop rule (keep_prob_all=%d): sharded %s vs unsharded %s" %
+                           (keep, (n_it, n_bu, pc), (int(fi.n_iter), int(fi.n_buin), float(fi.percent_converged))))
+            elif not np.allclose(prob, full.fetch("prob")[lo:hi], rtol=0, atol=1e-9):
+                ok = False
+                msg.append("posterior means differ (keep_prob_all=%d)" % keep)
+        if stop[1][:2] != stop[0][:2]:
+            ok = False
+            msg.append("streaming and exact mode stop at different iterations: %s vs %s" % (stop[0][:2], stop[1][:2]))
+        print(json.dumps({"ok": ok, "world": world, "messages": msg, "stop": [stop[1][:3], stop[0][:3]]}))
     # ---- independent chains, one group per GPU (BASELINE config 5): the merged result equals the one of the same
     # chains (same Philox chain numbers) run in a single process ----
     d = np.load(os.path.join(ROOT, "tests", "golden", "example_donor.npz"))
