@@ -194,6 +194,27 @@ def geweke_z(X, first=0.1, last=0.5):
         return (mA - mB) / np.sqrt(vA + vB + 1e-50)
 
 
+def geweke_z_running_sums(X, first=0.1, last=0.5):
+    """The same Z from RUNNING column sums of x and x^2, as the streaming mode of the CUDA path evaluates it
+    (csrc/post.cu::k_geweke_sums): prefix sums over rows 1..r snapshotted at r = floor(first n) and
+    r = ceil(last n) - 1, and current at r = n.  One-pass variances clamped at 0."""
+    X = np.asarray(X, dtype=np.float64)
+    n = X.shape[0]
+    s1, s2 = np.cumsum(X, axis=0), np.cumsum(X * X, axis=0)
+    zero = np.zeros(X.shape[1])
+    at = lambda S, r: S[r - 1] if r >= 1 else zero
+    nA = math.floor(first * n)
+    rb = math.ceil(last * n) - 1
+    nB = n - rb
+    with np.errstate(invalid="ignore", divide="ignore"):
+        mA = at(s1, nA) / nA
+        b1, b2 = s1[-1] - at(s1, rb), s2[-1] - at(s2, rb)
+        mB = b1 / nB
+        vA = np.maximum(at(s2, nA) - nA * mA * mA, 0.0) / (nA - 1)
+        vB = np.maximum(b2 - nB * mB * mB, 0.0) / (nA - 1)
+        return (mA - mB) / np.sqrt(vA + vB + 1e-50)
+
+
 def r_round(x, digits=0):
     """R's round() to `digits` decimals (half-even on the decimal representation is not needed at the
     3-digit precision the sampler prints)."""

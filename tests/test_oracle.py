@@ -110,6 +110,22 @@ def test_geweke_matches_definition():
     assert np.all(np.isnan(O.geweke_z(X[:5])))            # first window empty -> NaN like R
 
 
+def test_geweke_from_running_sums_is_the_same_test():
+    """Streaming mode evaluates the stop rule from running sums and window snapshots: the
+    Z values agree with the definition to rounding, hence the same |Z| <= 2 decisions, on probability-like
+    traces including saturated (constant 1 / 0) and tiny-valued columns, first row zero as in prob_all."""
+    rng = np.random.default_rng(11)
+    n = 700
+    X = np.column_stack([rng.random(n), 0.9 + 0.1 * rng.random(n), np.ones(n), np.zeros(n),
+                         1e-30 * 10.0 ** (-8 * rng.random(n)), rng.beta(0.3, 0.3, n),
+                         np.r_[rng.random(n // 2), 0.2 * rng.random(n - n // 2)]])       # last column: a chain that drifts
+    X[0] = 0.0
+    for rows in (n, 500, 300):
+        Z, Zs = O.geweke_z(X[:rows]), O.geweke_z_running_sums(X[:rows])
+        assert np.allclose(Z, Zs, rtol=1e-6, atol=1e-9), (Z, Zs)
+        assert np.array_equal(np.abs(Z) <= 2, np.abs(Zs) <= 2)
+
+
 def test_deviance_ic():
     d = O.devianceIC(np.array([-10.0, -12.0, -11.0]), -9.0)
     assert d["DIC_Gelman"] == pytest.approx(18 + 4 * 1.0)
