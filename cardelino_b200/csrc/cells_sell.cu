@@ -35,7 +35,8 @@ struct SellParams {
     const uint4* a8;
     const uint4* b8;
     int64_t n_slices;
-    unsigned int* work;          // dynamic work-item counter (zeroed before the launch)
+    unsigned int* work;          // counter of the work items after every warp's static first one; zero on entry
+                                 // (k_table's last block re-arms it)
     // small shards: a slice's groups are split over `parts` warps (work item = slice * parts + part); each
     // part leaves its partial logits in `scratch`, the part that finishes last (ticket) adds them up in part
     // order -- deterministic -- and runs the epilogue

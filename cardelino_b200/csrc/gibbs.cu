@@ -215,8 +215,8 @@ struct StatsParams {
     int n_cb;             // cell blocks
     const unsigned int* run_flag;   // incremental mode: the full pass runs only if *run_flag != 0 (else nullptr)
     const int* plan;      // [grid + 2 * n_cb]: home block of each CTA, first CTA and CTA count of each block
-    int chunks_per_warp;  // 1: one static range per warp; > 1: ranges are pulled from the block's counter
-    unsigned int* work;   // [n_cb] chunk counters (zeroed before the launch; used when chunks_per_warp > 1)
+    int chunks_per_warp;  // k_stats_units: work units per segment (k_stats_stream takes one static range per warp)
+    unsigned int* work;   // [n_cb] unit counters of k_stats_units; zero on entry (k_table's last block re-arms them)
 };
 
 // One 8-entry group of a variant segment into the lane-private clone bins.  A and B share one 32-bit bin
