@@ -8,5 +8,7 @@ from ._lib import CdlError, Handle, load_library, LIB_PATH, EXPORTS  # noqa: F40
 from .clone_id import (clone_id, clone_id_Gibbs, clone_id_EM, get_logLik, colMatch, devianceIC,  # noqa: F401
                        Geweke_Z, assign_cells_to_clones, SparseCounts)
 
-__all__ = ["clone_id", "clone_id_Gibbs", "clone_id_EM", "get_logLik", "colMatch", "devianceIC", "Geweke_Z",
+from .assessment import (rowMax, rowArgmax, binaryPRC, binaryROC, multiPRC, assign_scores)  # noqa: F401
+
+__all__ = ["rowMax", "rowArgmax", "binaryPRC", "binaryROC", "multiPRC", "assign_scores", "clone_id", "clone_id_Gibbs", "clone_id_EM", "get_logLik", "colMatch", "devianceIC", "Geweke_Z",
            "assign_cells_to_clones", "Handle", "CdlError", "load_library"]
