@@ -49,6 +49,64 @@ class SparseCounts:
         self.indptr, self.indices, self.a, self.d = indptr, indices, a, d
         self.cell_offset, self.M_total = int(cell_offset), int(M if M_total is None else M_total)
 
+    @classmethod
+    def from_sparse(cls, A, D):
+        """Merge two SciPy sparse matrices (variants x cells) -- the AD and DP matrices cellSNP / vcf loading
+        yields (R/read_data.R:293-294) -- into the one-pattern uint16 form, without densifying (replaces
+        as.matrix() at R/clone_id.R:121-122).  D == 0 is missing; an A entry there is dropped and an A entry absent
+        where D > 0 is 0 (R/clone_id.R:380-386)."""
+        if _sp is None:
+            raise ImportError("scipy is needed for sparse inputs")
+        D = _sp.csc_matrix(D, dtype=np.float64, copy=True)
+        A = _sp.csc_matrix(A, dtype=np.float64, copy=True)
+        if A.shape != D.shape:
+            raise ValueError("A and D must have the same size")
+        for X in (A, D):
+            X.sum_duplicates()
+            X.eliminate_zeros()
+            X.sort_indices()
+        if np.any(A.data % 1 != 0) or np.any(D.data % 1 != 0):
+            raise ValueError("A and/or D contain non-integer values.")
+        if A.nnz and A.data.min() < 0 or D.nnz and D.data.min() < 0:
+            raise ValueError("A and/or D contain negative values.")
+        if (A.nnz and A.data.max() > 65535) or (D.nnz and D.data.max() > 65535):
+            raise ValueError("count above 65535 (uint16 storage)")
+        N, M = D.shape
+        col = lambda X: np.repeat(np.arange(M, dtype=np.int64), np.diff(X.indptr))
+        key_d = col(D) * N + D.indices
+        key_a = col(A) * N + A.indices
+        pos = np.searchsorted(key_d, key_a)
+        pos[pos == key_d.size] = 0
+        hit = key_d[pos] == key_a if key_d.size else np.zeros(key_a.size, dtype=bool)
+        a = np.zeros(D.nnz, dtype=np.uint16)
+        a[pos[hit]] = A.data[hit].astype(np.uint16)
+        d = D.data.astype(np.uint16)
+        if np.any(a > d):
+            raise ValueError("A exceeds D at a covered entry")
+        return cls(N, M, D.indptr.astype(np.int64), D.indices.astype(np.int32), a, d)
+
+    @classmethod
+    def from_mtx(cls, ad_path, dp_path):
+        """The same from two MatrixMarket files (e.g. the reference's inst/extdata/passed_ad.mtx / passed_dp.mtx)."""
+        from scipy.io import mmread
+
+        def read(path):
+            try:
+                return mmread(path, spmatrix=False)      # SciPy >= 1.15: say which sparse flavour explicitly
+            except TypeError:
+                return mmread(path)
+        return cls.from_sparse(read(ad_path), read(dp_path))
+
+    def to_dense(self):
+        """(A, D) as float64 arrays with NaN where D is missing -- the form sim_read_count emits."""
+        N, M = self.shape
+        A = np.full((N, M), np.nan)
+        D = np.full((N, M), np.nan)
+        cols = np.repeat(np.arange(M), np.diff(np.asarray(self.indptr)))
+        A[self.indices, cols] = self.a
+        D[self.indices, cols] = self.d
+        return A, D
+
 
 def _names(x):
     if _pd is not None and isinstance(x, _pd.DataFrame):

@@ -132,3 +132,38 @@ def test_r_shim_compiles_against_stub_headers():
                         "-I", os.path.join(root, "include"), os.path.join(root, "r", "cardelino_b200_shim.c")],
                        capture_output=True, text=True)
     assert r.returncode == 0, r.stderr
+
+
+def test_sparse_counts_from_sparse_and_mtx(tmp_path):
+    """Sparse ingestion without densifying: two sparse matrices / MatrixMarket files
+    -> the one-pattern uint16 form, with the reference's missing-data rules (R/clone_id.R:380-386) and the
+    library's limits."""
+    import scipy.sparse as sp
+    from scipy.io import mmwrite
+    import cardelino_b200 as cb
+    d = np.load(os.path.join(ROOT, "tests", "golden", "mito_passed.npz"))
+    AD, DP = d["AD"], d["DP"]                       # the reference's inst/extdata/passed_{ad,dp}.mtx, decoded
+    rng = np.random.default_rng(0)
+    DP = DP * (rng.random(DP.shape) < 0.7)          # knock out a third of the entries: D == 0 is missing
+    AD = np.minimum(AD, 60000)
+    DP = np.maximum(np.minimum(DP, 65535), AD) * (DP > 0)
+    stray = AD * (DP == 0)                          # A entries where D is missing must be dropped
+    assert stray.sum() > 0
+    sc = cb.SparseCounts.from_sparse(sp.coo_matrix(AD), sp.csr_matrix(DP))
+    A2, D2 = sc.to_dense()
+    assert np.array_equal(np.isnan(D2), DP == 0) and np.array_equal(np.isnan(A2), DP == 0)
+    assert np.array_equal(np.nan_to_num(D2), DP) and np.array_equal(np.nan_to_num(A2), AD * (DP > 0))
+    assert sc.a.dtype == np.uint16 and sc.d.dtype == np.uint16 and sc.indptr[-1] == (DP > 0).sum()
+    mmwrite(str(tmp_path / "ad.mtx"), sp.coo_matrix(AD))
+    mmwrite(str(tmp_path / "dp.mtx"), sp.coo_matrix(DP))
+    sm = cb.SparseCounts.from_mtx(str(tmp_path / "ad.mtx"), str(tmp_path / "dp.mtx"))
+    assert np.array_equal(sm.indptr, sc.indptr) and np.array_equal(sm.indices, sc.indices)
+    assert np.array_equal(sm.a, sc.a) and np.array_equal(sm.d, sc.d)
+    with pytest.raises(ValueError, match="non-integer"):
+        cb.SparseCounts.from_sparse(sp.csc_matrix(AD * 0.5), sp.csc_matrix(DP))
+    with pytest.raises(ValueError, match="65535"):
+        cb.SparseCounts.from_sparse(sp.csc_matrix(AD), sp.csc_matrix(DP * 100))
+    with pytest.raises(ValueError, match="exceeds"):
+        cb.SparseCounts.from_sparse(sp.csc_matrix(DP + (DP > 0)), sp.csc_matrix(DP))
+    with pytest.raises(ValueError, match="same size"):
+        cb.SparseCounts.from_sparse(sp.csc_matrix(AD[:-1]), sp.csc_matrix(DP))
