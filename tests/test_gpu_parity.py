@@ -548,7 +548,15 @@ def test_full_size_properties(gpu_handle):
     t0, t1 = h.fetch("theta_traces")
     assert np.all((t0 > 0) & (t0 < 1)) and np.all((t1 > 0) & (t1 < 1))
     lab = h.synth_labels()
-    assert (h.fetch("prob").argmax(1) + 1 == lab).mean() > 0.98
+    prob = h.fetch("prob")
+    assert (prob.argmax(1) + 1 == lab).mean() > 0.98
+    # scored like a simulation in the reference (R/assessment.R:354-373): clone columns match the truth, and the
+    # precision / recall curve of the assignment is near 1
+    cb = _cb()
+    I_sim = np.zeros((M, K))
+    I_sim[np.arange(M), lab - 1] = 1
+    assert np.array_equal(cb.colMatch(I_sim, prob), np.arange(K))
+    assert cb.multiPRC(prob, I_sim, verbose=False)["AUC"] > 0.97
     h.gibbs_run(cfg, None, **kw)
     assert np.array_equal(prob_all, h.fetch("prob_all")) and np.array_equal(ll, h.fetch("logLik"))
     p, i, a, d = h.export_csc_u16()
