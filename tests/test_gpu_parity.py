@@ -389,6 +389,28 @@ def test_relabel(gpu_handle, example_donor):
     assert g["prob"].shape == (428, 4) and np.allclose(g["prob"].sum(1), 1)
 
 
+def test_reference_testthat_clone_id(gpu_handle, example_donor):
+    """The reference's own hot-path test file, call for call (tests/testthat/test-clone_id.R:7-49): EM, the one
+    sampler configuration it exercises (min_iter = 200, max_iter = 500, relax_Config, relabel), and the consumers
+    of the result (assign_scores / multiPRC / binaryPRC, binaryROC).  Like there, the assertions are on types and
+    shapes -- the reference pins nothing else."""
+    cb = _cb()
+    A_clone, D_clone, Z = example_donor
+    assignments_EM = cb.clone_id(A_clone, D_clone, Config=Z, inference="EM", handle=gpu_handle, verbose=False)
+    assert isinstance(assignments_EM, dict) and assignments_EM["prob"].shape == (428, 4)
+    assignments = cb.clone_id(A_clone, D_clone, Config=Z, min_iter=200, max_iter=500, relax_Config=True,
+                              relabel=True, handle=gpu_handle, verbose=False)
+    assert isinstance(assignments, dict)
+    assert assignments["prob"].shape == (428, 4) and assignments["prob_variant"].shape == (34, 428)
+    assert assignments["Config_prob"].shape == (34, 4) and 200 <= assignments["n_iter"] <= 500
+    I_sim = assignments["prob"] == cb.rowMax(assignments["prob"])[:, None]
+    res = cb.assign_scores(assignments["prob"], I_sim, verbose=False)
+    assert isinstance(res, dict) and set(res) == {"df_sg", "df_db", "AUC_sg", "AUC_db"}
+    assert len(res["df_sg"]["cutoff"]) == 1001 and len(res["df_db"]["Recall"]) == 1001
+    res = cb.binaryROC(assignments["prob"][:, 0], I_sim[:, 0])
+    assert isinstance(res, dict) and 0.0 <= res["AUC"] <= 1.0
+
+
 def test_converged_posterior_matches_oracle_chains(gpu_handle, c2_donor, example_donor):
     """Correctness check 3: converged prob agrees with independent CPU chains within Monte-Carlo error
     (max |dprob| <= 0.02, identical argmax where prob > 0.9) wherever the posterior is identified: the
