@@ -5,10 +5,13 @@ Tolerances (BASELINE.json north_star): get_logLik / EM <= 1e-6 relative; replaye
 assignments exactly except draws within 1e-6 of a CDF boundary (or whose order in sample()'s sort is
 decided by rounding between two probabilities equal to 1e-12); converged prob within Monte-Carlo error
 (max |dprob| <= 0.02 on decided cells, identical argmax where prob > 0.9)."""
+import os
+
 import numpy as np
 import pytest
 
 pytestmark = pytest.mark.gpu
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 
 from oracle import cardelino_oracle as O  # noqa: E402
 
@@ -346,6 +349,40 @@ def test_replay_mode(gpu_handle, example_donor):
         assert np.array_equal(g["Config_all"], o["Config_all"])
         assert np.abs(g["prob"] - o["prob"]).max() <= 1e-9
         assert abs(g["DIC"]["DIC"] - o["DIC"]["DIC"]) <= 1e-6 * abs(o["DIC"]["DIC"])
+
+
+def test_committed_golden_vectors(gpu_handle, example_donor):
+    """The committed golden vectors (tests/golden/oracle_example_donor.npz, written by tools/make_golden.py from the
+    oracle; a genuine R recording made with tools/record_reference.R has the same fields): the recorded uniforms
+    and Beta draws injected through cdl_replay reproduce the recorded assignments and Config flips exactly and the
+    probabilities / logLik trace to 1e-9; cdl_em_run and cdl_get_loglik reproduce the stored EM fixed point and
+    log-likelihood to 1e-6 relative (the north star's bars)."""
+    cb = _cb()
+    g0 = np.load(os.path.join(ROOT, "tests", "golden", "oracle_example_donor.npz"))
+    A, D, Z = example_donor
+    T = int(g0["T"])
+    replay = {"n_rows": T, "u_assign": g0["u_assign"], "u_config": g0["u_config"], "theta0": g0["theta0_all"],
+              "theta1": g0["theta1_all"], "relax_rate": g0["relax_rate_all"]}
+    for layout in ("auto", "rows"):
+        gpu_handle.set_cells_layout(layout)
+        try:
+            g = cb.clone_id_Gibbs(A, D, Z, min_iter=T, max_iter=T, replay=replay, keep_assign_all=True,
+                                  handle=gpu_handle, verbose=False)
+        finally:
+            gpu_handle.set_cells_layout("auto")
+        assert np.array_equal(g["assign_all"], g0["assign_all"]) and np.array_equal(g["Config_all"], g0["Config_all"])
+        assert np.abs(g["prob"] - g0["prob"]).max() <= 1e-9
+        assert np.abs(g["prob_all"][T - 1] - g0["prob_all_last"]).max() <= 1e-9
+        assert np.allclose(g["logLik"][1:], g0["logLik"][1:], rtol=REL, atol=0)
+        assert np.array_equal(g["Config_prob"], g0["Config_prob"])
+    em = cb.clone_id_EM(A, D, Z, theta_init=tuple(g0["em_theta_init"]), handle=gpu_handle, verbose=False)
+    assert em["n_iter"] == int(g0["em_n_iter"]) and np.allclose(em["theta"], g0["em_theta"], rtol=REL, atol=0)
+    assert abs(em["logLik"] - float(g0["em_logLik"])) <= REL * abs(float(g0["em_logLik"]))
+    assert np.abs(em["prob"] - g0["em_prob"]).max() <= 1e-9
+    it, K, N = int(g0["ll_it"]), Z.shape[1], Z.shape[0]
+    ll = cb.get_logLik(A, D, g0["Config_all"][it - 1].reshape(K, N).T.astype(float), g0["assign_all"][it - 1],
+                       float(g0["theta0_all"][it - 1]), g0["theta1_all"][it - 1], handle=gpu_handle)
+    assert abs(ll - float(g0["ll_value"])) <= REL * abs(float(g0["ll_value"]))
 
 
 def test_stop_rule_and_summaries(gpu_handle, example_donor):

@@ -231,3 +231,28 @@ def test_c_oracle_runner_and_generator():
     assert all(np.all(np.diff(vi[p[j]:p[j + 1]]) > 0) for j in range(0, M, 97))
     sec, z, th1 = CO.run(N, M, K, p, vi, a, d, CO.config_masks(cfg), 30, seed=1)
     assert sec > 0 and (z + 1 == lab).mean() > 0.95 and np.all((th1 > 0) & (th1 < 1))
+
+
+def test_oracle_reproduces_committed_golden_vectors(example_donor):
+    """tests/golden/oracle_example_donor.npz (tools/make_golden.py): replaying the recorded uniforms and Beta draws
+    reproduces the recorded chain; EM from the stored start and get_logLik at the stored state give the stored
+    numbers.  Pins the oracle against drift (the reference itself cannot run here: parity unpinned)."""
+    import os
+    g = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "oracle_example_donor.npz"))
+    A, D, Z = example_donor
+    T = int(g["T"])
+    draws = O.ReplayDraws(theta0_all=g["theta0_all"], theta1_all=g["theta1_all"], relax_rate_all=g["relax_rate_all"],
+                          u_assign=g["u_assign"], u_config=g["u_config"])
+    o = O.clone_id_Gibbs(A, D, Z, min_iter=T, max_iter=T, draws=draws)
+    assert np.array_equal(o["assign_all"], g["assign_all"]) and np.array_equal(o["Config_all"], g["Config_all"])
+    assert np.abs(o["prob"] - g["prob"]).max() <= 1e-12 and np.abs(o["prob_all"][T - 1] - g["prob_all_last"]).max() <= 1e-12
+    assert np.allclose(o["logLik"], g["logLik"], rtol=1e-12, atol=0)
+    assert np.array_equal(o["Config_prob"], g["Config_prob"])
+    em = O.clone_id_EM(A, D, Z, theta_init=g["em_theta_init"])
+    assert em["n_iter"] == int(g["em_n_iter"]) and np.allclose(em["theta"], g["em_theta"], rtol=1e-12)
+    assert em["logLik"] == pytest.approx(float(g["em_logLik"]), rel=1e-12)
+    A1, B1, _ = O.preprocess(A, D)
+    it, K, N = int(g["ll_it"]), Z.shape[1], Z.shape[0]
+    ll = O.get_logLik_tables(A1, B1, g["Config_all"][it - 1].reshape(K, N).T.astype(float), g["assign_all"][it - 1],
+                             g["theta0_all"][it - 1], g["theta1_all"][it - 1])
+    assert ll == pytest.approx(float(g["ll_value"]), rel=1e-12)
