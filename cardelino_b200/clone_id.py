@@ -153,7 +153,8 @@ def colMatch(A, B, force=False):
     if A.shape[1] > B.shape[1]:
         raise ValueError("A must have equal or smaller columns than B.")
     ka, kb = A.shape[1], B.shape[1]
-    cost = np.abs(A[:, :, None] - B[:, None, :]).mean(axis=0)        # ka x kb column distances
+    # ka x kb column distances, one column of A at a time (an M x ka x kb temporary is 2 GB at 10^6 cells x 16)
+    cost = np.stack([np.abs(A[:, i:i + 1] - B).mean(axis=0) for i in range(ka)]) if ka else np.zeros((0, kb))
     if force:
         if kb <= 8:
             best, best_idx = None, None
