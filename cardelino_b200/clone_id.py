@@ -248,11 +248,13 @@ def clone_id_Gibbs(A, D, Config, Psi=None, relax_Config=True, relax_rate_fixed=N
                    keep_base_clone=True, prior0=(0.2, 99.8), prior1=(0.45, 0.55), min_iter=5000,
                    max_iter=20000, buin_frac=0.5, wise="variant", relabel=False, verbose=True,
                    seed=1, n_chain=1, replay=None, keep_assign_all=False, keep_prob_all=-1,
-                   handle=None, light=False, incremental_stats=False, chain_offset=0, _loaded=False,
+                   handle=None, light=None, incremental_stats=False, chain_offset=0, _loaded=False,
                    _all_chains=False):
     """R/clone_id.R:351-675.  Returns the reference's list (:662-673) as a dict.  Extra arguments: `seed`
     (Philox key; the reference uses R's global RNG), `n_chain` (chains run inside the library), `replay`
-    (dict of injected draws, see cdl_replay)."""
+    (dict of injected draws, see cdl_replay), `light` (leave out the fields that are dense N x M or
+    max_iter x N*K doubles -- theta1, prob_variant, element, Config_all, prob_all; default: only when they would
+    not fit a workstation's memory, i.e. N*M > 2e8 or the Config trace above 2 GB)."""
     Av, Dv = _values(A), _values(D)
     Config = np.asarray(_values(Config), dtype=np.float64)
     if Psi is None:
@@ -277,6 +279,8 @@ def clone_id_Gibbs(A, D, Config, Psi=None, relax_Config=True, relax_rate_fixed=N
         _load(h, Av, Dv)
     N, M = Av.shape
     K = Config.shape[1]
+    if light is None:
+        light = (not relabel) and (N * M > _DENSE_LIMIT or float(max_iter) * N * K * 8.0 > 2.0 ** 31)
     h.gibbs_run(Config, Psi, replay=replay, relax_Config=int(relax), relax_rate_fixed=relax_rate_fixed,
                 relax_rate_prior=relax_rate_prior if relax_rate_prior is not None else (1, 9),
                 keep_base_clone=int(bool(keep_base_clone)), prior0=prior0, prior1=prior1,
@@ -293,6 +297,11 @@ def _collect(h, chain, Av, Config, wise, relabel, verbose, keep_assign_all, ligh
     N, M = Av.shape
     if light:   # large donors: only the fields that stay small (no dense N x M, no big traces)
         info = h.gibbs_info(chain)
+        pc = info.percent_converged
+        if pc <= 95 or pc != pc:
+            warnings.warn("Only %s%% of parameters converged. Consider increasing `max_iter`." % pc)
+        elif verbose:
+            print("Converged in %d iterations." % info.n_iter)
         theta0, theta1_el = h.fetch("theta", chain)
         theta0_all, theta1_all = h.fetch("theta_traces", chain)
         relax_rate, relax_rate_all = h.fetch("relax_rate", chain)
@@ -301,6 +310,7 @@ def _collect(h, chain, Av, Config, wise, relabel, verbose, keep_assign_all, ligh
                 "relax_rate": relax_rate, "relax_rate_all": relax_rate_all,
                 "Config_prob": h.fetch("Config_prob", chain), "n_iter": info.n_iter, "n_buin": info.n_buin,
                 "percent_converged": info.percent_converged, "logLik_post": info.logLik_post,
+                "W_log": info.W_log, "exact_trace": bool(info.exact_trace),
                 "DIC": dict(zip(("DIC", "logLik_var", "D_mean", "D_post", "DIC_Gelman", "DIC_Spiegelhalter"),
                                 list(info.dic)))}
     K = Config.shape[1]
