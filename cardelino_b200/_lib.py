@@ -9,7 +9,8 @@ import os
 import numpy as np
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libcardelino_b200.so")
+# CARDELINO_B200_LIB selects another build of the same library (kernel A/B experiments); the default is the in-tree one
+LIB_PATH = os.environ.get("CARDELINO_B200_LIB") or os.path.join(_HERE, "libcardelino_b200.so")
 
 EXPORTS = [
     "cdl_version", "cdl_last_error", "cdl_create", "cdl_destroy", "cdl_load_dense", "cdl_load_csc",
@@ -19,6 +20,7 @@ EXPORTS = [
     "cdl_fetch_loglik_trace", "cdl_fetch_relax_rate", "cdl_fetch_prob_all", "cdl_fetch_config_all",
     "cdl_fetch_assign_all", "cdl_fetch_prob_variant", "cdl_fetch_element_index", "cdl_get_loglik",
     "cdl_em_run", "cdl_bench_sweeps", "cdl_set_cells_layout", "cdl_set_exchange_mode", "cdl_exchange_is_peer", "cdl_incremental_full_passes",
+    "cdl_debug_capture", "cdl_debug_fetch",
 ]
 
 WISE = {"global": 0, "variant": 1, "element": 2}
@@ -31,6 +33,10 @@ class CdlError(RuntimeError):
         self.code = code
 
 
+# int (*cdl_progress_fn)(void* user, int32_t chain, int32_t iteration, double fraction)
+PROGRESS_FN = C.CFUNCTYPE(C.c_int, C.c_void_p, C.c_int32, C.c_int32, C.c_double)
+
+
 class GibbsParams(C.Structure):
     _fields_ = [
         ("relax_Config", C.c_int32), ("relax_rate_fixed_set", C.c_int32), ("relax_rate_fixed", C.c_double),
@@ -40,6 +46,8 @@ class GibbsParams(C.Structure):
         ("seed", C.c_uint64), ("keep_assign_all", C.c_int32), ("keep_prob_all", C.c_int32),
         ("trace_budget_bytes", C.c_int64), ("check_every", C.c_int32), ("verbose", C.c_int32),
         ("acc_fp32", C.c_int32), ("chain_offset", C.c_int32), ("incremental_stats", C.c_int32),
+        ("relabel", C.c_int32), ("prior1_matrix_rows", C.c_int64), ("progress", PROGRESS_FN),
+        ("progress_user", C.c_void_p), ("snapshot_fp32", C.c_int32),
     ]
 
 
@@ -199,6 +207,7 @@ class Handle:
         p = GibbsParams()
         self.lib.cdl_gibbs_defaults(C.byref(p))
         keep = []
+        pending = []
         for name, val in kw.items():
             if name in ("relax_rate_prior", "prior0", "prior1"):
                 arr = getattr(p, name)
@@ -206,8 +215,25 @@ class Handle:
             elif name == "prior1_matrix":
                 if val is not None:
                     m = _f64(val)
+                    if m.ndim != 2 or m.shape[1] != 2:
+                        raise CdlError(1, "prior1 must be a matrix with two columns")
                     keep.append(m)
                     p.prior1_matrix = _dp(m)
+                    p.prior1_matrix_rows = m.shape[0]
+            elif name == "progress":
+                if val is not None:
+                    # exceptions must not cross the C frames: remember the first one, ask the library to stop
+                    # (CDL_ERR_INTERRUPTED) and re-raise after the call has returned
+                    def _cb(_user, chain, it, frac, _f=val):
+                        try:
+                            return int(bool(_f(chain, it, frac)))
+                        except BaseException as e:      # noqa: BLE001 (KeyboardInterrupt included)
+                            if not pending:
+                                pending.append(e)
+                            return 1
+                    fn = PROGRESS_FN(_cb)
+                    keep.append(fn)
+                    p.progress = fn
             elif name == "relax_rate_fixed":
                 if val is None:
                     p.relax_rate_fixed_set = 0
@@ -231,10 +257,29 @@ class Handle:
                     v = np.ascontiguousarray(v, np.float64)
                     keep.append(v)
                     setattr(rp, f, _dp(v))
-        self._check(self.lib.cdl_gibbs_run(self.h, _dp(Config), C.c_int32(K), _dp(psi), C.byref(p),
-                                           C.byref(rp) if rp is not None else None))
+        rc = self.lib.cdl_gibbs_run(self.h, _dp(Config), C.c_int32(K), _dp(psi), C.byref(p),
+                                    C.byref(rp) if rp is not None else None)
+        if pending:
+            raise pending[0]
+        self._check(rc)
         self._N, self._K = N, K
         return p
+
+    # ---- test hooks ----
+    def debug_capture(self, enable=True):
+        self._check(self.lib.cdl_debug_capture(self.h, C.c_int32(1 if enable else 0)))
+
+    def debug_fetch(self):
+        """(SA, SB) this rank's N x K statistic table of the last sweep (before any exchange), the integers added to
+        the theta1 priors (S3[N], S4[N]) and the totals (S1, S2, S3, S4, diff1)."""
+        N, K = self._N, self._K
+        SA = np.zeros((N, K), np.uint64)
+        SB = np.zeros((N, K), np.uint64)
+        S3 = np.zeros(N, np.uint64)
+        S4 = np.zeros(N, np.uint64)
+        tot = np.zeros(5, np.uint64)
+        self._check(self.lib.cdl_debug_fetch(self.h, *[C.c_void_p(x.ctypes.data) for x in (SA, SB, S3, S4, tot)]))
+        return SA, SB, S3, S4, tot
 
     def incremental_full_passes(self, chain=0):
         out = C.c_uint32()

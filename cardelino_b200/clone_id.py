@@ -248,13 +248,16 @@ def clone_id_Gibbs(A, D, Config, Psi=None, relax_Config=True, relax_rate_fixed=N
                    keep_base_clone=True, prior0=(0.2, 99.8), prior1=(0.45, 0.55), min_iter=5000,
                    max_iter=20000, buin_frac=0.5, wise="variant", relabel=False, verbose=True,
                    seed=1, n_chain=1, replay=None, keep_assign_all=False, keep_prob_all=-1,
-                   handle=None, light=None, incremental_stats=False, chain_offset=0, _loaded=False,
-                   _all_chains=False):
+                   handle=None, light=None, incremental_stats=None, chain_offset=0, _loaded=False,
+                   _all_chains=False, progress=None, **lib_kw):
     """R/clone_id.R:351-675.  Returns the reference's list (:662-673) as a dict.  Extra arguments: `seed`
     (Philox key; the reference uses R's global RNG), `n_chain` (chains run inside the library), `replay`
     (dict of injected draws, see cdl_replay), `light` (leave out the fields that are dense N x M or
     max_iter x N*K doubles -- theta1, prob_variant, element, Config_all, prob_all; default: only when they would
-    not fit a workstation's memory, i.e. N*M > 2e8 or the Config trace above 2 GB)."""
+    not fit a workstation's memory, i.e. N*M > 2e8 or the Config trace above 2 GB), `incremental_stats` (None: the
+    library default, on wherever it applies; see cdl_gibbs_params), `progress(chain, iteration, fraction)` (called
+    every 100 sweeps; a true return value stops the run -- `verbose` prints the reference's "x% converged." lines
+    through it)."""
     Av, Dv = _values(A), _values(D)
     Config = np.asarray(_values(Config), dtype=np.float64)
     if Psi is None:
@@ -262,7 +265,7 @@ def clone_id_Gibbs(A, D, Config, Psi=None, relax_Config=True, relax_rate_fixed=N
     _check_shapes(Av, Dv, Config, Psi, gibbs=True)
     if wise not in ("element", "variant", "global"):
         raise ValueError("Input wise mode: %s, while only supporting: element, variant, global" % wise)
-    relax = relax_Config is not None and relax_Config is not False
+    relax = relax_Config is not None and bool(relax_Config)        # R: !is.null(relax_Config) && relax_Config != FALSE
     if relax and relax_rate_fixed is not None and (relax_rate_fixed > 1 or relax_rate_fixed < 0):
         raise ValueError("relax_rate_fixed needs to be NULL or in [0, 1].")
     if relax and relax_rate_fixed is None and relax_rate_prior is None:
@@ -270,6 +273,8 @@ def clone_id_Gibbs(A, D, Config, Psi=None, relax_Config=True, relax_rate_fixed=N
     prior1 = np.asarray(prior1, dtype=np.float64)
     prior1_matrix = None
     if prior1.ndim == 2:
+        if prior1.shape[1] != 2 or prior1.shape[0] < 1:
+            raise ValueError("prior1 need to be a matrix of n_element x 2")
         prior1_matrix = prior1
         prior1 = prior1[0]
     elif not (prior1.ndim == 1 and prior1.size == 2):
@@ -279,6 +284,12 @@ def clone_id_Gibbs(A, D, Config, Psi=None, relax_Config=True, relax_rate_fixed=N
         _load(h, Av, Dv)
     N, M = Av.shape
     K = Config.shape[1]
+    if prior1_matrix is not None:
+        # one row per theta1 element (R/clone_id.R:418-424): 1, N or the number of covered entries
+        n_el = {"global": 1, "variant": N}.get(wise) or h.data_info()[2]
+        if prior1_matrix.shape[0] != n_el:
+            raise ValueError("prior1 need to be a matrix of n_element x 2 (n_element = %d for wise = %r, got %d rows)"
+                             % (n_el, wise, prior1_matrix.shape[0]))
     if light is None:
         light = (not relabel) and (N * M > _DENSE_LIMIT or float(max_iter) * N * K * 8.0 > 2.0 ** 31)
     h.gibbs_run(Config, Psi, replay=replay, relax_Config=int(relax), relax_rate_fixed=relax_rate_fixed,
@@ -287,10 +298,24 @@ def clone_id_Gibbs(A, D, Config, Psi=None, relax_Config=True, relax_rate_fixed=N
                 prior1_matrix=prior1_matrix, min_iter=int(min_iter), max_iter=int(max_iter),
                 buin_frac=float(buin_frac), wise=wise, n_chain=int(n_chain), seed=int(seed),
                 keep_assign_all=int(bool(keep_assign_all)),
-                keep_prob_all=1 if relabel else int(keep_prob_all), verbose=0,
-                incremental_stats=int(bool(incremental_stats)), chain_offset=int(chain_offset))
+                keep_prob_all=1 if relabel else int(keep_prob_all), verbose=0, relabel=int(bool(relabel)),
+                incremental_stats=-1 if incremental_stats is None else int(bool(incremental_stats)),
+                chain_offset=int(chain_offset), progress=_progress_printer(verbose, progress), **lib_kw)
     outs = [_collect(h, c, Av, Config, wise, relabel, verbose, keep_assign_all, light) for c in range(n_chain)]
     return outs if _all_chains else outs[0]
+
+
+def _progress_printer(verbose, user_cb):
+    """The reference cat()s "x% converged." at every convergence check (R/clone_id.R:583-588); the library reports the
+    fraction through its progress callback and prints nothing itself."""
+    if not verbose and user_cb is None:
+        return None
+
+    def cb(chain, it, frac):
+        if verbose and frac == frac:
+            print("%g%% converged." % (round(frac, 3) * 100))
+        return bool(user_cb(chain, it, frac)) if user_cb is not None else False
+    return cb
 
 
 def _collect(h, chain, Av, Config, wise, relabel, verbose, keep_assign_all, light=False):
@@ -350,22 +375,7 @@ def _collect(h, chain, Av, Config, wise, relabel, verbose, keep_assign_all, ligh
         out["prob_variant"] = h.fetch("prob_variant", chain)
     else:
         out["theta1_elements"] = theta1_el
-    logLik_post = info.logLik_post
-    if relabel:
-        # R/clone_id.R:624-644 on the host (needs the full traces; O(it * K!) like the reference)
-        prob_all, Config_all = out["prob_all"], out["Config_all"]
-        col_idx_use = np.arange(K)
-        for ii in range(n_buin, it + 1):
-            mat1 = prob_all[ii - 2].reshape(K, M).T
-            mat2 = prob_all[ii - 1].reshape(K, M).T
-            idx = colMatch(mat1, mat2, force=(K <= 5))
-            col_idx_use = col_idx_use[idx]
-            prob_all[ii - 1] = mat2[:, col_idx_use].T.ravel()
-            Config_all[ii - 1] = Config_all[ii - 1].reshape(K, N).T[:, col_idx_use].T.ravel()
-        out["prob"] = prob_all[n_buin - 1:it].mean(axis=0).reshape(K, M).T.copy()
-        out["Config_prob"] = Config_all[n_buin - 1:it].mean(axis=0).reshape(K, N).T.copy()
-        logLik_post = h.get_loglik(out["Config_prob"], out["prob"], theta0, theta1_el)
-        out["logLik_post"] = logLik_post
+    logLik_post = info.logLik_post       # relabel (R/clone_id.R:624-644) ran on the device before the summaries
     out["DIC"] = devianceIC(out["logLik"][n_buin - 1:it], logLik_post, verbose=verbose)
     return out
 
@@ -406,7 +416,11 @@ def clone_id(A, D, Config=None, n_clone=None, Psi=None, relax_Config=True, relax
     if Config is None and n_clone is None:
         raise ValueError("Config and n_clone can't be NULL together.")
     Av, Dv = _values(A), _values(D)
+    if isinstance(Av, SparseCounts) and Dv is None:
+        Dv = Av                 # compact counts carry both matrices (already validated integers)
     for name, X in (("A", Av), ("D", Dv)):
+        if isinstance(X, SparseCounts):
+            continue
         vals = X.data if (_sp is not None and _sp.issparse(X)) else X
         with np.errstate(invalid="ignore"):
             if np.any((vals % 1 != 0) & ~np.isnan(vals)):
@@ -422,7 +436,8 @@ def clone_id(A, D, Config=None, n_clone=None, Psi=None, relax_Config=True, relax
         c_rows, c_cols = _names(Config)
         Cv = np.asarray(_values(Config), dtype=np.float64)
     if c_rows is not None and d_rows is not None:
-        common = [v for v in c_rows if v in set(d_rows)]           # intersect(rownames(Config), rownames(D))
+        d_set = set(d_rows)
+        common = [v for v in c_rows if v in d_set]                 # intersect(rownames(Config), rownames(D))
         if not common:
             raise ValueError("No matches in variant names between Config and D arguments.")
         di = {v: n for n, v in enumerate(d_rows)}

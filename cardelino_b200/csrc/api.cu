@@ -80,6 +80,7 @@ struct Chain {
     DevBuf<uint8_t> chg_old;
     DevBuf<double> sell_scratch;
     DevBuf<double2> tab_g;
+    DevBuf<unsigned long long> dbg_s34, dbg_sab;   // test hooks (cdl_debug_capture)
     // summaries
     DevBuf<double> prob_mean, config_prob, theta1_mean;
     double theta0_mean = 0.0, relax_mean = 0.0;
@@ -115,6 +116,7 @@ struct cdl_handle_s {
     P2PState p2p;
     bool p2p_active = false;
     std::vector<void*> p2p_opened;       // cudaIpcOpenMemHandle mappings to close
+    bool debug_capture = false;          // cdl_debug_capture
     int cells_layout = CDL_CELLS_AUTO;   // cdl_set_cells_layout
     bool use_sell = false;               // decided per run
 };
@@ -379,14 +381,22 @@ void one_sweep(cdl_handle h, Chain& ch, SweepArgs& a, uint32_t it, const cdl_rep
     }
     if (h->use_sell) launch_cells_sell(h->donor, a, ch.dev, h->sm_count, h->st);
     else launch_cells(h->donor, a, ch.dev, h->sm_count, h->st);
+    auto capture = [&]() {       // test hook: this rank's table as the statistic kernel left it
+        if (ch.dev.dbg_sab)
+            CDL_CUDA(cudaMemcpyAsync(ch.dev.dbg_sab, ch.dev.sab, sizeof(unsigned long long) * (size_t)(a.N * a.K),
+                                     cudaMemcpyDeviceToDevice, h->st));
+    };
     if (h->p2p_active) {
         // statistic table into this sweep's half of the peer-visible arena; publish; the table kernel sums
-        // the peers' halves while it reads them (no collective call)
+        // the peers' halves while it reads them (no collective call).  With incremental statistics the previous
+        // table kernel has left this rank's previous table in this half, for k_stats_incr to correct.
         P2PState& q = h->p2p;
         ++q.epoch;
         ch.dev.sab = q.arena + (size_t)(q.epoch & 1ull) * q.table_elems;
         a.p2p = &q;
-        launch_stats(h->donor, a, ch.dev, h->sm_count, h->st);
+        if (a.incremental) { launch_stats_incremental(h->donor, a, ch.dev, h->sm_count, h->st); h->launches += 2; }
+        else launch_stats(h->donor, a, ch.dev, h->sm_count, h->st);
+        capture();
         launch_signal(q, h->st);
         launch_table(h->donor, a, ch.dev, h->st);
         h->launches += 4;   // + k_signal
@@ -394,6 +404,7 @@ void one_sweep(cdl_handle h, Chain& ch, SweepArgs& a, uint32_t it, const cdl_rep
         a.p2p = nullptr;
         if (a.incremental) { launch_stats_incremental(h->donor, a, ch.dev, h->sm_count, h->st); h->launches += 2; }
         else launch_stats(h->donor, a, ch.dev, h->sm_count, h->st);
+        capture();
         allreduce_u64(h, ch.dev.sab, (size_t)(a.N * a.K));
         launch_table(h->donor, a, ch.dev, h->st);
         h->launches += 3;   // k_cells / k_cells_sell, k_stats, k_table (+ memset nodes)
@@ -475,6 +486,8 @@ int cdl_load_dense(cdl_handle h, int64_t N, int64_t M, const double* A, const do
                 const double dv = D[i + j * N], av = A[i + j * N];
                 if (!is_na(av)) { if (av != std::floor(av)) throw Error(CDL_ERR_INVALID, "A and/or D contain non-integer values."); }
                 if (is_na(dv)) {
+                    // D missing (NA) with reads in A: the reference keeps A there (only D == 0 clears A, :380), then
+                    // B1 = D - A is NA -> 0 (:391): alternative reads with no depth.  Refused rather than guessed.
                     if (!is_na(av) && av != 0.0)
                         throw Error(CDL_ERR_INVALID, "A has a count where D is missing (NA); the reference would "
                                                      "count those reads with zero depth");
@@ -510,11 +523,9 @@ int cdl_load_csc(cdl_handle h, int64_t N, int64_t M, const int64_t* d_p, const i
                 if (i < 0 || i >= N) throw Error(CDL_ERR_INVALID, "row index out of range in D");
                 if (is_na(dv) || dv == 0.0) continue;
                 check_count(dv, "D");
-                while (ea < ea1 && a_i[ea] < i) {
-                    if (!is_na(a_x[ea]) && a_x[ea] != 0.0)
-                        throw Error(CDL_ERR_INVALID, "A has a count where D is zero/missing");
-                    ++ea;
-                }
+                // A entries at positions where D is zero or absent are dropped, as A[which(D == 0)] <- NA does
+                // (R/clone_id.R:380); the dense loader and SparseCounts.from_sparse do the same
+                while (ea < ea1 && a_i[ea] < i) ++ea;
                 double av = 0.0;
                 if (ea < ea1 && a_i[ea] == i) { av = is_na(a_x[ea]) ? 0.0 : a_x[ea]; ++ea; }
                 check_count(av, "A");
@@ -658,6 +669,8 @@ void cdl_gibbs_defaults(cdl_gibbs_params* p) {
     p->keep_prob_all = -1;
     p->trace_budget_bytes = (int64_t)48 << 30;
     p->check_every = 100;
+    p->incremental_stats = -1;
+    p->snapshot_fp32 = 1;
 }
 
 int cdl_gibbs_run(cdl_handle h, const double* Config, int32_t K, const double* Psi, const cdl_gibbs_params* params,
@@ -707,6 +720,9 @@ int cdl_gibbs_run(cdl_handle h, const double* Config, int32_t K, const double* P
         std::vector<uint32_t> masks = config_masks(Config, N, K, true);
         h->cfg0.alloc((size_t)N);
         h->cfg0.upload(masks.data(), (size_t)N, h->st);
+        if (gp.prior1_matrix && gp.prior1_matrix_rows != 0 && gp.prior1_matrix_rows != n_el)
+            throw Error(CDL_ERR_INVALID, "prior1 must be a matrix with one row per theta1 element (" +
+                                             std::to_string(n_el) + " rows for this wise mode) and two columns");
         if (gp.prior1_matrix) {
             h->prior1_mat.alloc((size_t)n_el * 2);
             h->prior1_mat.upload(gp.prior1_matrix, (size_t)n_el * 2, h->st);
@@ -734,8 +750,11 @@ int cdl_gibbs_run(cdl_handle h, const double* Config, int32_t K, const double* P
         a.W_log = allreduce_scalar_d(h, d.W_log);
         a.key = PhiloxKey{(uint32_t)(gp.seed & 0xffffffffu), (uint32_t)(gp.seed >> 32)};
         a.T = T;
-        // incremental statistics: single GPU, per-variant tables (the element path keeps fp64 sums)
-        a.incremental = (gp.incremental_stats && h->world == 1 && !element) ? 1 : 0;
+        // incremental statistics: per-variant tables (the element path keeps fp64 sums); across GPUs only with the
+        // peer-memory exchange, whose arena keeps each rank's own table apart from the sum (the NCCL all-reduce
+        // overwrites it in place)
+        const bool incr_possible = !element && !replay && (h->world == 1 || h->p2p_active);
+        a.incremental = (gp.incremental_stats != 0 && incr_possible) ? 1 : 0;
 
         // replay arrays -> device
         DevBuf<double> r_ua, r_uc, r_t0, r_t1, r_rr;
@@ -761,7 +780,17 @@ int cdl_gibbs_run(cdl_handle h, const double* Config, int32_t K, const double* P
         // exact mode?
         const double trace_bytes = (double)T * (double)M * (double)K * 8.0;
         bool exact = gp.keep_prob_all == 1 || (gp.keep_prob_all == -1 && trace_bytes <= (double)gp.trace_budget_bytes);
+        if (gp.relabel && !exact)
+            throw Error(CDL_ERR_UNSUPPORTED, "relabel needs the prob_all trace (keep_prob_all = 1, or a trace that fits "
+                                             "trace_budget_bytes)");
+        if (gp.relabel && h->world > 1)
+            throw Error(CDL_ERR_UNSUPPORTED, "relabel runs on one GPU (the column match of every row is a reduction over all cells)");
         const int check_every = gp.check_every > 0 ? gp.check_every : 100;
+        // host callback (verbose printing, user interrupt) every check_every sweeps; never from another thread
+        auto notify = [&](int chain, int64_t it, double frac) {
+            if (gp.progress && gp.progress(gp.progress_user, (int32_t)chain, (int32_t)it, frac) != 0)
+                throw Error(CDL_ERR_INTERRUPTED, "interrupted by the progress callback");
+        };
         const int64_t n_buin_planned = (int64_t)std::ceil((double)T * gp.buin_frac);
         DevBuf<unsigned long long> gcounts(2);
 
@@ -772,7 +801,13 @@ int cdl_gibbs_run(cdl_handle h, const double* Config, int32_t K, const double* P
         // check row n.  That is 2-3 snapshots per check instead of n rows; used when a stop before max_iter is
         // possible, the snapshots that are alive together fit the trace budget, and the run takes the plain
         // one-chain-at-a-time branch (wise = global / variant).
-        struct Snap { DevBuf<double> s1, s2; int64_t last_use = 0; bool need_s2 = false; };
+        // Snapshots are kept as fp32 by default (snapshot_fp32): they only enter differences of sums over hundreds of
+        // rows, so Z moves by ~1e-6 relative and the posterior means by < 1e-7, for half the memory.
+        const bool snap32 = gp.snapshot_fp32 != 0;
+        struct Snap {
+            DevBuf<double> s1, s2; DevBuf<float> f1, f2; int64_t last_use = 0; bool need_s2 = false;
+            void release() { s1.release(); s2.release(); f1.release(); f2.release(); }
+        };
         std::map<int64_t, Snap> snaps;          // by row count r (rows 1..r summed); r <= 1 needs no buffer
         std::vector<int64_t> win_checks;
         auto rowsA = [](int64_t n) { return (int64_t)std::floor(0.1 * (double)n); };
@@ -800,7 +835,9 @@ int cdl_gibbs_run(cdl_handle h, const double* Config, int32_t K, const double* P
                     if (kw.first <= kv.first && kw.second.last_use >= kv.first) live += kw.second.need_s2 ? 2.0 : 1.0;
                 peak = std::max(peak, live);
             }
-            if ((peak + 2.0) * (double)M * (double)K * 8.0 > (double)gp.trace_budget_bytes) { win = false; snaps.clear(); }
+            if ((peak * (snap32 ? 0.5 : 1.0) + 2.0) * (double)M * (double)K * 8.0 > (double)gp.trace_budget_bytes) {
+                win = false; snaps.clear();
+            }
         }
 
         // ---- a chain's life in three steps, each on whatever stream h->st currently is ----
@@ -859,6 +896,12 @@ int cdl_gibbs_run(cdl_handle h, const double* Config, int32_t K, const double* P
                 ch.chg_ctl.upload(ctl0, 4, h->st);
                 CDL_CUDA(cudaStreamSynchronize(h->st));
             }
+            ch.dev.dbg_s34 = nullptr; ch.dev.dbg_sab = nullptr;
+            if (h->debug_capture) {
+                ch.dbg_s34.alloc((size_t)(2 * N + 5)); ch.dbg_s34.zero(h->st);
+                ch.dbg_sab.alloc((size_t)(N * K)); ch.dbg_sab.zero(h->st);
+                ch.dev.dbg_s34 = ch.dbg_s34.p; ch.dev.dbg_sab = ch.dbg_sab.p;
+            }
             ch.dev.sell_scratch = nullptr; ch.dev.sell_tickets = nullptr;
             if (h->use_sell && d.s_slices < 64 * (int64_t)h->sm_count) {
                 const int KPs = K <= 4 ? 4 : (K <= 8 ? 8 : (K <= 16 ? 16 : 32));
@@ -880,7 +923,7 @@ int cdl_gibbs_run(cdl_handle h, const double* Config, int32_t K, const double* P
             if (element) launch_el_init(h->donor, a, ch.dev, h->st);
             return chp;
         };
-        const double* win_burn_s1 = nullptr;    // windows mode: snapshot at row ceil(it * buin_frac) - 1 of the final it
+        const void* win_burn_s1 = nullptr;      // windows mode: snapshot at row ceil(it * buin_frac) - 1 of the final it
         auto finish_chain = [&](Chain& ch, SweepArgs& a, int64_t it_final, double frac) {
             const int64_t itf = it_final;
             if (exact) frac = geweke_fraction(h, ch, itf, gcounts);
@@ -903,10 +946,11 @@ int cdl_gibbs_run(cdl_handle h, const double* Config, int32_t K, const double* P
             ch.info.exact_trace = exact ? 1 : 0;
             ch.info.W_log = a.W_log;
             const int64_t r0 = n_buin - 1, r1 = itf;
+            if (gp.relabel) relabel_trace(ch.prob_all.p, ch.config_all.p, M, N, K, n_buin, itf, h->st);   // (:624-644)
             // posterior means (:645-653)
             ch.prob_mean.alloc((size_t)(M * K));
             if (exact) launch_col_means_d(ch.prob_all.p, M * K, r0, r1, ch.prob_mean.p, h->st);
-            else if (win) launch_window_mean(ch.prob_acc.p, win_burn_s1, M * K, 1.0 / (double)(r1 - r0), ch.prob_mean.p, h->st);
+            else if (win) launch_window_mean(ch.prob_acc.p, win_burn_s1, snap32, M * K, 1.0 / (double)(r1 - r0), ch.prob_mean.p, h->st);
             else {
                 // accumulator holds the sum over rows [n_buin_planned, T]
                 CDL_CUDA(cudaMemcpyAsync(ch.prob_mean.p, ch.prob_acc.p, sizeof(double) * (size_t)(M * K),
@@ -946,9 +990,9 @@ int cdl_gibbs_run(cdl_handle h, const double* Config, int32_t K, const double* P
         // small donors: every chain is one CTA of one grid, check_every sweeps per launch (small.cu)
         const bool small = (h->cells_layout == CDL_CELLS_SMALL ||
                             (h->cells_layout == CDL_CELLS_AUTO && d.M_total < 16384)) &&
-                           h->world == 1 && !rp && !element && !a.incremental && small_path_fits(d, K, gp.wise) &&
+                           h->world == 1 && !rp && !element && gp.incremental_stats != 1 && small_path_fits(d, K, gp.wise) &&
                            per_chain_bytes * gp.n_chain <= (double)gp.trace_budget_bytes;
-        if (small) { win = false; snaps.clear(); }
+        if (small) { win = false; snaps.clear(); a.incremental = 0; }
         const bool concurrent = concurrent_ok && !win;     // the windowed stop rule runs one chain at a time
         if (h->cells_layout == CDL_CELLS_SMALL && !small)
             throw Error(CDL_ERR_UNSUPPORTED, "the small-donor path does not apply (size, replay, sharding, element or incremental mode)");
@@ -988,9 +1032,11 @@ int cdl_gibbs_run(cdl_handle h, const double* Config, int32_t K, const double* P
                     for (int c = 0; c < gp.n_chain; ++c) {
                         if (!active[(size_t)c]) continue;
                         fr[(size_t)c] = geweke_fraction(h, *run[(size_t)c], end, gcounts);
-                        if (gp.verbose) std::printf("%g%% converged.\n", r_round3_percent(fr[(size_t)c]));
+                        notify(gp.chain_offset + c, end, fr[(size_t)c]);
                         if (fr[(size_t)c] > 0.995) { it_final[(size_t)c] = end; active[(size_t)c] = 0; --n_active; }
                     }
+                } else {
+                    notify(gp.chain_offset, end, NAN);
                 }
                 it = end + 1;
             }
@@ -1006,7 +1052,7 @@ int cdl_gibbs_run(cdl_handle h, const double* Config, int32_t K, const double* P
                 int64_t it_final = T;
                 double frac = NAN;
                 if (win && c > 0)       // every chain walks the same snapshot schedule
-                    for (auto& kv : snaps) { kv.second.s1.release(); kv.second.s2.release(); }
+                    for (auto& kv : snaps) kv.second.release();
                 size_t next_check = 0;
                 win_burn_s1 = nullptr;
                 for (int64_t it = 2; it <= T; ++it) {
@@ -1015,42 +1061,55 @@ int cdl_gibbs_run(cdl_handle h, const double* Config, int32_t K, const double* P
                     one_sweep(h, ch, a, (uint32_t)it, rp, n_el);
                     if (exact && it >= gp.min_iter && it % check_every == 0) {
                         frac = geweke_fraction(h, ch, it, gcounts);
-                        if (gp.verbose) std::printf("%g%% converged.\n", r_round3_percent(frac));
+                        notify(gp.chain_offset + c, it, frac);
                         if (frac > 0.995) { it_final = it; break; }
+                    } else if (it % check_every == 0 && !(win && it >= gp.min_iter)) {
+                        notify(gp.chain_offset + c, it, NAN);
                     }
                     if (!win) continue;
                     auto sn = snaps.find(it);
                     if (sn != snaps.end()) {           // the sums over rows 1..it, kept for a later window
                         const size_t nb = sizeof(double) * (size_t)(M * K);
-                        sn->second.s1.alloc((size_t)(M * K));
-                        CDL_CUDA(cudaMemcpyAsync(sn->second.s1.p, ch.prob_acc.p, nb, cudaMemcpyDeviceToDevice, h->st));
-                        if (sn->second.need_s2) {
-                            sn->second.s2.alloc((size_t)(M * K));
-                            CDL_CUDA(cudaMemcpyAsync(sn->second.s2.p, ch.prob_sq.p, nb, cudaMemcpyDeviceToDevice, h->st));
+                        if (snap32) {
+                            sn->second.f1.alloc((size_t)(M * K));
+                            launch_to_float(ch.prob_acc.p, sn->second.f1.p, M * K, h->st);
+                            if (sn->second.need_s2) {
+                                sn->second.f2.alloc((size_t)(M * K));
+                                launch_to_float(ch.prob_sq.p, sn->second.f2.p, M * K, h->st);
+                            }
+                        } else {
+                            sn->second.s1.alloc((size_t)(M * K));
+                            CDL_CUDA(cudaMemcpyAsync(sn->second.s1.p, ch.prob_acc.p, nb, cudaMemcpyDeviceToDevice, h->st));
+                            if (sn->second.need_s2) {
+                                sn->second.s2.alloc((size_t)(M * K));
+                                CDL_CUDA(cudaMemcpyAsync(sn->second.s2.p, ch.prob_sq.p, nb, cudaMemcpyDeviceToDevice, h->st));
+                            }
                         }
                     }
                     if (next_check < win_checks.size() && it == win_checks[next_check]) {
                         ++next_check;
-                        auto buf = [&](int64_t r, bool sq) -> const double* {
+                        auto buf = [&](int64_t r, bool sq) -> const void* {
                             if (r <= 1) return nullptr;
                             const Snap& q = snaps.at(r);
-                            return sq ? q.s2.p : q.s1.p;
+                            if (snap32) return sq ? (const void*)q.f2.p : (const void*)q.f1.p;
+                            return sq ? (const void*)q.s2.p : (const void*)q.s1.p;
                         };
                         launch_geweke_sums(buf(rowsA(it), false), buf(rowsA(it), true), buf(rowsB(it), false),
-                                           buf(rowsB(it), true), ch.prob_acc.p, ch.prob_sq.p, M * K, it, gcounts.p, h->st);
+                                           buf(rowsB(it), true), snap32, ch.prob_acc.p, ch.prob_sq.p, M * K, it, gcounts.p,
+                                           h->st);
                         if (h->world > 1) allreduce_u64(h, gcounts.p, 2);
                         unsigned long long cnt[2];
                         gcounts.download(cnt, 2, h->st);
                         frac = cnt[0] ? (double)cnt[1] / (double)cnt[0] : NAN;
                         const bool rule = it >= gp.min_iter && it % check_every == 0;     // (:580); else the final row
-                        if (rule && gp.verbose) std::printf("%g%% converged.\n", r_round3_percent(frac));
+                        if (rule) notify(gp.chain_offset + c, it, frac);
                         if ((rule && frac > 0.995) || it == T) {
                             it_final = it;
                             win_burn_s1 = buf(rowsU(it), false);
                             break;
                         }
                         for (auto& kv : snaps)         // snapshots no later check needs
-                            if (kv.second.last_use <= it) { kv.second.s1.release(); kv.second.s2.release(); }
+                            if (kv.second.last_use <= it) kv.second.release();
                     }
                 }
                 finish_chain(ch, a, it_final, frac);
@@ -1088,9 +1147,11 @@ int cdl_gibbs_run(cdl_handle h, const double* Config, int32_t K, const double* P
                             if (!lv.active) continue;
                             h->st = lv.st;
                             lv.frac = geweke_fraction(h, *lv.ch, it, gcounts);
-                            if (gp.verbose) std::printf("%g%% converged.\n", r_round3_percent(lv.frac));
+                            notify((int)lv.a.chain, it, lv.frac);
                             if (lv.frac > 0.995) { lv.it_final = it; lv.active = false; --n_active; }
                         }
+                    } else if (it % check_every == 0) {
+                        notify(gp.chain_offset, it, NAN);
                     }
                 }
                 for (Live& lv : live) {
@@ -1133,6 +1194,30 @@ int cdl_incremental_full_passes(cdl_handle h, int32_t chain, uint32_t* out) {
         unsigned int ctl[4] = {0, 0, 0, 0};
         ch.chg_ctl.download(ctl, 4, h->st);
         *out = ctl[3];
+    });
+}
+
+int cdl_debug_capture(cdl_handle h, int32_t enable) {
+    return guard(h, [&] { h->debug_capture = enable != 0; });
+}
+
+int cdl_debug_fetch(cdl_handle h, uint64_t* SA, uint64_t* SB, uint64_t* S3, uint64_t* S4, uint64_t* totals5) {
+    return guard(h, [&] {
+        Chain& ch = get_chain(h, 0);
+        if (!ch.dbg_sab.p) throw Error(CDL_ERR_STATE, "cdl_debug_capture was not enabled before the run");
+        const int64_t N = h->donor.N, K = h->K;
+        std::vector<unsigned long long> t((size_t)(N * K)), s((size_t)(2 * N + 5));
+        ch.dbg_sab.download(t.data(), t.size(), h->st);
+        ch.dbg_s34.download(s.data(), s.size(), h->st);
+        for (int64_t q = 0; q < N * K; ++q) {
+            if (SA) SA[q] = (uint64_t)(uint32_t)t[(size_t)q];
+            if (SB) SB[q] = (uint64_t)(t[(size_t)q] >> 32);
+        }
+        for (int64_t i = 0; i < N; ++i) {
+            if (S3) S3[i] = s[(size_t)i];
+            if (S4) S4[i] = s[(size_t)(N + i)];
+        }
+        if (totals5) for (int q = 0; q < 5; ++q) totals5[q] = s[(size_t)(2 * N + q)];
     });
 }
 

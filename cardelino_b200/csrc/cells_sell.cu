@@ -20,6 +20,10 @@
 #include <cub/cub.cuh>
 #include <cstdlib>
 
+#ifndef CDL_SELL_MAGIC
+#define CDL_SELL_MAGIC 0
+#endif
+
 namespace cdl {
 
 namespace {
@@ -40,6 +44,7 @@ struct SellParams {
     // small shards: a slice's groups are split over `parts` warps (work item = slice * parts + part); each
     // part leaves its partial logits in `scratch`, the part that finishes last (ticket) adds them up in part
     // order -- deterministic -- and runs the epilogue
+    int hi_shift;                // the odd entries of a group store their variant id << hi_shift (Donor::s_hi_shift)
     int parts;
     double* scratch;             // [n_slices][parts][32][KP]
     unsigned int* tickets;       // [n_slices], zero between launches
@@ -62,9 +67,88 @@ __device__ __forceinline__ void masked_add8(double (&acc)[KP], double del, uint3
     }
 }
 
+// ---- the fast path: weight table in shared memory, K <= 16, uint16 variant ids (every BASELINE shape) ----
+// The inner loop is bound by instruction issue and the fp64 pipe together (15-16 predicated DADDs + DMUL + DFMA per
+// covered entry), so everything else per entry is cut to the bone (profiles/r2_sass_k_cells_sell_inner_loop.txt):
+//   * the odd entries of a group store their variant id PRE-SHIFTED by two (Donor::s_hi_shift): the table address of
+//     the high half is ONE LEA.HI (base + (w >> 14)); the low half costs PRMT + LEA.HI;
+//   * counts are converted straight from the register halves (I2F.F64.U16 .H0 / .H1);
+//   * the Config bits ride in the weights' low mantissa bytes in R2P order: clones 1-7 (0-6 without the base-clone
+//     shortcut) in bits 0-6 of du's byte, the next seven in bits 0-6 of dv's byte, the one or two left over in
+//     bit 7 of each -- two R2P + one LOP3 per entry, no shifts;
+//   * two groups per loop trip with ping-pong registers: no register rotation, 32-bit loop arithmetic.
+template <int KP, bool SKIP0>
+__host__ __device__ constexpr int sell_bitpos(int k) {
+    const int a = k - (SKIP0 ? 1 : 0);          // rank among the clones that get a masked add
+    return a < 0 ? 31 : (a < 7 ? a : (a < 14 ? 8 + (a - 7) : (a == 14 ? 7 : 15)));
+}
+// Config row (clone bit mask) -> the two mask bytes in sell_bitpos order
+template <int KP, bool SKIP0>
+__device__ __forceinline__ uint32_t sell_pack_mask(uint32_t m) {
+    uint32_t o = 0;
+#pragma unroll
+    for (int k = SKIP0 ? 1 : 0; k < KP; ++k) o |= ((m >> k) & 1u) << sell_bitpos<KP, SKIP0>(k);
+    return o;
+}
+__device__ __forceinline__ double u16lo_to_double(uint32_t w) {
+    double r;
+    asm("{\n\t.reg .b16 l, h;\n\tmov.b32 {l, h}, %1;\n\tcvt.rn.f64.u16 %0, l;\n\t}" : "=d"(r) : "r"(w));
+    return r;
+}
+__device__ __forceinline__ double u16hi_to_double(uint32_t w) {
+    double r;
+    asm("{\n\t.reg .b16 l, h;\n\tmov.b32 {l, h}, %1;\n\tcvt.rn.f64.u16 %0, h;\n\t}" : "=d"(r) : "r"(w));
+    return r;
+}
+template <int KP, bool SKIP0>
+__device__ __forceinline__ void sell_group_fast(double (&acc)[KP], const Grp<uint16_t>& q, uint32_t tab_sa) {
+#pragma unroll
+    for (int e = 0; e < 8; ++e) {
+        const uint32_t vw = e < 2 ? q.v.x : (e < 4 ? q.v.y : (e < 6 ? q.v.z : q.v.w));
+        const uint32_t aw = e < 2 ? q.a.x : (e < 4 ? q.a.y : (e < 6 ? q.a.z : q.a.w));
+        const uint32_t bw = e < 2 ? q.b.x : (e < 4 ? q.b.y : (e < 6 ? q.b.z : q.b.w));
+        // byte offset of the variant's double2: high half holds 4 * id (bits 14-15 of the low half are zero, ids
+        // are below 2^14), low half the plain id moved to the top of a word first
+        const uint32_t off = (e & 1) ? (vw >> 14) : (__byte_perm(vw, 0u, 0x1044) >> 12);
+        double du, dv;
+        asm volatile("ld.shared.v2.f64 {%0, %1}, [%2];" : "=d"(du), "=d"(dv) : "r"(tab_sa + off));
+#if CDL_SELL_MAGIC
+        // counts -> double without I2F.F64 (which shares the fp64 pipe): 2^52 + a is the register pair (a, 0x43300000),
+        // and fma(2^52 + a, du, -2^52 du) is a * du correctly rounded (the product and the sum are exact inside the
+        // fma); -2^52 du is du with 52 added to the exponent field and the sign flipped: one integer add
+        const double da = __hiloint2double(0x43300000, (int)((e & 1) ? (aw >> 16) : (aw & 0xffffu)));
+        const double db = __hiloint2double(0x43300000, (int)((e & 1) ? (bw >> 16) : (bw & 0xffffu)));
+        const double c1 = __hiloint2double(__double2hiint(du) + (int)0x83400000, __double2loint(du));
+        const double c2 = __hiloint2double(__double2hiint(dv) + (int)0x83400000, __double2loint(dv));
+        const double del = fma(da, du, c1) + fma(db, dv, c2);
+#else
+        const double da = (e & 1) ? u16hi_to_double(aw) : u16lo_to_double(aw);
+        const double db = (e & 1) ? u16hi_to_double(bw) : u16lo_to_double(bw);
+        const double del = fma(da, du, db * dv);
+#endif
+        // both mask bytes in ONE integer register: ptxas then produces the predicates with R2P (seven per
+        // instruction); testing the low words of du / dv in place makes it emit one LOP3 per clone instead
+        const uint32_t m = __byte_perm((uint32_t)__double2loint(du), (uint32_t)__double2loint(dv), 0x7740);
+#pragma unroll
+        for (int k = SKIP0 ? 1 : 0; k < KP; ++k) {
+            asm volatile("{\n\t.reg .pred p;\n\t.reg .b32 t;\n\t"
+                         "and.b32 t, %2, %3;\n\tsetp.eq.u32 p, t, 0;\n\t@p bra SKIP%=;\n\t"
+                         "add.f64 %0, %0, %1;\n\tSKIP%=:\n\t}"
+                         : "+d"(acc[k])
+                         : "d"(del), "r"(m), "r"(1u << sell_bitpos<KP, SKIP0>(k)));
+        }
+    }
+}
+
+template <int KP, typename VIdx, bool SKIP0>
+__device__ __forceinline__ void sell_group_fast_any(double (&acc)[KP], const Grp<VIdx>& q, uint32_t tab_sa) {
+    if constexpr (sizeof(VIdx) == 2) sell_group_fast<KP, SKIP0>(acc, q, tab_sa);
+}
+
 template <int KP, typename VIdx, bool SMEM, bool PACKED, bool SKIP0>
 __device__ __forceinline__ void sell_group(double (&acc)[KP], const Grp<VIdx>& q, uint32_t tab_sa, uint32_t msk_sa,
-                                           const double2* __restrict__ tab_g, const uint32_t* __restrict__ msk_g) {
+                                           const double2* __restrict__ tab_g, const uint32_t* __restrict__ msk_g,
+                                           int hi_shift) {
 #pragma unroll
     for (int e = 0; e < 8; ++e) {
         const uint32_t aw = e < 2 ? q.a.x : (e < 4 ? q.a.y : (e < 6 ? q.a.z : q.a.w));
@@ -73,7 +157,7 @@ __device__ __forceinline__ void sell_group(double (&acc)[KP], const Grp<VIdx>& q
         const uint32_t b = (e & 1) ? (bw >> 16) : (bw & 0xffffu);
         double du, dv;
         if (PACKED) {
-            const uint32_t i = q.idx(e);
+            const uint32_t i = (e & 1) ? (q.idx(e) >> hi_shift) : q.idx(e);
             if (SMEM) {
                 asm volatile("ld.shared.v2.f64 {%0, %1}, [%2];" : "=d"(du), "=d"(dv) : "r"(tab_sa + (i << 4)));
             } else {
@@ -95,7 +179,7 @@ __device__ __forceinline__ void sell_group(double (&acc)[KP], const Grp<VIdx>& q
             if (KP > 8) masked_add8<8, KP - 8, KP>(acc, del, m >> 8);
         } else {
             uint32_t m;
-            load_tab<SMEM>(tab_sa, msk_sa, tab_g, msk_g, q.idx(e), du, dv, m);
+            load_tab<SMEM>(tab_sa, msk_sa, tab_g, msk_g, (e & 1) ? (q.idx(e) >> hi_shift) : q.idx(e), du, dv, m);
             const double del = fma(u16_to_double(a), du, u16_to_double(b) * dv);
             masked_add8<0, 8, KP>(acc, del, m);
             masked_add8<8, 8, KP>(acc, del, m >> 8);
@@ -110,6 +194,7 @@ __device__ __forceinline__ void sell_group(double (&acc)[KP], const Grp<VIdx>& q
 template <int KP, typename VIdx, bool SMEM, int SELL_THREADS, int SELL_DEPTH, bool SPLIT, bool SKIP0>
 __global__ void __launch_bounds__(SELL_THREADS, 1) k_cells_sell(const SellParams P) {
     constexpr bool PACKED = KP <= 16;
+    constexpr bool FAST = SMEM && PACKED && sizeof(VIdx) == 2;     // see sell_group_fast
     extern __shared__ __align__(16) unsigned char smem_raw[];
     pdl_trigger();
     const CellsParams& C = P.c;
@@ -157,7 +242,8 @@ __global__ void __launch_bounds__(SELL_THREADS, 1) k_cells_sell(const SellParams
         for (int64_t i = threadIdx.x; i < C.N; i += blockDim.x) {
             const int64_t t = C.n_tab == 1 ? 0 : i;
             double du = C.l1[t] - l0, dv = C.l1c[t] - l0c;
-            const uint32_t m = C.mask[i];
+            uint32_t m = C.mask[i];
+            if (FAST) m = sell_pack_mask<KP, SKIP0>(m);
             if (PACKED) {
                 du = __hiloint2double(__double2hiint(du), (__double2loint(du) & ~0xff) | (int)(m & 0xffu));
                 dv = __hiloint2double(__double2hiint(dv), (__double2loint(dv) & ~0xff) | (int)((m >> 8) & 0xffu));
@@ -185,6 +271,18 @@ __global__ void __launch_bounds__(SELL_THREADS, 1) k_cells_sell(const SellParams
         double acc[KP];
 #pragma unroll
         for (int q_ = 0; q_ < KP; ++q_) acc[q_] = 0.0;
+        if (FAST && SELL_DEPTH == 1) {
+            // two groups per trip, ping-pong between q[0] and n: the loads of a group are issued one group ahead
+            // (look-ahead index clamped to the slice's last slot, so they need no predicate)
+            const uint32_t ge = (uint32_t)g1, gl = (uint32_t)g1 - 1u;
+            for (uint32_t g = (uint32_t)g0; g < ge; g += 2) {
+                Grp<VIdx> n;
+                n.load(C.vidx, P.a8, P.b8, (int64_t)(min(g + 1u, gl) * 32u + (uint32_t)lane));
+                sell_group_fast_any<KP, VIdx, SKIP0>(acc, q[0], tab_sa);
+                q[0].load(C.vidx, P.a8, P.b8, (int64_t)(min(g + 2u, gl) * 32u + (uint32_t)lane));
+                if (g + 1u < ge) sell_group_fast_any<KP, VIdx, SKIP0>(acc, n, tab_sa);
+            }
+        } else {
         for (int64_t g = g0; g < g1; g += SELL_DEPTH) {
             Grp<VIdx> n[SELL_DEPTH];
 #pragma unroll
@@ -192,9 +290,13 @@ __global__ void __launch_bounds__(SELL_THREADS, 1) k_cells_sell(const SellParams
                 n[h].load(C.vidx, P.a8, P.b8, min(g + SELL_DEPTH + h, g1 - 1) * 32 + lane);
 #pragma unroll
             for (int h = 0; h < SELL_DEPTH; ++h)
-                if (h == 0 || g + h < g1) sell_group<KP, VIdx, SMEM, PACKED, SKIP0>(acc, q[h], tab_sa, msk_sa, tab_g, msk_g);
+                if (h == 0 || g + h < g1) {
+                    if (FAST) sell_group_fast_any<KP, VIdx, SKIP0>(acc, q[h], tab_sa);
+                    else sell_group<KP, VIdx, SMEM, PACKED, SKIP0>(acc, q[h], tab_sa, msk_sa, tab_g, msk_g, P.hi_shift);
+                }
 #pragma unroll
             for (int h = 0; h < SELL_DEPTH; ++h) q[h] = n[h];
+        }
         }
         if (SPLIT && parts > 1) {
             double* mine = P.scratch + (((size_t)s * parts + part) * 32 + lane) * KP;
@@ -350,7 +452,7 @@ __global__ void k_sell_fill(const uint32_t* __restrict__ rowgrp, const uint32_t*
                             const uint32_t* __restrict__ slice_off, int64_t n_slices, int64_t N,
                             const VIdx* __restrict__ cv, const uint16_t* __restrict__ ca,
                             const uint16_t* __restrict__ cb, VIdx* __restrict__ ov, uint16_t* __restrict__ oa,
-                            uint16_t* __restrict__ ob) {
+                            uint16_t* __restrict__ ob, int hi_shift) {
     const int64_t slot = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
     if (slot >= n_slices * 32) return;
     const int64_t s = slot >> 5;
@@ -372,7 +474,7 @@ __global__ void k_sell_fill(const uint32_t* __restrict__ rowgrp, const uint32_t*
         const int e = (int)((v - (uint32_t)lane) & 7u);
         if (cursor[e] < ngs) {
             const int64_t o = out_index(cursor[e]++, e);
-            ov[o] = (VIdx)v; oa[o] = (uint16_t)a; ob[o] = (uint16_t)b;
+            ov[o] = (VIdx)(v << ((e & 1) ? hi_shift : 0)); oa[o] = (uint16_t)a; ob[o] = (uint16_t)b;
         }
     }
     // pass 2: the overflow of over-full classes goes to the free slots of the others
@@ -389,7 +491,7 @@ __global__ void k_sell_fill(const uint32_t* __restrict__ rowgrp, const uint32_t*
         while (fe < GROUP && fill[fe] >= ngs) ++fe;
         if (fe >= GROUP) break;                            // cannot happen: the row has <= 8 * ngs entries
         const int64_t o = out_index(fill[fe]++, fe);
-        ov[o] = (VIdx)v; oa[o] = (uint16_t)a; ob[o] = (uint16_t)b;
+        ov[o] = (VIdx)(v << ((fe & 1) ? hi_shift : 0)); oa[o] = (uint16_t)a; ob[o] = (uint16_t)b;
     }
     // padding: zero counts, a variant id of the slot's class so that it gathers conflict-free too
     for (int e = 0; e < GROUP; ++e) {
@@ -397,7 +499,7 @@ __global__ void k_sell_fill(const uint32_t* __restrict__ rowgrp, const uint32_t*
         const uint32_t vpad = (int64_t)want < N ? want : 0u;
         for (int g = fill[e]; g < ngs; ++g) {
             const int64_t o = out_index(g, e);
-            ov[o] = (VIdx)vpad; oa[o] = 0; ob[o] = 0;
+            ov[o] = (VIdx)(vpad << ((e & 1) ? hi_shift : 0)); oa[o] = 0; ob[o] = 0;
         }
     }
 }
@@ -486,16 +588,20 @@ void donor_build_sell(Donor& d, cudaStream_t st) {
         CDL_CUDA(cudaStreamSynchronize(st));
         const size_t words = (size_t)std::max<int64_t>((int64_t)total * 32, 1);
         const int vw = d.vidx32 ? 2 : 1;
+        // variant ids below 2^14 (every donor whose weight table fits shared memory): the odd entries of a group are
+        // stored pre-shifted by two, which makes their table address a single instruction (sell_group_fast)
+        d.s_hi_shift = (!d.vidx32 && d.N <= 13824) ? 2 : 0;
+        if ((uint64_t)words >= (1ull << 32)) throw Error(5, "slice layout: more than 2^32 group slots");
         CDL_CUDA(cudaMalloc(&d.s_vidx, 16 * words * vw));
         CDL_CUDA(cudaMalloc(&d.s_a, 16 * words));
         CDL_CUDA(cudaMalloc(&d.s_b, 16 * words));
         const unsigned blocks = (unsigned)((n_slices * 32 + threads - 1) / threads);
         if (d.vidx32)
             k_sell_fill<uint32_t><<<blocks, threads, 0, st>>>(d.c_rowgrp, d.s_perm, d.s_off, n_slices, d.N,
-                (const uint32_t*)d.c_vidx, d.c_a, d.c_b, (uint32_t*)d.s_vidx, d.s_a, d.s_b);
+                (const uint32_t*)d.c_vidx, d.c_a, d.c_b, (uint32_t*)d.s_vidx, d.s_a, d.s_b, 0);
         else
             k_sell_fill<uint16_t><<<blocks, threads, 0, st>>>(d.c_rowgrp, d.s_perm, d.s_off, n_slices, d.N,
-                (const uint16_t*)d.c_vidx, d.c_a, d.c_b, (uint16_t*)d.s_vidx, d.s_a, d.s_b);
+                (const uint16_t*)d.c_vidx, d.c_a, d.c_b, (uint16_t*)d.s_vidx, d.s_a, d.s_b, d.s_hi_shift);
         CDL_CUDA(cudaGetLastError());
         CDL_CUDA(cudaStreamSynchronize(st));
         d.s_slices = n_slices;
@@ -528,6 +634,7 @@ void launch_cells_sell(const Donor& d, const SweepArgs& a, ChainDev& c, int sm_c
     P.slice_off = d.s_off; P.perm = d.s_perm;
     P.v8 = nullptr; P.a8 = (const uint4*)d.s_a; P.b8 = (const uint4*)d.s_b;
     P.n_slices = d.s_slices;
+    P.hi_shift = d.s_hi_shift;
     P.work = c.work;
     // too few slices to give every SM a CTA's worth of warps: split each slice's groups over 2 or 4 warps
     {

@@ -570,7 +570,11 @@ struct TableParams {
     const unsigned long long* sab;
     unsigned long long* sab_next;   // table the NEXT sweep's k_stats accumulates into: cleared here, element by
                                     // element, once this sweep's value has been read (saves a memset per sweep);
-                                    // nullptr with incremental statistics, which carry the table over
+                                    // nullptr with incremental statistics on one GPU, which carry the table over in place
+    int carry_local;                // incremental statistics over peer memory: sab_next (the other half of the arena)
+                                    // receives THIS rank's table instead of zeros, for the next sweep to correct
+    unsigned long long* dbg_s34;    // test hook: [2N] the integers added to the theta1 priors (S3_i, S4_i), else nullptr
+    unsigned long long* dbg_tot;    // test hook: [5] S1, S2, S3, S4, diff1 totals
     unsigned int* sell_work;        // k_cells_sell's work counter, re-armed by the last block
     unsigned int* stats_work;       // k_stats_units' per-cell-block unit counters [n_cb], re-armed likewise
     int n_cb;
@@ -672,6 +676,7 @@ __global__ void __launch_bounds__(TABLE_THREADS) k_table(const TableParams P) {
         const double du = l1 - l0, dv = l1c - l0c;
         const uint32_t c0 = P.cfg0[i];
         unsigned long long pk = P.sab[i * P.K + k];
+        const unsigned long long pk_local = pk;
         if (P.n_peer > 0) {
             // all peers' loads in flight together: one NVLink round trip, not one per peer
             unsigned long long pv[MAX_PEERS];
@@ -680,7 +685,7 @@ __global__ void __launch_bounds__(TABLE_THREADS) k_table(const TableParams P) {
 #pragma unroll
             for (int q = 0; q < MAX_PEERS; ++q) pk += pv[q];
         }
-        if (P.sab_next) P.sab_next[i * P.K + k] = 0ull;
+        if (P.sab_next) P.sab_next[i * P.K + k] = P.carry_local ? pk_local : 0ull;
         const double SA = (double)(uint32_t)pk, SB = (double)(uint32_t)(pk >> 32);
         const double sd = element ? P.sd1[i * P.K + k] : 0.0;       // per-entry theta1: the theta1 part, summed
         const uint32_t cbit = (c0 >> k) & 1u;
@@ -751,7 +756,10 @@ __global__ void __launch_bounds__(TABLE_THREADS) k_table(const TableParams P) {
             tl += ((const volatile double*)P.part_d)[b];
         }
         table_block_sums(t1, t2, t3, t4, td, tl, sm_u, sm_d);
-        if (threadIdx.x < 5) s_tot[threadIdx.x] = sm_u[threadIdx.x * 32];
+        if (threadIdx.x < 5) {
+            s_tot[threadIdx.x] = sm_u[threadIdx.x * 32];
+            if (P.dbg_tot) P.dbg_tot[threadIdx.x] = sm_u[threadIdx.x * 32];
+        }
         if (threadIdx.x == 5) P.loglik_all[(int64_t)P.it - 1] = sm_d[0] + P.W_log;
         if (threadIdx.x == 0) {
             *P.ticket = 0;
@@ -772,6 +780,7 @@ __global__ void __launch_bounds__(TABLE_THREADS) k_table(const TableParams P) {
                 const double pa = P.prior1_mat ? P.prior1_mat[iv] : P.prior1[0];
                 const double pb = P.prior1_mat ? P.prior1_mat[P.n_el + iv] : P.prior1[1];
                 shape = (j & 1) ? pb + (double)s_s4[j >> 1] : pa + (double)s_s3[j >> 1];
+                if (P.dbg_s34) P.dbg_s34[(j & 1) ? P.N + iv : iv] = (j & 1) ? s_s4[j >> 1] : s_s3[j >> 1];
                 stream = STREAM_THETA1; idx = (uint32_t)iv;
             }
         } else if (last && j < NJOB) {
@@ -1158,6 +1167,8 @@ void launch_table(const Donor& d, const SweepArgs& a, ChainDev& c, cudaStream_t 
     P.sell_work = c.work;
     P.stats_work = c.stats_work; P.n_cb = (int)d.n_cb;
     P.sab_next = (a.incremental || a.wise == 2) ? nullptr : c.sab;
+    P.carry_local = 0;
+    P.dbg_s34 = c.dbg_s34; P.dbg_tot = c.dbg_s34 ? c.dbg_s34 + 2 * d.N : nullptr;
     P.n_peer = 0;
     if (a.p2p && a.p2p->n_peer > 0) {
         const P2PState& q = *a.p2p;
@@ -1167,6 +1178,7 @@ void launch_table(const Donor& d, const SweepArgs& a, ChainDev& c, cudaStream_t 
             P.peer_rank[r] = q.peer_rank[r];
         }
         P.sab_next = q.arena + (size_t)((q.epoch + 1ull) & 1ull) * q.table_elems;   // not read by any peer any more
+        P.carry_local = a.incremental ? 1 : 0;
         P.my_flags = q.my_flags;
         P.epoch = q.epoch;
         P.p2p_error = q.error;

@@ -78,6 +78,7 @@ struct Donor {
     uint16_t* s_a = nullptr;
     uint16_t* s_b = nullptr;
     int64_t s_slices = 0, s_slots = 0;
+    int s_hi_shift = 0;                 // odd entries of a slice group store variant id << s_hi_shift (2 when N <= 13824)
     double W_log = 0.0;                 // local shard's sum(lchoose(D, A))
     int32_t* labels = nullptr;          // synthetic ground truth (1-based), optional
     uint64_t max_variant_depth = 0;     // max_i sum_j D_ij (must stay < 2^32 for packed statistics)
@@ -128,6 +129,8 @@ struct ChainDev {
     uint32_t* chg_list;          // [M] local cell ids
     uint8_t* chg_old;            // [M] their previous labels
     unsigned int* chg_ctl;       // [4]: changed count, need-full-pass flag, force-full flag, full passes done
+    unsigned long long* dbg_s34;  // test hook (cdl_debug_capture): [2N + 5] Beta shape increments of the last sweep, or nullptr
+    unsigned long long* dbg_sab;  // test hook: [N*K] copy of the local statistic table taken before the table kernel, or nullptr
     unsigned int* work;  // dynamic work-item counter of k_cells_sell
     unsigned int* stats_work;    // [n_cb] dynamic unit counters of k_stats
 };
@@ -207,9 +210,14 @@ void launch_el_theta(const Donor& d, const SweepArgs& a, ChainDev& c, cudaStream
 // post-processing
 void launch_geweke(const double* prob_all, int64_t cols, int64_t n_rows, unsigned long long* counts2,
                    cudaStream_t st);  // counts2[0] = #non-NaN, counts2[1] = #|Z|<=2
-void launch_geweke_sums(const double* s1a, const double* s2a, const double* s1b, const double* s2b, const double* s1n,
+// window snapshots (s1a .. s2b) are fp32 or fp64 arrays, the running sums s1n / s2n always fp64
+void launch_geweke_sums(const void* s1a, const void* s2a, const void* s1b, const void* s2b, bool fp32, const double* s1n,
                         const double* s2n, int64_t cols, int64_t n_rows, unsigned long long* counts2, cudaStream_t st);
-void launch_window_mean(const double* s1n, const double* s1u, int64_t n, double inv, double* out, cudaStream_t st);
+void launch_window_mean(const double* s1n, const void* s1u, bool fp32, int64_t n, double inv, double* out, cudaStream_t st);
+void launch_to_float(const double* x, float* y, int64_t n, cudaStream_t st);
+// R/clone_id.R:624-644 on the device trace (prob_all [T][cell][clone], Config_all [T][i + k*N]); rows n_buin..it (1-based)
+void relabel_trace(double* prob_all, uint8_t* config_all, int64_t M, int64_t N, int K, int64_t n_buin, int64_t it,
+                   cudaStream_t st);
 void launch_col_means_d(const double* X, int64_t cols, int64_t r0, int64_t r1, double* out, cudaStream_t st);
 void launch_transpose_scale(const double* in, int64_t R, int64_t C, double scale, double* out, cudaStream_t st);
 void launch_scale(double* x, int64_t n, double s, cudaStream_t st);

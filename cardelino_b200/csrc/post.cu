@@ -62,12 +62,22 @@ __global__ void k_prob_variant(const uint32_t* __restrict__ rowgrp, const VIdx* 
             const uint32_t a = ca[e], b = cb[e];
             if (a + b == 0) continue;
             const int64_t i = vidx[e];
+            // sum_t dbinom(a, d, th1_t) / (sum_t dbinom(a, d, th1_t) + sum_t dbinom(a, d, th0_t)): choose(d, a) is common
+            // to every term and cancels; so does exp(mx), mx the largest exponent of either arm -- without it deep
+            // entries (mtDNA: a = 326 of d = 6213 has exponents near -1300) underflow to 0 / 0, where R's dbinom
+            // stays representable because it carries the binomial coefficient.
+            const int64_t t1i = wise == 2 ? elem0[j] + (e - e0) : (wise == 1 ? i : 0);
+            double mx = -INFINITY;
+            for (int64_t r = r0; r < r1; ++r) {
+                const double t1 = th1[r * n_el + t1i], t0 = th0[r];
+                mx = fmax(mx, fmax((double)a * log(t1) + (double)b * log(1.0 - t1),
+                                   (double)a * log(t0) + (double)b * log(1.0 - t0)));
+            }
             double p1 = 0.0, p0 = 0.0;
             for (int64_t r = r0; r < r1; ++r) {
-                const double t1 = th1[r * n_el + (wise == 2 ? elem0[j] + (e - e0) : (wise == 1 ? i : 0))];
-                const double t0 = th0[r];
-                p1 += exp((double)a * log(t1) + (double)b * log(1.0 - t1));
-                p0 += exp((double)a * log(t0) + (double)b * log(1.0 - t0));
+                const double t1 = th1[r * n_el + t1i], t0 = th0[r];
+                p1 += exp((double)a * log(t1) + (double)b * log(1.0 - t1) - mx);
+                p0 += exp((double)a * log(t0) + (double)b * log(1.0 - t0) - mx);
             }
             out[i + j * N] = p1 / (p1 + p0);
         }
@@ -260,8 +270,9 @@ __global__ void k_transpose_scale(const double* __restrict__ in, int64_t R, int6
 // rows before window B) and current at r = n.  A null snapshot stands for r <= 1 (row 1 of prob_all is all zero).
 // One-pass variances (clamped at 0) differ from the two-pass ones of k_geweke by rounding only, relative to the
 // column's mean square.
-__global__ void k_geweke_sums(const double* __restrict__ s1a, const double* __restrict__ s2a,
-                              const double* __restrict__ s1b, const double* __restrict__ s2b,
+template <typename S>
+__global__ void k_geweke_sums(const S* __restrict__ s1a, const S* __restrict__ s2a,
+                              const S* __restrict__ s1b, const S* __restrict__ s2b,
                               const double* __restrict__ s1n, const double* __restrict__ s2n, int64_t cols, int64_t n,
                               unsigned long long* counts) {
     const int64_t c = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
@@ -269,9 +280,12 @@ __global__ void k_geweke_sums(const double* __restrict__ s1a, const double* __re
     if (c < cols) {
         const double nA = floor(0.1 * (double)n);
         const double nB = (double)n - (ceil(0.5 * (double)n) - 1.0);
-        const double a1 = s1a ? s1a[c] : 0.0, a2 = s2a ? s2a[c] : 0.0;
-        const double b1 = s1n[c] - (s1b ? s1b[c] : 0.0), b2 = s2n[c] - (s2b ? s2b[c] : 0.0);
+        const double a1 = s1a ? (double)s1a[c] : 0.0, a2 = s2a ? (double)s2a[c] : 0.0;
+        const double b1 = s1n[c] - (s1b ? (double)s1b[c] : 0.0), b2 = s2n[c] - (s2b ? (double)s2b[c] : 0.0);
         const double mA = a1 / nA, mB = b1 / nB;
+        // One-pass variances.  Their cancellation error is ~1e-16 (fp64 snapshots) or ~6e-8 (fp32) of the column's
+        // mean square m^2 -- and never decides Z: window A contains trace row 1, which is all zero (the reference
+        // starts filling prob_all at row 2), so vA >= ~m^2 / nA for every column and dominates that error.
         const double vA = fmax(a2 - nA * mA * mA, 0.0) / (nA - 1.0);
         const double vB = fmax(b2 - nB * mB * mB, 0.0) / (nA - 1.0);     // nrow(A) - 1, as the reference has it
         const double Z = (mA - mB) / sqrt(vA + vB + 1e-50);
@@ -285,11 +299,17 @@ __global__ void k_geweke_sums(const double* __restrict__ s1a, const double* __re
     }
 }
 
+__global__ void k_to_float(const double* __restrict__ x, float* __restrict__ y, int64_t n) {
+    const int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+    if (i < n) y[i] = (float)x[i];
+}
+
 // out = (s1n - s1u) * inv: column means over the rows after snapshot u
-__global__ void k_window_mean(const double* __restrict__ s1n, const double* __restrict__ s1u, int64_t n, double inv,
+template <typename S>
+__global__ void k_window_mean(const double* __restrict__ s1n, const S* __restrict__ s1u, int64_t n, double inv,
                               double* __restrict__ out) {
     const int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
-    if (i < n) out[i] = (s1n[i] - (s1u ? s1u[i] : 0.0)) * inv;
+    if (i < n) out[i] = (s1n[i] - (s1u ? (double)s1u[i] : 0.0)) * inv;
 }
 
 __global__ void k_scale(double* __restrict__ x, int64_t n, double s) {
@@ -297,6 +317,138 @@ __global__ void k_scale(double* __restrict__ x, int64_t n, double s) {
     if (i < n) x[i] *= s;
 }
 
+
+// ---- relabel (R/clone_id.R:624-644) on the device ---------------------------------------------------------------
+// For every trace row ii from n_buin on, the clone columns of prob_all[ii] are matched to those of prob_all[ii - 1]
+// (already relabelled) by colMatch (R/assessment.R:87-121): minimum mean absolute difference over all K!
+// permutations for K <= 5, greedy above; the reference then COMPOSES the match into col_idx_use and permutes the
+// row with col_idx_use (not with the match itself) -- kept as written.  Rows depend on their predecessor, so the
+// rows are walked in order: cost matrix (one pass over the two rows), solve + compose (one thread), permute.
+constexpr int RELABEL_TILE = 64;
+__global__ void __launch_bounds__(256) k_relabel_cost(const double* __restrict__ A, const double* __restrict__ B,
+                                                      int64_t M, int K, double* __restrict__ partials) {
+    __shared__ double tA[RELABEL_TILE * KMAX], tB[RELABEL_TILE * KMAX];
+    const int KK = K * K;
+    double acc[4] = {0.0, 0.0, 0.0, 0.0};            // pairs p = tid + 256 q, q < 4 (K*K <= 1024)
+    for (int64_t c0 = (int64_t)blockIdx.x * RELABEL_TILE; c0 < M; c0 += (int64_t)gridDim.x * RELABEL_TILE) {
+        const int nc = (int)min((int64_t)RELABEL_TILE, M - c0);
+        __syncthreads();
+        for (int t = threadIdx.x; t < nc * K; t += blockDim.x) { tA[t] = A[c0 * K + t]; tB[t] = B[c0 * K + t]; }
+        __syncthreads();
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+            const int p = threadIdx.x + 256 * q;
+            if (p < KK) {
+                const int i = p / K, j = p - i * K;
+                double s = 0.0;
+                for (int c = 0; c < nc; ++c) s += fabs(tA[c * K + i] - tB[c * K + j]);
+                acc[q] += s;
+            }
+        }
+    }
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+        const int p = threadIdx.x + 256 * q;
+        if (p < KK) partials[(size_t)blockIdx.x * KK + p] = acc[q];
+    }
+}
+
+__global__ void __launch_bounds__(256) k_relabel_solve(const double* __restrict__ partials, int nblocks, int K, int64_t M,
+                                                       int* __restrict__ col_idx_use) {
+    __shared__ double cost[KMAX * KMAX];
+    const int KK = K * K;
+    for (int p = threadIdx.x; p < KK; p += blockDim.x) {
+        double s = 0.0;
+        for (int b = 0; b < nblocks; ++b) s += partials[(size_t)b * KK + p];     // blocks in order: fixed rounding
+        cost[p] = s / (double)M;                                                 // MAE_mat[i, j]
+    }
+    __syncthreads();
+    if (threadIdx.x != 0) return;
+    int idx[KMAX];
+    if (K <= 5) {
+        // all permutations in lexicographic order, first minimum (which.min)
+        int perm[5], best[5];
+        for (int k = 0; k < K; ++k) perm[k] = k;
+        double bv = INFINITY;
+        for (;;) {
+            double v = 0.0;
+            for (int i = 0; i < K; ++i) v += cost[i * K + perm[i]];
+            if (v < bv) { bv = v; for (int i = 0; i < K; ++i) best[i] = perm[i]; }
+            int i = K - 2;
+            while (i >= 0 && perm[i] > perm[i + 1]) --i;
+            if (i < 0) break;
+            int j = K - 1;
+            while (perm[j] < perm[i]) --j;
+            int t = perm[i]; perm[i] = perm[j]; perm[j] = t;
+            for (int l = i + 1, r = K - 1; l < r; ++l, --r) { t = perm[l]; perm[l] = perm[r]; perm[r] = t; }
+        }
+        for (int i = 0; i < K; ++i) idx[i] = best[i];
+    } else {
+        // greedy: repeatedly the smallest remaining entry (first in column-major order), then its row and column
+        // are struck out
+        double big = -INFINITY;
+        for (int p = 0; p < KK; ++p) big = fmax(big, cost[p]);
+        big += 1.0;
+        for (int i = 0; i < K; ++i) idx[i] = -1;
+        for (int step = 0; step < K; ++step) {
+            double mv = INFINITY; int mr = 0, mc = 0;
+            for (int c = 0; c < K; ++c)
+                for (int r = 0; r < K; ++r)
+                    if (cost[r * K + c] < mv) { mv = cost[r * K + c]; mr = r; mc = c; }
+            idx[mr] = mc;
+            for (int q = 0; q < K; ++q) { cost[mr * K + q] = big; cost[q * K + mc] = big; }
+        }
+    }
+    int nu[KMAX];
+    for (int i = 0; i < K; ++i) nu[i] = col_idx_use[idx[i]];                     // col_idx_use <- col_idx_use[idx]
+    for (int i = 0; i < K; ++i) col_idx_use[i] = nu[i];
+}
+
+__global__ void k_relabel_apply(double* __restrict__ prob_row, uint8_t* __restrict__ cfg_row, int64_t M, int64_t N, int K,
+                                const int* __restrict__ col_idx_use) {
+    const int64_t t = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+    if (t < M) {
+        double v[KMAX];
+        for (int k = 0; k < K; ++k) v[k] = prob_row[t * K + col_idx_use[k]];
+        for (int k = 0; k < K; ++k) prob_row[t * K + k] = v[k];
+    }
+    if (t < N) {
+        uint8_t v[KMAX];
+        for (int k = 0; k < K; ++k) v[k] = cfg_row[t + (int64_t)col_idx_use[k] * N];
+        for (int k = 0; k < K; ++k) cfg_row[t + (int64_t)k * N] = v[k];
+    }
+}
+
+}  // namespace
+
+void relabel_trace(double* prob_all, uint8_t* config_all, int64_t M, int64_t N, int K, int64_t n_buin, int64_t it,
+                   cudaStream_t st) {
+    if (n_buin < 2 || it < n_buin) return;       // row n_buin needs its predecessor
+    const int nblocks = (int)std::max<int64_t>(1, std::min<int64_t>((M + RELABEL_TILE - 1) / RELABEL_TILE, 296));
+    double* partials = nullptr;
+    int* use = nullptr;
+    CDL_CUDA(cudaMalloc(&partials, sizeof(double) * (size_t)nblocks * K * K));
+    cudaError_t e = cudaMalloc(&use, sizeof(int) * KMAX);
+    if (e != cudaSuccess) { cudaFree(partials); CDL_CUDA(e); }
+    int ident[KMAX];
+    for (int k = 0; k < KMAX; ++k) ident[k] = k;
+    cudaMemcpyAsync(use, ident, sizeof(ident), cudaMemcpyHostToDevice, st);
+    const int64_t mx = std::max(M, N);
+    for (int64_t ii = n_buin; ii <= it; ++ii) {
+        double* prev = prob_all + (ii - 2) * M * K;
+        double* cur = prob_all + (ii - 1) * M * K;
+        k_relabel_cost<<<nblocks, 256, 0, st>>>(prev, cur, M, K, partials);
+        k_relabel_solve<<<1, 256, 0, st>>>(partials, nblocks, K, M, use);
+        k_relabel_apply<<<(unsigned)((mx + 255) / 256), 256, 0, st>>>(cur, config_all + (ii - 1) * N * K, M, N, K, use);
+    }
+    e = cudaStreamSynchronize(st);
+    cudaFree(partials);
+    cudaFree(use);
+    CDL_CUDA(e);
+    CDL_CUDA(cudaGetLastError());
+}
+
+namespace {
 }  // namespace
 
 void launch_transpose_scale(const double* in, int64_t R, int64_t C, double scale, double* out, cudaStream_t st) {
@@ -326,16 +478,30 @@ void launch_geweke(const double* prob_all, int64_t cols, int64_t n_rows, unsigne
     CDL_CUDA(cudaGetLastError());
 }
 
-void launch_geweke_sums(const double* s1a, const double* s2a, const double* s1b, const double* s2b, const double* s1n,
+void launch_geweke_sums(const void* s1a, const void* s2a, const void* s1b, const void* s2b, bool fp32, const double* s1n,
                         const double* s2n, int64_t cols, int64_t n_rows, unsigned long long* counts2, cudaStream_t st) {
     CDL_CUDA(cudaMemsetAsync(counts2, 0, 2 * sizeof(unsigned long long), st));
-    k_geweke_sums<<<(unsigned)((cols + 255) / 256), 256, 0, st>>>(s1a, s2a, s1b, s2b, s1n, s2n, cols, n_rows, counts2);
+    const unsigned grid = (unsigned)((cols + 255) / 256);
+    if (fp32)
+        k_geweke_sums<float><<<grid, 256, 0, st>>>((const float*)s1a, (const float*)s2a, (const float*)s1b,
+                                                   (const float*)s2b, s1n, s2n, cols, n_rows, counts2);
+    else
+        k_geweke_sums<double><<<grid, 256, 0, st>>>((const double*)s1a, (const double*)s2a, (const double*)s1b,
+                                                    (const double*)s2b, s1n, s2n, cols, n_rows, counts2);
     CDL_CUDA(cudaGetLastError());
 }
 
-void launch_window_mean(const double* s1n, const double* s1u, int64_t n, double inv, double* out, cudaStream_t st) {
+void launch_to_float(const double* x, float* y, int64_t n, cudaStream_t st) {
     if (n <= 0) return;
-    k_window_mean<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(s1n, s1u, n, inv, out);
+    k_to_float<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(x, y, n);
+    CDL_CUDA(cudaGetLastError());
+}
+
+void launch_window_mean(const double* s1n, const void* s1u, bool fp32, int64_t n, double inv, double* out, cudaStream_t st) {
+    if (n <= 0) return;
+    const unsigned grid = (unsigned)((n + 255) / 256);
+    if (fp32) k_window_mean<float><<<grid, 256, 0, st>>>(s1n, (const float*)s1u, n, inv, out);
+    else k_window_mean<double><<<grid, 256, 0, st>>>(s1n, (const double*)s1u, n, inv, out);
     CDL_CUDA(cudaGetLastError());
 }
 

@@ -36,8 +36,15 @@ enum {
     CDL_ERR_NOMEM = 3,
     CDL_ERR_STATE = 4,       /* call order violated (e.g. fetch before run) */
     CDL_ERR_UNSUPPORTED = 5, /* documented limit (K > 32, counts > 65535, ...) */
-    CDL_ERR_COMM = 6         /* NCCL failure */
+    CDL_ERR_COMM = 6,        /* NCCL failure */
+    CDL_ERR_INTERRUPTED = 7  /* the progress callback asked to stop (R: user interrupt); no results are kept */
 };
+
+/* Progress callback of cdl_gibbs_run.  Called on the calling thread (never from a worker thread) for every chain
+ * every check_every sweeps; `fraction` is the converged fraction of the reference's Geweke check when one was made
+ * at this iteration (R/clone_id.R:580-592; the host prints "x% converged." from it like the reference's cat()),
+ * NaN otherwise.  A non-zero return value stops the run with CDL_ERR_INTERRUPTED.  The library prints nothing itself. */
+typedef int (*cdl_progress_fn)(void* user, int32_t chain, int32_t iteration, double fraction);
 
 enum { CDL_WISE_GLOBAL = 0, CDL_WISE_VARIANT = 1, CDL_WISE_ELEMENT = 2 };
 
@@ -68,9 +75,21 @@ typedef struct cdl_gibbs_params {
     int32_t acc_fp32;            /* reserved, must be 0 (fp64 accumulation) */
     int32_t chain_offset;        /* chains are numbered chain_offset .. chain_offset + n_chain - 1 in the Philox keys, so
                                     chain groups placed on different GPUs / processes draw independent streams */
-    int32_t incremental_stats;   /* 1: when at most ~3 % of the cells changed label in a sweep, correct the previous
+    int32_t incremental_stats;   /* when at most ~3 % of the cells changed label in a sweep, correct the previous
                                     sweep's SA/SB table from those cells instead of re-reading every count (exact:
-                                    integer sums, bit-identical chains); single GPU, wise = global / variant */
+                                    integer sums, bit-identical chains; falls back to the full pass sweep by sweep).
+                                    -1 (default): on wherever it applies (wise = global / variant; one GPU or the
+                                    peer-memory exchange; not replay, not the single-CTA small-donor path); 1: on,
+                                    which also takes small donors off the single-CTA path; 0: always the full pass */
+    int32_t relabel;             /* R/clone_id.R:624-644: match the clone columns of consecutive prob_all rows from
+                                    n_buin on (colMatch; all permutations for K <= 5, greedy above) and permute
+                                    prob_all / Config_all rows accordingly, on the device, before the summaries.
+                                    Needs the exact trace (keep_prob_all = 1, or -1 with a trace that fits). */
+    int64_t prior1_matrix_rows;  /* rows of prior1_matrix (checked against n_element; 0 = not given) */
+    cdl_progress_fn progress;    /* may be NULL */
+    void* progress_user;
+    int32_t snapshot_fp32;       /* streaming stop rule: keep the window snapshots as fp32 (default 1; half the memory,
+                                    Z changes by ~1e-6 relative) or fp64 (0) */
 } cdl_gibbs_params;
 
 /* Optional injected draws ("replay mode", north_star correctness check 2).  Any pointer may be NULL,
@@ -183,6 +202,15 @@ int cdl_fetch_assign_all(cdl_handle h, int32_t chain, int32_t* out /* n_iter x M
 int cdl_fetch_prob_variant(cdl_handle h, int32_t chain, double* out /* N x M dense, NaN-free (:606-622) */);
 /* indices (0-based, column-major i + j*N) of the covered entries, in theta1_all column order for wise=element */
 int cdl_fetch_element_index(cdl_handle h, int64_t* out /* nnz */);
+
+/* ---- test hooks (tests/ only) ----
+ * cdl_debug_capture(h, 1): every following sweep keeps a copy of this rank's SA/SB statistic table as it stands
+ * between the statistic kernel and the table kernel (before any exchange with other ranks), and the table kernel
+ * records the integers it adds to the Beta priors: S3[i], S4[i] per variant (R/clone_id.R:557-562) and the totals
+ * S1, S2, S3, S4, diff1 (:546-556,502).  cdl_debug_fetch returns those of the last sweep of chain 0. */
+int cdl_debug_capture(cdl_handle h, int32_t enable);
+int cdl_debug_fetch(cdl_handle h, uint64_t* SA /* N x K row-major [i*K+k] */, uint64_t* SB, uint64_t* S3 /* N */,
+                    uint64_t* S4 /* N */, uint64_t* totals5);
 
 /* ---- get_logLik (R/clone_id.R:734-752) ----
  * Config N x K doubles (may be fractional); exactly one of assign (1-based labels, M) / assign_prob
