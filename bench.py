@@ -50,6 +50,24 @@ def make_config(N, K, seed=SEED_DATA):
     return cfg
 
 
+def workload_string(name):
+    """config.workload: the same string in both arms (ours and --impl reference)."""
+    if name == "C5":
+        return ("C5: 64 independent chains on example_donor (34 variants x 428 cells x 4 clones), relax_Config=TRUE, "
+                "min_iter=2000, max_iter=5000, Geweke stop rule, chain merge; plus one clone_id(inference='EM') call")
+    N, M, K, cov = WORKLOADS[name]
+    return ("%s: %d variants x %d cells x %d clones, %.0f%% coverage, wise=variant, relax_Config=TRUE (learned rate), "
+            "1 chain" % (name, N, M, K, cov * 100))
+
+
+def sha16(*arrays):
+    import hashlib
+    hh = hashlib.sha256()
+    for a in arrays:
+        hh.update(np.ascontiguousarray(a).tobytes())
+    return hh.hexdigest()[:16]
+
+
 def peaks():
     p = os.path.join(ROOT, "MEASURED_PEAKS.json")
     if os.path.exists(p):
@@ -69,7 +87,7 @@ class ClockSampler:
     def start(self):
         try:
             self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.Q,
-                                          "--format=csv,noheader,nounits", "-lms", "100"],
+                                          "--format=csv,noheader,nounits", "-lms", "20"],
                                          stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
             self.t = threading.Thread(target=self._read, daemon=True)
             self.t.start()
@@ -148,8 +166,12 @@ def run_ours(args):
     h.synth_generate(N, M, K, cfg, cov, SEED_DATA, cell_offset=off, M_local=Ml)
     _, _, nnz_local, _ = h.data_info()
     T0 = 4
-    h.gibbs_run(cfg, None, min_iter=T0, max_iter=T0, seed=SEED_CHAIN, keep_prob_all=1, wise="variant",
-                relax_Config=1)
+
+    def prime(incremental):
+        """A short run that leaves a chain on the device for the bench hook: -1 = the library default (incremental
+        statistics wherever they apply), 0 = the full statistic pass every sweep."""
+        h.gibbs_run(cfg, None, min_iter=T0, max_iter=T0, seed=SEED_CHAIN, keep_prob_all=1, wise="variant",
+                    relax_Config=1, incremental_stats=incremental)
 
     def barrier():
         torch.cuda.synchronize()
@@ -157,49 +179,76 @@ def run_ours(args):
             dist.barrier()
             torch.cuda.synchronize()
 
+    def timed(incremental):
+        """W untimed warm-up sweeps and the K timed sweeps are enqueued by ONE library call: the CUDA events that
+        bracket the K sweeps are recorded on the library's stream right after the warm-up sweeps, whose per-sweep
+        exchange has already aligned the ranks -- otherwise the few milliseconds of host-side skew between the
+        ranks' Python processes would be charged to the first timed sweep.  barrier + synchronize on both sides,
+        max over ranks."""
+        prime(incremental)
+        full0 = h.incremental_full_passes()
+        barrier()
+        r = h.bench_sweeps(args.warmup, args.steps, breakdown=False)
+        barrier()
+        ms = torch.tensor([r["ms_total"]], dtype=torch.float64, device="cuda")
+        if world > 1:
+            dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+        nb = max(3, min(args.steps, 10))
+        bd = h.bench_sweeps(1, nb, breakdown=True)      # per-kernel durations (events around each kernel)
+        return {"ms_total": float(ms.item()), "launches": int(r["launches"]),
+                "full_passes": h.incremental_full_passes() - full0,
+                "cells_ms": bd["ms_cells"] / nb, "stats_ms": bd["ms_stats"] / nb, "table_ms": bd["ms_table"] / nb}
+
     sampler = ClockSampler(local) if rank == 0 else None
     if sampler:
         sampler.start()
-    barrier()
-    # W untimed warm-up sweeps and the K timed sweeps are enqueued by ONE library call: the CUDA events that
-    # bracket the K sweeps are recorded on the stream right after the warm-up sweeps, whose per-sweep exchange
-    # has already aligned the ranks -- otherwise the few milliseconds of host-side skew between the ranks'
-    # Python processes would be charged to the first timed sweep.  barrier + synchronize on both sides.
-    r = h.bench_sweeps(args.warmup, args.steps, breakdown=False)
-    barrier()
-    clocks = sampler.stop() if sampler else None
-    ms = torch.tensor([r["ms_total"]], dtype=torch.float64, device="cuda")
+    main = timed(-1)            # the library's default path: this is `value`
+    full = timed(0)             # every sweep re-reads all counts for the statistic table (round 1's `value`)
     nnz_t = torch.tensor([float(nnz_local)], dtype=torch.float64, device="cuda")
     if world > 1:
-        dist.all_reduce(ms, op=dist.ReduceOp.MAX)
         dist.all_reduce(nnz_t, op=dist.ReduceOp.SUM)
-    ms_total = float(ms.item())
     nnz = int(nnz_t.item())
-    # per-kernel durations (second pass; events around each kernel on the library's stream)
-    bd = h.bench_sweeps(1, max(3, min(args.steps, 10)), breakdown=True)
-    nb = max(3, min(args.steps, 10))
     cells_b, stats_b = algorithmic_bytes(nnz_local, Ml, K, N)
     peak, peak_src = peaks()
-    cells_ms = bd["ms_cells"] / nb
-    stats_ms = bd["ms_stats"] / nb
-    value = args.steps / (ms_total * 1e-3)
+    value = args.steps / (main["ms_total"] * 1e-3)
 
-    # ---- optional mode: incremental statistics (exact; reported beside, never instead of, `value`) ----
-    incr = None
-    if world == 1 and not args.no_incremental:
-        h.gibbs_run(cfg, None, min_iter=T0, max_iter=T0, seed=SEED_CHAIN, keep_prob_all=1, wise="variant",
-                    relax_Config=1, incremental_stats=1)
-        full0 = h.incremental_full_passes()
-        ri = h.bench_sweeps(args.warmup, args.steps, breakdown=False)
-        incr = {"value": args.steps / (ri["ms_total"] * 1e-3), "unit": "Gibbs iterations/s",
-                "ms_per_step": ri["ms_total"] / args.steps,
-                "full_statistic_passes": h.incremental_full_passes() - full0,
-                "of_sweeps": args.steps + args.warmup,
-                "note": "cdl_gibbs_params.incremental_stats = 1: SA/SB corrected from the cells whose label changed "
-                        "(integer sums, bit-identical chain) when they are <= ~3 % of the cells; on this synthetic "
-                        "donor every cell has ~500 covered variants, so labels are settled after the first sweeps"}
-        h.gibbs_run(cfg, None, min_iter=T0, max_iter=T0, seed=SEED_CHAIN, keep_prob_all=1, wise="variant",
-                    relax_Config=1)
+    # ---- parity: the sharded run against the unsharded donor on rank 0 (first sweeps, exact) ----
+    parity = None
+    if not args.no_parity:
+        def first_sweeps(hh, mloc):
+            hh.gibbs_run(cfg, None, min_iter=T0, max_iter=T0, seed=SEED_CHAIN, keep_prob_all=0, keep_assign_all=1,
+                         wise="variant", relax_Config=1)
+            z = hh.fetch("assign_all").astype(np.uint8)                  # T0 x M_local (row 1 is zeros)
+            t0_, t1_ = hh.fetch("theta_traces")
+            return z, hh.fetch("Config_all").astype(np.uint8), t0_, t1_, hh.fetch("logLik")
+        z, c_all, th0, th1, ll = first_sweeps(h, Ml)
+        if world > 1:
+            zt = torch.zeros((T0, bounds[1] - bounds[0] + 1), dtype=torch.uint8, device="cuda")
+            zt[:, :Ml] = torch.from_numpy(z).cuda()
+            parts = [torch.empty_like(zt) for _ in range(world)] if rank == 0 else None
+            dist.gather(zt, parts, dst=0)
+            if rank == 0:
+                z = np.concatenate([pp.cpu().numpy()[:, :bounds[r + 1] - bounds[r]] for r, pp in enumerate(parts)], axis=1)
+        if rank == 0:
+            parity = {"sweeps": T0 - 1, "labels_hash": sha16(z), "config_hash": sha16(c_all),
+                      "theta_hash": sha16(th0, th1), "loglik_hash": sha16(ll),
+                      "what": "sha256[:16] of assign_all (all %d cells in global order), Config_all and the theta0 / "
+                              "theta1 traces of the first %d sweeps of the bench chain" % (M, T0 - 1)}
+            if world > 1:
+                h2 = cb.Handle(local)                  # the WHOLE donor on rank 0's GPU, no communicator
+                h2.synth_generate(N, M, K, cfg, cov, SEED_DATA)
+                z2, c2, a0, a1, l2 = first_sweeps(h2, M)
+                h2.close()
+                ref = {"labels_hash": sha16(z2), "config_hash": sha16(c2), "theta_hash": sha16(a0, a1),
+                       "loglik_hash": sha16(l2)}
+                parity["unsharded"] = ref
+                parity["sharded_equals_unsharded"] = all(parity[k] == ref[k] for k in ref)
+                parity["label_mismatches"] = int((z != z2).sum())
+            else:
+                parity["sharded_equals_unsharded"] = True
+                parity["note"] = "one rank: the run IS the unsharded donor; compare the hashes across N in SCALE"
+        barrier()
+        prime(-1)
 
     # ---- end to end through the public API with host buffers (load + T sweeps + fetch) ----
     e2e = None
@@ -228,43 +277,58 @@ def run_ours(args):
         e2e = {"value": (T - 1) / float(dt.item()), "unit": "Gibbs iterations/s",
                "h2d_bytes_per_step": h2d / (T - 1), "d2h_bytes_per_step": d2h / (T - 1),
                "chain_iterations": T, "seconds": float(dt.item()),
-               "note": "one clone_id_Gibbs call on host uint16 CSC buffers: H2D + layout build + T sweeps + D2H; "
-                       "T = --e2e-iters (default: the reference's default min_iter)"}
+               "note": "one clone_id_Gibbs call on pinned host uint16 CSC buffers: H2D + layout build + T sweeps + D2H "
+                       "of prob / Config_prob / theta traces; T = --e2e-iters (default: the reference's default "
+                       "min_iter); library defaults (incremental statistics on)"}
+    clocks = sampler.stop() if sampler else None
+    if clocks is not None:
+        clocks["window"] = "timed sweeps (both modes), per-kernel passes, parity sweeps and the e2e call; 20 ms period"
 
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu:
-        cpu = cpu_sparse_port(args.workload, budget_s=20.0, counts=h.export_csc_u16())
-        cpu["dense_reference_shaped"] = cpu_dense_reference_shaped(args.workload, args.cpu_cells, args.cpu_iters)
+        cpu = cpu_baseline_leg(args.workload, h.export_csc_u16())
+        if not args.no_dense:
+            cpu["dense_reference_shaped"] = cpu_dense_reference_shaped(args.workload, args.cpu_cells, args.cpu_iters)
 
     if rank == 0:
+        kname = "k_cells_sell" if M >= 16384 else "k_cells"
+
+        def roof(ms_launch, nbytes, kernel, traffic_key):
+            return {"kernel": kernel, "achieved": nbytes / (ms_launch * 1e-3) / 1e9,
+                    "frac": nbytes / (ms_launch * 1e-3) / 1e9 / peak,
+                    "traffic": ncu_traffic(args.workload, traffic_key) if world == 1 else None,
+                    "algorithmic_bytes_per_launch": nbytes, "ms_per_launch": ms_launch}
+        r1 = roof(main["cells_ms"], cells_b, "%s (logLik + softmax + draw)" % kname, "k_cells_sell")
         out = {
             "metric": "Gibbs iterations/sec", "value": value, "unit": "Gibbs iterations/s", "n_gpus": world,
-            "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_total / args.steps,
+            "steps": args.steps, "warmup": args.warmup, "ms_per_step": main["ms_total"] / args.steps,
             "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f64",
             "data": "synthetic (device generator with sim_read_count's distributions)",
-            "config": {"workload": "%s: %d variants x %d cells x %d clones, %.0f%% coverage, nnz=%d, "
-                                   "wise=variant, relax_Config=TRUE (learned rate), 1 chain" %
-                                   (args.workload, N, M, K, cov * 100, nnz),
-                       "sharding": "cells over %d rank(s); per sweep the %d x %d statistic table is %s" %
-                                   (world, N, K, "not exchanged (1 rank)" if world == 1 else
-                                    ("summed over peer memory inside the table kernel (NVLink loads, no collective call)"
-                                     if h.exchange_is_peer() else "all-reduced with NCCL")),
-                       "l2": "inputs (%.1f GB per rank per pass) exceed the 126 MB L2" % (nnz_local * 6 / 1e9)},
+            "config": {"workload": workload_string(args.workload)},
+            "nnz": nnz,
+            "sharding": "cells over %d rank(s); per sweep the %d x %d statistic table is %s" %
+                        (world, N, K, "not exchanged (1 rank)" if world == 1 else
+                         ("summed over peer memory inside the table kernel (NVLink loads, no collective call)"
+                          if h.exchange_is_peer() else "all-reduced with NCCL")),
+            "l2": "inputs (%.1f GB per rank per pass) exceed the 126 MB L2" % (nnz_local * 6 / 1e9),
             "nnz_clone_updates_per_s": value * nnz * K,
-            "roofline": {"bound": "hbm", "kernel": "%s (logLik + softmax + draw)" % ("k_cells_sell" if M >= 16384 else "k_cells"),
-                         "achieved": cells_b / (cells_ms * 1e-3) / 1e9, "peak": peak, "unit": "GB/s",
-                         "frac": cells_b / (cells_ms * 1e-3) / 1e9 / peak,
-                         "traffic": ncu_traffic(args.workload, "k_cells_sell") if world == 1 else None,
-                         "peak_source": peak_src, "algorithmic_bytes_per_launch": cells_b,
-                         "ms_per_launch": cells_ms,
-                         "second_kernel": {"kernel": "k_stats (per-variant x clone read sums)",
-                                           "achieved": stats_b / (stats_ms * 1e-3) / 1e9,
-                                           "frac": stats_b / (stats_ms * 1e-3) / 1e9 / peak,
-                                           "traffic": ncu_traffic(args.workload, "k_stats") if world == 1 else None,
-                                           "algorithmic_bytes_per_launch": stats_b, "ms_per_launch": stats_ms},
-                         "table_kernel_ms": bd["ms_table"] / nb},
-            "cpu_baseline": cpu, "e2e": e2e, "incremental_stats_mode": incr, "clocks": clocks,
-            "gpu_launches": int(r["launches"]),
+            "statistics": {"mode": "incremental (library default): SA/SB corrected from the cells whose label changed "
+                                   "when they are <= ~3 % of the cells, else the full pass; exact either way",
+                           "full_statistic_passes": main["full_passes"],
+                           "of_sweeps": args.steps + args.warmup + 1 + max(3, min(args.steps, 10))},
+            "roofline": dict(r1, bound="hbm", peak=peak, unit="GB/s", peak_source=peak_src,
+                             whole_sweep_frac=cells_b / (main["ms_total"] / args.steps * 1e-3) / 1e9 / peak,
+                             statistics_ms=main["stats_ms"], table_kernel_ms=main["table_ms"]),
+            "full_pass_mode": {
+                "value": args.steps / (full["ms_total"] * 1e-3), "unit": "Gibbs iterations/s",
+                "ms_per_step": full["ms_total"] / args.steps,
+                "note": "incremental_stats = 0: every sweep reads the counts twice (cell pass + statistic pass); "
+                        "round 1's `value`",
+                "cells_kernel": roof(full["cells_ms"], cells_b, kname, "k_cells_sell"),
+                "statistic_kernel": roof(full["stats_ms"], stats_b, "k_stats (per-variant x clone read sums)", "k_stats"),
+                "table_kernel_ms": full["table_ms"]},
+            "parity": parity, "cpu_baseline": cpu, "e2e": e2e, "clocks": clocks,
+            "gpu_launches": main["launches"],
         }
         print(json.dumps(out))
     if world > 1:
@@ -274,9 +338,8 @@ def run_ours(args):
 
 def _cpu_dense_chain(job):
     """One reference-SHAPED chain (dense, op-for-op NumPy restatement of R/clone_id.R:466-593) on a cell sample;
-    returns seconds per iteration."""
+    returns seconds per iteration (the first sweep, which pays the allocations, is not timed)."""
     workload, cells, iters, seed = job
-    os.environ.setdefault("OMP_NUM_THREADS", "1")
     from oracle import cardelino_oracle as O
     N, M, K, cov = WORKLOADS[workload]
     rng = np.random.default_rng(seed)
@@ -288,31 +351,38 @@ def _cpu_dense_chain(job):
     H = cfg[:, lab]
     p = np.where(H > 0, th1[:, None], 0.002)
     A = np.where(covered, rng.binomial(np.nan_to_num(D).astype(int), p), np.nan)
-    T = iters + 2
-    t0 = time.perf_counter()
-    O.clone_id_Gibbs(A, D, cfg, min_iter=T, max_iter=T, draws=O.NumpyDraws(seed))
-    dt = time.perf_counter() - t0
-    return dt / (T - 1)
+    times = []
+    for T in (2, iters + 2):          # rows 1..T: T - 1 sweeps; the difference of the two runs is `iters` sweeps
+        t0 = time.perf_counter()
+        O.clone_id_Gibbs(A, D, cfg, min_iter=T, max_iter=T, draws=O.NumpyDraws(seed))
+        times.append(time.perf_counter() - t0)
+    return (times[1] - times[0]) / iters
 
 
-def cpu_dense_reference_shaped(workload, cells=64, iters=2):
-    """The reference's own DENSE formulation (4K dense N x M matrices, R/clone_id.R:394-403) cannot hold C3 / C4
-    (SURVEY.md fact 4); timed on a few cells, cost is linear in cells."""
+def cpu_dense_reference_shaped(workload, cells=None, iters=2):
+    """The reference's own DENSE formulation (4K dense N x M double matrices rebuilt every sweep, R/clone_id.R:394-403,
+    537-542) cannot hold C3 / C4 (51 GB / 5 TB of S-lists): it is timed on as many cells as fit a few GB -- 10 000 of
+    C3's 100 000 cells, as BASELINE.md section 3 says, 1 000 of C4's 10^6 -- and scaled linearly in cells (every
+    term of the dense sweep is O(N M K))."""
     N, M, K, cov = WORKLOADS[workload]
+    if cells is None:
+        cells = int(min(M, max(64, 6.4e8 // (4 * N * K))))      # S-lists of ~5 GB: 4K N x cells doubles
     sec = _cpu_dense_chain((workload, cells, iters, 100))
-    return {"value": cells / M / sec, "unit": "Gibbs iterations/s", "cores": 1,
-            "sample": "%d sweeps of the dense R-shaped NumPy restatement on %d of %d cells, scaled linearly in "
-                      "cells" % (iters, cells, M)}
+    return {"value": cells / M / sec, "unit": "Gibbs iterations/s", "cores": os.cpu_count(),
+            "seconds_per_sweep_on_sample": sec,
+            "sample": "%d sweeps of the dense R-shaped NumPy restatement (oracle/cardelino_oracle.py, BLAS threads as "
+                      "NumPy finds them) on %d of %d cells, all %d variants and %d clones; scaled linearly in cells"
+                      % (iters, cells, M, N, K)}
 
 
-def cpu_sparse_port(workload, budget_s=20.0, counts=None):
+def cpu_sparse_port(workload, budget_s=20.0, counts=None, sweeps=None):
     """Best CPU figure: the sparse C / OpenMP restatement (oracle/gibbs_sparse.c, sufficient-statistic form, fp64)
-    on all host threads.  Runs whole sweeps on the full donor when one sweep fits the budget, else on a cell
-    sample (cost is linear in cells) -- says which."""
+    on ALL host threads (set explicitly: a launcher's OMP_NUM_THREADS=1 is ignored).  Runs whole sweeps on the
+    full donor when they fit the budget, else on a cell sample (cost is linear in cells) -- says which."""
     from oracle import c_oracle as CO
     N, M, K, cov = WORKLOADS[workload]
     cfg_mask = CO.config_masks(make_config(N, K))
-    threads = CO.threads()
+    threads = CO.set_threads()
     probe_cells = min(M, 20000)
     if counts is None:
         # no GPU in this process: make the donor on the host with the same distributions
@@ -323,52 +393,164 @@ def cpu_sparse_port(workload, budget_s=20.0, counts=None):
         probe_cells = min(M, probe_cells)
     sec, _, _ = CO.run(N, probe_cells, K, p[:probe_cells + 1], vi, a, d, cfg_mask, 2, seed=1)
     per_cell = sec / 2 / probe_cells
-    Ms = M if per_cell * M * 3 <= budget_s else max(probe_cells, int(budget_s / 3 / per_cell))
+    want = sweeps if sweeps is not None else 3
+    Ms = M if per_cell * M * want <= budget_s else max(probe_cells, int(budget_s / want / per_cell))
     if counts is None and Ms != probe_cells:
         p, vi, a, d, _ = CO.synth(N, Ms, K, cov, cfg_mask, seed=SEED_DATA)
     p = p[:Ms + 1]
-    T = max(2, min(20, int(budget_s / max(per_cell * Ms, 1e-9))))
-    sec, _, _ = CO.run(N, Ms, K, p, vi, a, d, cfg_mask, T, seed=1)
-    return {"value": T / sec * Ms / M, "unit": "Gibbs iterations/s", "cores": threads, "kind": "port",
+    T = sweeps if sweeps is not None else max(2, min(20, int(budget_s / max(per_cell * Ms, 1e-9))))
+    return {"N": N, "K": K, "M": M, "Ms": Ms, "T": T, "threads": threads, "run": lambda t: CO.run(N, Ms, K, p, vi, a, d, cfg_mask, t, seed=1)[0]}
+
+
+def cpu_baseline_leg(workload, counts):
+    c = cpu_sparse_port(workload, budget_s=20.0, counts=counts)
+    sec = c["run"](c["T"])
+    return {"value": c["T"] / sec * c["Ms"] / c["M"], "unit": "Gibbs iterations/s", "cores": c["threads"], "kind": "port",
             "sample": "%d sweeps of the sparse C/OpenMP restatement (oracle/gibbs_sparse.c, fp64) on %d of %d cells "
                       "(all %d variants, %d clones), %d threads%s" %
-                      (T, Ms, M, N, K, threads, "" if Ms == M else "; scaled linearly in cells to the full donor"),
-            "seconds_per_sweep_on_sample": sec / T}
+                      (c["T"], c["Ms"], c["M"], c["N"], c["K"], c["threads"],
+                       "" if c["Ms"] == c["M"] else "; scaled linearly in cells to the full donor"),
+            "seconds_per_sweep_on_sample": sec / c["T"]}
 
 
 def run_reference(args):
+    """The reference arm: R is not installed (here or on the GPU box) and the reference is pure R, so the reference's
+    ALGORITHM is timed as its sparse C/OpenMP restatement (oracle/gibbs_sparse.c) on all host threads: W warm-up
+    sweeps, then exactly K timed sweeps, each one full Gibbs sweep over the whole donor (a cell sample only if the
+    host is too slow for the whole donor to finish in a few minutes; the line says which).  Rank 0 only."""
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
-    N, M, K, cov = WORKLOADS[args.workload]
-    t0 = time.perf_counter()
-    vals, cpu = [], None
-    budget = max(5.0, 120.0 / max(1, args.steps + args.warmup))
-    for s in range(args.warmup + args.steps):
-        c = cpu_sparse_port(args.workload, budget_s=budget)
-        if s >= args.warmup:
-            vals.append(c["value"])
-            cpu = c
-        if time.perf_counter() - t0 > 150:
-            break
-    if not vals:
-        cpu = cpu_sparse_port(args.workload, budget_s=5.0)
-        vals = [cpu["value"]]
-    value = float(np.mean(vals))
-    cpu = dict(cpu, value=value)
-    dense = cpu_dense_reference_shaped(args.workload)
+    if args.workload == "C5":
+        return run_reference_c5(args)
+    c = cpu_sparse_port(args.workload, budget_s=150.0, sweeps=args.steps + args.warmup)
+    if args.warmup:
+        c["run"](args.warmup)
+    sec = c["run"](args.steps)
+    value = args.steps / sec * c["Ms"] / c["M"]
+    sample = ("%d sweeps of the sparse C/OpenMP restatement (oracle/gibbs_sparse.c, fp64) on %d of %d cells (all %d "
+              "variants, %d clones), %d threads%s" % (args.steps, c["Ms"], c["M"], c["N"], c["K"], c["threads"],
+                                                      "" if c["Ms"] == c["M"] else "; scaled linearly in cells"))
     out = {"impl": "reference", "metric": "Gibbs iterations/sec", "value": value, "unit": "Gibbs iterations/s",
-           "n_gpus": args.gpus, "steps": len(vals), "warmup": args.warmup,
-           "ms_per_step": 1e3 / value if value else None, "higher_is_better": True, "scaling": "strong",
-           "vs_baseline": None, "dtype": "f64", "data": "synthetic (host generator with sim_read_count's distributions)",
-           "config": {"workload": "%s: %d variants x %d cells x %d clones, %.0f%% coverage, wise=variant, "
-                                  "relax_Config=TRUE, 1 chain.  R is not installed here: the reference ALGORITHM is "
-                                  "timed as the sparse C/OpenMP restatement on all host threads (the best CPU figure); "
-                                  "its dense R-shaped formulation is in dense_reference_shaped" %
-                                  (args.workload, N, M, K, cov * 100)},
-           "cpu_baseline": cpu, "dense_reference_shaped": dense,
+           "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 / value,
+           "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f64",
+           "data": "synthetic (host generator with sim_read_count's distributions)",
+           "config": {"workload": workload_string(args.workload)},
+           "reference_kind": "R is not installed: the reference ALGORITHM as its sparse C/OpenMP restatement on all "
+                             "host threads (a far better CPU program than the reference's dense R loop; see "
+                             "cpu_baseline.dense_reference_shaped in the other arm)",
+           "cpu_baseline": {"value": value, "unit": "Gibbs iterations/s", "cores": c["threads"], "kind": "port",
+                            "sample": sample},
            "e2e": {"value": value, "unit": "Gibbs iterations/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
     print(json.dumps(out))
+
+
+# ---- C5: 64 independent chains (one group per GPU) + the EM path + the Geweke stop rule ---------------------------
+C5_CHAINS, C5_MIN, C5_MAX = 64, 2000, 5000
+
+
+def _c5_donor():
+    d = np.load(os.path.join(ROOT, "tests", "golden", "example_donor.npz"))
+    return d["A"], d["D"], d["Z"]
+
+
+def run_ours_c5(args):
+    """BASELINE configs[4]: 64 chains of clone_id() on the reference's example_donor, one chain group per GPU
+    (no communication while sampling), the reference's stop rule, chains merged like R/clone_id.R:165-181; plus
+    one inference = "EM" call.  A step = one whole clone_id(n_chain = 64) call; value = chain iterations per second
+    (the sum of the chains' n_iter over the call's wall time, merge included), max over ranks."""
+    import torch
+    import torch.distributed as dist
+    import cardelino_b200 as cb
+    from cardelino_b200 import distributed as cd
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    else:
+        dist.init_process_group("gloo", init_method="tcp://127.0.0.1:%d" % (29000 + os.getpid() % 2000), rank=0, world_size=1)
+    A, D, Z = _c5_donor()
+    h = cb.Handle(local)
+    kw = dict(min_iter=C5_MIN, max_iter=C5_MAX, seed=SEED_CHAIN, handle=h, verbose=False)
+    sampler = ClockSampler(local) if rank == 0 else None
+
+    def one_call():
+        torch.cuda.synchronize()
+        dist.barrier()
+        t0 = time.perf_counter()
+        res = cd.clone_id_chain_groups(A, D, Z, C5_CHAINS, **kw)
+        torch.cuda.synchronize()
+        dt = time.perf_counter() - t0
+        t = torch.tensor([dt], dtype=torch.float64, device="cuda" if world > 1 else "cpu")
+        if world > 1:
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return res, float(t.item())
+    for _ in range(max(1, min(args.warmup, 3))):
+        one_call()
+    if sampler:
+        sampler.start()
+    steps = max(1, min(args.steps, 20))
+    tot_it, tot_s, res = 0, 0.0, None
+    for _ in range(steps):
+        res, dt = one_call()
+        tot_it += sum(int(o["n_iter"]) - 1 for o in res["chains"])
+        tot_s += dt
+    clocks = sampler.stop() if sampler else None
+    t0 = time.perf_counter()
+    em = cb.clone_id(A, D, Config=Z, inference="EM", handle=h, verbose=False)
+    em_s = time.perf_counter() - t0
+    if rank == 0:
+        value = tot_it / tot_s
+        out = {"metric": "Gibbs iterations/sec", "value": value, "unit": "Gibbs iterations/s (summed over chains)",
+               "n_gpus": world, "steps": steps, "warmup": max(1, min(args.warmup, 3)), "ms_per_step": tot_s / steps * 1e3,
+               "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f64",
+               "data": "the reference's example_donor fixture (tests/golden/example_donor.npz)",
+               "config": {"workload": workload_string("C5")},
+               "chains": C5_CHAINS, "chain_iterations_per_call": tot_it / steps,
+               "mean_n_iter": float(np.mean([o["n_iter"] for o in res["chains"]])),
+               "em": {"seconds": em_s, "n_iter": int(em["n_iter"]), "logLik": float(em["logLik"])},
+               "merged_prob_hash": sha16(np.round(res["prob"], 12)),
+               "e2e": {"value": value, "unit": "Gibbs iterations/s (summed over chains)",
+                       "h2d_bytes_per_step": int(A.nbytes + D.nbytes + Z.nbytes),
+                       "d2h_bytes_per_step": int(sum(o["prob"].nbytes + o["Config_prob"].nbytes for o in res["chains"])),
+                       "note": "value IS end to end: every step is a whole clone_id(n_chain = 64) call from host arrays "
+                               "(dense load, 64 chains, per-chain fetches, host merge)"},
+               "clocks": clocks, "gpu_launches": None, "roofline": None, "cpu_baseline": None}
+        print(json.dumps(out))
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+def run_reference_c5(args):
+    """C5 on the host: the NumPy restatement (op for op with the R loop) runs a few chains of the same call on one
+    core each; chain iterations per second, scaled to the host's cores (chains are independent)."""
+    from concurrent.futures import ProcessPoolExecutor
+    cores = os.cpu_count() or 1
+    n = min(cores, 8)
+    t0 = time.perf_counter()
+    with ProcessPoolExecutor(n) as ex:
+        its = list(ex.map(_c5_cpu_chain, range(n)))
+    dt = time.perf_counter() - t0
+    value = sum(its) / dt * (cores / n)
+    out = {"impl": "reference", "metric": "Gibbs iterations/sec", "value": value,
+           "unit": "Gibbs iterations/s (summed over chains)", "n_gpus": args.gpus, "steps": 1, "warmup": 0,
+           "ms_per_step": dt * 1e3, "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f64",
+           "data": "the reference's example_donor fixture", "config": {"workload": workload_string("C5")},
+           "cpu_baseline": {"value": value, "unit": "Gibbs iterations/s", "cores": cores, "kind": "port",
+                            "sample": "%d chains of 300 sweeps of the dense NumPy restatement, one process each; scaled "
+                                      "to %d cores" % (n, cores)},
+           "e2e": {"value": value, "unit": "Gibbs iterations/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+    print(json.dumps(out))
+
+
+def _c5_cpu_chain(c):
+    os.environ["OMP_NUM_THREADS"] = "1"
+    from oracle import cardelino_oracle as O
+    A, D, Z = _c5_donor()
+    O.clone_id_Gibbs(A, D, Z, min_iter=300, max_iter=300, draws=O.NumpyDraws(1000 + c))
+    return 299
 
 
 def main():
@@ -377,17 +559,19 @@ def main():
     ap.add_argument("--steps", type=int, default=50)
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--workload", default="C4", choices=list(WORKLOADS))
+    ap.add_argument("--workload", default="C4", choices=list(WORKLOADS) + ["C5"])
     ap.add_argument("--e2e-iters", type=int, default=5000,
                     help="sweeps of the end-to-end clone_id_Gibbs call; 5000 = the reference's default min_iter "
                          "(R/clone_id.R:352), i.e. the shortest chain a stock clone_id() call runs")
-    ap.add_argument("--cpu-cells", type=int, default=64)
+    ap.add_argument("--cpu-cells", type=int, default=None,
+                    help="cells of the dense R-shaped CPU sample (default: as many as give ~5 GB of S-lists)")
     ap.add_argument("--cpu-iters", type=int, default=2)
     ap.add_argument("--exchange", default="auto", choices=["auto", "nccl", "peer"],
                     help="multi-GPU statistic-table exchange: peer memory fused into the table kernel, or NCCL")
     ap.add_argument("--no-e2e", action="store_true")
-    ap.add_argument("--no-incremental", action="store_true")
     ap.add_argument("--no-cpu", action="store_true")
+    ap.add_argument("--no-dense", action="store_true", help="skip the dense R-shaped CPU sample (about a minute)")
+    ap.add_argument("--no-parity", action="store_true")
     args = ap.parse_args()
     if args.warmup < 3 and args.impl == "ours":
         args.warmup = 3
@@ -410,6 +594,8 @@ def main():
     try:
         if args.impl == "reference":
             run_reference(args)
+        elif args.workload == "C5":
+            run_ours_c5(args)
         else:
             run_ours(args)
     finally:

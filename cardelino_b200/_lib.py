@@ -63,7 +63,7 @@ class GibbsInfo(C.Structure):
     _fields_ = [
         ("n_iter", C.c_int32), ("n_buin", C.c_int32), ("n_element", C.c_int32), ("exact_trace", C.c_int32),
         ("percent_converged", C.c_double), ("logLik_post", C.c_double), ("W_log", C.c_double),
-        ("dic", C.c_double * 6),
+        ("dic", C.c_double * 6), ("stop_rule", C.c_int32),
     ]
 
 

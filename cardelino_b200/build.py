@@ -9,7 +9,7 @@ CSRC = os.path.join(HERE, "csrc")
 OUT = os.path.join(HERE, "libcardelino_b200.so")
 SOURCES = ["api.cu", "formats.cu", "gibbs.cu", "cells_sell.cu", "element.cu", "small.cu", "post.cu", "synth.cu"]
 NVCC = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
-FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
+FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17"] + os.environ.get("CDL_EXTRA_NVCC_FLAGS", "").split() + [
          "-Xcompiler", "-fPIC", "-Xptxas", "-v"]
 
 

@@ -335,7 +335,7 @@ def _collect(h, chain, Av, Config, wise, relabel, verbose, keep_assign_all, ligh
                 "relax_rate": relax_rate, "relax_rate_all": relax_rate_all,
                 "Config_prob": h.fetch("Config_prob", chain), "n_iter": info.n_iter, "n_buin": info.n_buin,
                 "percent_converged": info.percent_converged, "logLik_post": info.logLik_post,
-                "W_log": info.W_log, "exact_trace": bool(info.exact_trace),
+                "W_log": info.W_log, "exact_trace": bool(info.exact_trace), "stop_rule": int(info.stop_rule),
                 "DIC": dict(zip(("DIC", "logLik_var", "D_mean", "D_post", "DIC_Gelman", "DIC_Spiegelhalter"),
                                 list(info.dic)))}
     K = Config.shape[1]
@@ -355,7 +355,7 @@ def _collect(h, chain, Av, Config, wise, relabel, verbose, keep_assign_all, ligh
         "relax_rate": relax_rate, "Config_prob": h.fetch("Config_prob", chain),
         "Config_all": h.fetch("Config_all", chain), "relax_rate_all": relax_rate_all,
         "n_iter": it, "n_buin": n_buin, "percent_converged": pc, "logLik_post": info.logLik_post,
-        "W_log": info.W_log, "exact_trace": bool(info.exact_trace),
+        "W_log": info.W_log, "exact_trace": bool(info.exact_trace), "stop_rule": int(info.stop_rule),
     }
     if info.exact_trace:
         out["prob_all"] = h.fetch("prob_all", chain)

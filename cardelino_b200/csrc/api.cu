@@ -944,6 +944,7 @@ int cdl_gibbs_run(cdl_handle h, const double* Config, int32_t K, const double* P
             ch.info.n_buin = (int32_t)n_buin;
             ch.info.n_element = (int32_t)n_el;
             ch.info.exact_trace = exact ? 1 : 0;
+            ch.info.stop_rule = exact ? 0 : (win ? 1 : 2);
             ch.info.W_log = a.W_log;
             const int64_t r0 = n_buin - 1, r1 = itf;
             if (gp.relabel) relabel_trace(ch.prob_all.p, ch.config_all.p, M, N, K, n_buin, itf, h->st);   // (:624-644)
@@ -991,7 +992,8 @@ int cdl_gibbs_run(cdl_handle h, const double* Config, int32_t K, const double* P
         const bool small = (h->cells_layout == CDL_CELLS_SMALL ||
                             (h->cells_layout == CDL_CELLS_AUTO && d.M_total < 16384)) &&
                            h->world == 1 && !rp && !element && gp.incremental_stats != 1 && small_path_fits(d, K, gp.wise) &&
-                           per_chain_bytes * gp.n_chain <= (double)gp.trace_budget_bytes;
+                           per_chain_bytes * gp.n_chain <= (double)gp.trace_budget_bytes &&
+                           (exact || !win);    // without the trace the stop rule needs the window snapshots (three-kernel path)
         if (small) { win = false; snaps.clear(); a.incremental = 0; }
         const bool concurrent = concurrent_ok && !win;     // the windowed stop rule runs one chain at a time
         if (h->cells_layout == CDL_CELLS_SMALL && !small)

@@ -20,10 +20,6 @@
 #include <cub/cub.cuh>
 #include <cstdlib>
 
-#ifndef CDL_SELL_MAGIC
-#define CDL_SELL_MAGIC 0
-#endif
-
 namespace cdl {
 
 namespace {
@@ -112,20 +108,9 @@ __device__ __forceinline__ void sell_group_fast(double (&acc)[KP], const Grp<uin
         const uint32_t off = (e & 1) ? (vw >> 14) : (__byte_perm(vw, 0u, 0x1044) >> 12);
         double du, dv;
         asm volatile("ld.shared.v2.f64 {%0, %1}, [%2];" : "=d"(du), "=d"(dv) : "r"(tab_sa + off));
-#if CDL_SELL_MAGIC
-        // counts -> double without I2F.F64 (which shares the fp64 pipe): 2^52 + a is the register pair (a, 0x43300000),
-        // and fma(2^52 + a, du, -2^52 du) is a * du correctly rounded (the product and the sum are exact inside the
-        // fma); -2^52 du is du with 52 added to the exponent field and the sign flipped: one integer add
-        const double da = __hiloint2double(0x43300000, (int)((e & 1) ? (aw >> 16) : (aw & 0xffffu)));
-        const double db = __hiloint2double(0x43300000, (int)((e & 1) ? (bw >> 16) : (bw & 0xffffu)));
-        const double c1 = __hiloint2double(__double2hiint(du) + (int)0x83400000, __double2loint(du));
-        const double c2 = __hiloint2double(__double2hiint(dv) + (int)0x83400000, __double2loint(dv));
-        const double del = fma(da, du, c1) + fma(db, dv, c2);
-#else
         const double da = (e & 1) ? u16hi_to_double(aw) : u16lo_to_double(aw);
         const double db = (e & 1) ? u16hi_to_double(bw) : u16lo_to_double(bw);
         const double del = fma(da, du, db * dv);
-#endif
         // both mask bytes in ONE integer register: ptxas then produces the predicates with R2P (seven per
         // instruction); testing the low words of du / dv in place makes it emit one LOP3 per clone instead
         const uint32_t m = __byte_perm((uint32_t)__double2loint(du), (uint32_t)__double2loint(dv), 0x7740);
@@ -271,16 +256,24 @@ __global__ void __launch_bounds__(SELL_THREADS, 1) k_cells_sell(const SellParams
         double acc[KP];
 #pragma unroll
         for (int q_ = 0; q_ < KP; ++q_) acc[q_] = 0.0;
-        if (FAST && SELL_DEPTH == 1) {
-            // two groups per trip, ping-pong between q[0] and n: the loads of a group are issued one group ahead
-            // (look-ahead index clamped to the slice's last slot, so they need no predicate)
+        if (FAST) {
+            // A ring of SELL_DEPTH + 1 group buffers, SELL_DEPTH + 1 groups per trip so that every index is static (no
+            // register rotation): the loads of a group are written SELL_DEPTH groups before it is accumulated.  The
+            // look-ahead index is clamped to the slice's last slot, so the loads need no predicate.  (ptxas places
+            // the loads where its register budget allows -- at 72 registers one of the two groups is fetched just
+            // before its use, which shows as long-scoreboard samples on its first consumer; pinning the loads early
+            // with ld.volatile, 24 / 20 / 16 warps with two or three groups of look-ahead, all measured slower:
+            // profiles/README.md, "tried and not kept".)
             const uint32_t ge = (uint32_t)g1, gl = (uint32_t)g1 - 1u;
-            for (uint32_t g = (uint32_t)g0; g < ge; g += 2) {
-                Grp<VIdx> n;
-                n.load(C.vidx, P.a8, P.b8, (int64_t)(min(g + 1u, gl) * 32u + (uint32_t)lane));
-                sell_group_fast_any<KP, VIdx, SKIP0>(acc, q[0], tab_sa);
-                q[0].load(C.vidx, P.a8, P.b8, (int64_t)(min(g + 2u, gl) * 32u + (uint32_t)lane));
-                if (g + 1u < ge) sell_group_fast_any<KP, VIdx, SKIP0>(acc, n, tab_sa);
+            Grp<VIdx> n;
+            for (uint32_t g = (uint32_t)g0; g < ge; g += SELL_DEPTH + 1) {
+#pragma unroll
+                for (int st = 0; st <= SELL_DEPTH; ++st) {
+                    Grp<VIdx>& dst = ((st + SELL_DEPTH) % (SELL_DEPTH + 1)) == SELL_DEPTH ? n : q[(st + SELL_DEPTH) % (SELL_DEPTH + 1)];
+                    dst.load(C.vidx, P.a8, P.b8, (int64_t)(min(g + (uint32_t)(st + SELL_DEPTH), gl) * 32u + (uint32_t)lane));
+                    if (st == 0 || g + (uint32_t)st < ge)
+                        sell_group_fast_any<KP, VIdx, SKIP0>(acc, st == SELL_DEPTH ? n : q[st], tab_sa);
+                }
             }
         } else {
         for (int64_t g = g0; g < g1; g += SELL_DEPTH) {

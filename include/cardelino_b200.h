@@ -117,6 +117,10 @@ typedef struct cdl_gibbs_info {
     double  logLik_post;         /* (:656) */
     double  W_log;               /* (:388) */
     double  dic[6];              /* DIC, logLik_var, D_mean, D_post, DIC_Gelman, DIC_Spiegelhalter (:790-797) */
+    int32_t stop_rule;           /* how the reference's stop rule (:580-592) was applied: 0 = on the stored prob_all;
+                                    1 = the same test from running sums and window snapshots (streaming mode);
+                                    2 = not at all: max_iter sweeps (min_iter == max_iter, snapshots over the trace
+                                    budget, the single-CTA path without a trace, wise = "element" without a trace) */
 } cdl_gibbs_info;
 
 int  cdl_version(void);

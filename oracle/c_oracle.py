@@ -47,6 +47,17 @@ def threads():
     return int(lib().orc_threads())
 
 
+def set_threads(n=None):
+    """Use `n` OpenMP threads (default: every core this process may run on), whatever OMP_NUM_THREADS says."""
+    if n is None:
+        try:
+            n = len(os.sched_getaffinity(0))
+        except AttributeError:
+            n = os.cpu_count() or 1
+    lib().orc_set_threads(C.c_int(int(n)))
+    return threads()
+
+
 def config_masks(Config):
     Config = np.asarray(Config)
     m = np.zeros(Config.shape[0], np.uint32)

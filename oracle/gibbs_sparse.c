@@ -35,6 +35,16 @@ int orc_threads(void) {
 #endif
 }
 
+/* number of OpenMP threads of the following calls.  bench.py sets it to the host's core count explicitly: under
+ * torch.distributed.run the launcher exports OMP_NUM_THREADS=1, which would time the port on one core. */
+void orc_set_threads(int n) {
+#ifdef _OPENMP
+    if (n > 0) omp_set_num_threads(n);
+#else
+    (void)n;
+#endif
+}
+
 /* R's revsort (src/main/sort.c): heapsort a[] into descending order, permuting ib[] alongside */
 static void revsort(double* a, int* ib, int n) {
     int l, j, ir, i, ii;

@@ -66,3 +66,63 @@ def uniforms(seed, chain, iteration, stream, idx, sub=0):
     c3 = np.uint32(((int(chain) << 8) | int(stream)) & 0xFFFFFFFF)
     x0, x1, _, _ = philox4x32(idx, np.uint32(sub), np.uint32(iteration), c3, k0, k1)
     return u53(x0, x1)
+
+
+def uniform_pairs(seed, chain, iteration, stream, idx, sub):
+    """The two 53-bit uniforms of one Philox block (PhiloxSeq::next2 in csrc/common.cuh); idx / sub broadcast."""
+    seed = int(seed) & 0xFFFFFFFFFFFFFFFF
+    k0, k1 = seed & 0xFFFFFFFF, seed >> 32
+    c3 = np.uint32(((int(chain) << 8) | int(stream)) & 0xFFFFFFFF)
+    x0, x1, x2, x3 = philox4x32(np.asarray(idx, np.uint32), np.asarray(sub, np.uint32), np.uint32(iteration), c3, k0, k1)
+    return u53(x0, x1), u53(x2, x3)
+
+
+def gamma_mt(shape, seed, chain, iteration, stream, idx, sub0=0):
+    """Marsaglia-Tsang Gamma(shape, 1) exactly as csrc/common.cuh::gamma_mt walks its Philox sub-stream (vectorised
+    over `shape` / `idx`): used to check the Beta draws of the CUDA table kernel against the shape parameters
+    prior + S (R/clone_id.R:563-571).  Device libm differs from NumPy's in the last bits, so draws agree to
+    rounding, not bitwise (and a rejection test can, very rarely, fall the other way)."""
+    a = np.array(shape, dtype=np.float64, ndmin=1).copy()
+    idx = np.broadcast_to(np.asarray(idx, np.uint32), a.shape).copy()
+    sub = np.full(a.shape, int(sub0), dtype=np.uint64)
+    boost = np.ones_like(a)
+    small = a < 1.0
+    if small.any():
+        u, _ = uniform_pairs(seed, chain, iteration, stream, idx[small], sub[small].astype(np.uint32))
+        boost[small] = u ** (1.0 / a[small])
+        a[small] += 1.0
+        sub[small] += 1
+    d = a - 1.0 / 3.0
+    c = 1.0 / np.sqrt(9.0 * d)
+    out = np.full(a.shape, np.nan)
+    todo = np.ones(a.shape, dtype=bool)
+    for _ in range(1000):
+        if not todo.any():
+            break
+        t = np.flatnonzero(todo)
+        u1, u2 = uniform_pairs(seed, chain, iteration, stream, idx[t], sub[t].astype(np.uint32))
+        u3, _ = uniform_pairs(seed, chain, iteration, stream, idx[t], (sub[t] + 1).astype(np.uint32))
+        sub[t] += 2
+        x = np.sqrt(-2.0 * np.log(u1)) * np.cos(2.0 * np.pi * u2)
+        v = 1.0 + c[t] * x
+        ok = v > 0.0
+        v3 = np.where(ok, v, 1.0) ** 3
+        x2 = x * x
+        with np.errstate(invalid="ignore", divide="ignore"):
+            acc = ok & ((u3 < 1.0 - 0.0331 * x2 * x2) | (np.log(u3) < 0.5 * x2 + d[t] * (1.0 - v3 + np.log(v3))))
+        out[t[acc]] = boost[t[acc]] * d[t[acc]] * v3[acc]
+        todo[t[acc]] = False
+    return out
+
+
+def _clamp_theta(t):
+    return np.clip(t, 1e-300, 1.0 - 1.1102230246251565e-16)
+
+
+def beta_parallel(a, b, seed, chain, iteration, stream, idx):
+    """Beta(a, b) as the sweep's table kernel draws it: X ~ Gamma(a) on sub-stream 0, Y ~ Gamma(b) on sub-stream
+    2^31 of the same (chain, iteration, stream, idx) -- two jobs on two threads (csrc/gibbs.cu::k_table)."""
+    x = gamma_mt(a, seed, chain, iteration, stream, idx, 0)
+    y = gamma_mt(b, seed, chain, iteration, stream, idx, 1 << 31)
+    s = x + y
+    return _clamp_theta(np.where(s > 0.0, x / np.where(s > 0.0, s, 1.0), 0.5))

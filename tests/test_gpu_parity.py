@@ -301,7 +301,7 @@ def test_incremental_statistics_are_exact(gpu_handle, example_donor):
     A, D, Z = example_donor
     kw = dict(min_iter=40, max_iter=40, seed=8, keep_assign_all=True, handle=gpu_handle, verbose=False)
     gpu_handle.set_cells_layout("rows")          # both runs on the three-kernel sweep (the incremental update lives there)
-    a = cb.clone_id_Gibbs(A, D, Z, **kw)
+    a = cb.clone_id_Gibbs(A, D, Z, incremental_stats=False, **kw)
     b = cb.clone_id_Gibbs(A, D, Z, incremental_stats=True, **kw)
     gpu_handle.set_cells_layout("auto")
     for f in ("prob_all", "assign_all", "Config_all", "theta1_all", "logLik"):
@@ -493,11 +493,12 @@ def test_converged_posterior_matches_oracle_chains(gpu_handle, c2_donor, example
     assert abs(g["theta0"] - np.mean([o["theta0"] for o in os_])) < 2e-3
 
 
-@pytest.mark.parametrize("layout,buin_frac", [("rows", 0.5), ("slices", 0.3)])
-def test_streaming_stop_rule_matches_exact(gpu_handle, c2_donor, layout, buin_frac):
+@pytest.mark.parametrize("layout,buin_frac,snap32", [("rows", 0.5, 0), ("slices", 0.3, 1), ("rows", 0.5, 1)])
+def test_streaming_stop_rule_matches_exact(gpu_handle, c2_donor, layout, buin_frac, snap32):
     """Streaming mode (no prob_all) applies the reference's Geweke stop rule and its burn-in, which depends on
     the final iteration (R/clone_id.R:580-606,645), from running column sums and window snapshots: same stop
-    iteration, burn-in and posterior means as the exact mode that keeps the whole trace."""
+    iteration, burn-in and posterior means as the exact mode that keeps the whole trace.  Snapshots kept as fp64
+    reproduce the means to rounding; the default fp32 snapshots (half the memory) to ~1e-7."""
     cb = _cb()
     A, D, Z, _ = c2_donor
     gpu_handle.set_cells_layout(layout)
@@ -505,7 +506,7 @@ def test_streaming_stop_rule_matches_exact(gpu_handle, c2_donor, layout, buin_fr
         out = {}
         for keep in (1, 0):
             out[keep] = cb.clone_id_Gibbs(A, D, Z, min_iter=300, max_iter=2500, seed=11, buin_frac=buin_frac,
-                                          handle=gpu_handle, verbose=False, keep_prob_all=keep)
+                                          handle=gpu_handle, verbose=False, keep_prob_all=keep, snapshot_fp32=snap32)
     finally:
         gpu_handle.set_cells_layout("auto")
     ex, st = out[1], out[0]
@@ -513,10 +514,10 @@ def test_streaming_stop_rule_matches_exact(gpu_handle, c2_donor, layout, buin_fr
     assert st["n_iter"] == ex["n_iter"] and st["n_buin"] == ex["n_buin"]
     assert ex["n_iter"] < 2500, "pick parameters with which the exact run stops early"
     assert abs(st["percent_converged"] - ex["percent_converged"]) <= 0.2
-    assert np.abs(st["prob"] - ex["prob"]).max() < 1e-9          # difference of running sums vs mean of the rows
+    assert np.abs(st["prob"] - ex["prob"]).max() < (1e-6 if snap32 else 1e-9)   # difference of running sums vs mean of the rows
     assert np.array_equal(st["Config_prob"], ex["Config_prob"])
     assert st["theta0"] == ex["theta0"] and st["relax_rate"] == ex["relax_rate"]
-    assert np.isclose(st["logLik_post"], ex["logLik_post"], rtol=1e-9)
+    assert np.isclose(st["logLik_post"], ex["logLik_post"], rtol=1e-6 if snap32 else 1e-9)
 
 
 def test_device_beta_sampler_distribution(gpu_handle):
