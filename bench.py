@@ -239,11 +239,13 @@ def run_ours(args):
                 h2.synth_generate(N, M, K, cfg, cov, SEED_DATA)
                 z2, c2, a0, a1, l2 = first_sweeps(h2, M)
                 h2.close()
-                ref = {"labels_hash": sha16(z2), "config_hash": sha16(c2), "theta_hash": sha16(a0, a1),
-                       "loglik_hash": sha16(l2)}
-                parity["unsharded"] = ref
+                ref = {"labels_hash": sha16(z2), "config_hash": sha16(c2), "theta_hash": sha16(a0, a1)}
+                parity["unsharded"] = dict(ref, loglik_hash=sha16(l2))
+                # labels, Config flips and theta draws are exact (integer statistics, Philox keyed by global cell id); the
+                # logLik trace adds each rank's sum(lchoose(D, A)) in rank order, so it agrees to rounding, not bitwise
                 parity["sharded_equals_unsharded"] = all(parity[k] == ref[k] for k in ref)
                 parity["label_mismatches"] = int((z != z2).sum())
+                parity["loglik_max_rel_diff"] = float(np.max(np.abs(ll[1:] - l2[1:]) / np.abs(l2[1:])))
             else:
                 parity["sharded_equals_unsharded"] = True
                 parity["note"] = "one rank: the run IS the unsharded donor; compare the hashes across N in SCALE"
@@ -352,11 +354,11 @@ def _cpu_dense_chain(job):
     p = np.where(H > 0, th1[:, None], 0.002)
     A = np.where(covered, rng.binomial(np.nan_to_num(D).astype(int), p), np.nan)
     times = []
-    for T in (2, iters + 2):          # rows 1..T: T - 1 sweeps; the difference of the two runs is `iters` sweeps
-        t0 = time.perf_counter()
+    for T in (2, 2, iters + 2):       # rows 1..T: T - 1 sweeps.  The first run warms up (imports, page faults); the
+        t0 = time.perf_counter()      # difference of the other two is `iters` sweeps without set-up and summaries
         O.clone_id_Gibbs(A, D, cfg, min_iter=T, max_iter=T, draws=O.NumpyDraws(seed))
         times.append(time.perf_counter() - t0)
-    return (times[1] - times[0]) / iters
+    return max(times[2] - times[1], 1e-9) / iters
 
 
 def cpu_dense_reference_shaped(workload, cells=None, iters=2):
@@ -565,7 +567,7 @@ def main():
                          "(R/clone_id.R:352), i.e. the shortest chain a stock clone_id() call runs")
     ap.add_argument("--cpu-cells", type=int, default=None,
                     help="cells of the dense R-shaped CPU sample (default: as many as give ~5 GB of S-lists)")
-    ap.add_argument("--cpu-iters", type=int, default=2)
+    ap.add_argument("--cpu-iters", type=int, default=1)
     ap.add_argument("--exchange", default="auto", choices=["auto", "nccl", "peer"],
                     help="multi-GPU statistic-table exchange: peer memory fused into the table kernel, or NCCL")
     ap.add_argument("--no-e2e", action="store_true")

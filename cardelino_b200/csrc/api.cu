@@ -394,15 +394,15 @@ void one_sweep(cdl_handle h, Chain& ch, SweepArgs& a, uint32_t it, const cdl_rep
         ++q.epoch;
         ch.dev.sab = q.arena + (size_t)(q.epoch & 1ull) * q.table_elems;
         a.p2p = &q;
-        if (a.incremental) { launch_stats_incremental(h->donor, a, ch.dev, h->sm_count, h->st); h->launches += 2; }
+        // (the last CTA of the kernel that completes the table publishes it to the peers)
+        if (a.incremental) { launch_stats_incremental(h->donor, a, ch.dev, h->sm_count, h->st); h->launches += 1; }
         else launch_stats(h->donor, a, ch.dev, h->sm_count, h->st);
         capture();
-        launch_signal(q, h->st);
         launch_table(h->donor, a, ch.dev, h->st);
-        h->launches += 4;   // + k_signal
+        h->launches += 3;
     } else {
         a.p2p = nullptr;
-        if (a.incremental) { launch_stats_incremental(h->donor, a, ch.dev, h->sm_count, h->st); h->launches += 2; }
+        if (a.incremental) { launch_stats_incremental(h->donor, a, ch.dev, h->sm_count, h->st); h->launches += 1; }
         else launch_stats(h->donor, a, ch.dev, h->sm_count, h->st);
         capture();
         allreduce_u64(h, ch.dev.sab, (size_t)(a.N * a.K));
@@ -748,6 +748,14 @@ int cdl_gibbs_run(cdl_handle h, const double* Config, int32_t K, const double* P
             a.skip0 = (col0_zero && (!gp.relax_Config || gp.keep_base_clone)) ? 1 : 0;
         }
         a.W_log = allreduce_scalar_d(h, d.W_log);
+        if (h->p2p_active) {
+            // The all-reduce above is also the barrier that makes this safe: every rank has returned from its previous
+            // run (its last table kernel, which reads the peers' arenas, is complete).  A run with incremental
+            // statistics leaves its carried table in the arena; every run starts from cleared halves.
+            CDL_CUDA(cudaMemsetAsync(h->p2p.arena, 0, sizeof(unsigned long long) * 2 * h->p2p.table_elems, h->st));
+            CDL_CUDA(cudaStreamSynchronize(h->st));
+            allreduce_scalar_d(h, 0.0);      // nobody starts sweeping (and reading a peer's arena) before all are cleared
+        }
         a.key = PhiloxKey{(uint32_t)(gp.seed & 0xffffffffu), (uint32_t)(gp.seed >> 32)};
         a.T = T;
         // incremental statistics: per-variant tables (the element path keeps fp64 sums); across GPUs only with the
@@ -795,50 +803,79 @@ int cdl_gibbs_run(cdl_handle h, const double* Config, int32_t K, const double* P
         DevBuf<unsigned long long> gcounts(2);
 
         // Streaming mode with the reference's stop rule.  Without prob_all the Geweke test (:580-601) and the
-        // burn-in that depends on the final iteration (:604-606,645) are evaluated from RUNNING column sums of
-        // prob and prob^2 (kept by the cell kernel from row 2 on) and snapshots of them at the rows where a
-        // window of some later check begins: floor(.1 n), ceil(.5 n) - 1 and ceil(buin_frac n) - 1 for every
-        // check row n.  That is 2-3 snapshots per check instead of n rows; used when a stop before max_iter is
-        // possible, the snapshots that are alive together fit the trace budget, and the run takes the plain
+        // burn-in that depends on the final iteration (:604-606,645) are evaluated from column sums of prob and
+        // prob^2 over SEGMENTS of trace rows.  The cut rows are the rows where a window of some check begins or
+        // ends: floor(.1 n) (end of window A), ceil(.5 n) - 1 (row before window B) and ceil(buin_frac n) - 1
+        // (row before the burn-in mean) for every check row n.  The cell kernel accumulates into one pair of running
+        // sums; at a cut row they are stored as the segment (previous cut, this cut] and cleared.  A window is then a
+        // union of whole segments, ADDED up -- never a difference of two long prefix sums, which loses a window of
+        // tiny values behind a prefix that once held large ones (a cell that visited a clone early: found by the
+        // saturated-probability test).  Window A only grows, so its segments are folded into one fp64 pair as the
+        // checks pass.  About 2-3 segments per check are alive instead of n rows; kept as fp32 by default
+        // (snapshot_fp32: each is the sum of its own 10-50 rows, so the rounding is relative to the window's own
+        // scale; Z moves by ~1e-6 relative, the posterior means by < 1e-7) for half the memory.  Used when a stop
+        // before max_iter is possible, the segments alive together fit the trace budget, and the run takes the plain
         // one-chain-at-a-time branch (wise = global / variant).
-        // Snapshots are kept as fp32 by default (snapshot_fp32): they only enter differences of sums over hundreds of
-        // rows, so Z moves by ~1e-6 relative and the posterior means by < 1e-7, for half the memory.
         const bool snap32 = gp.snapshot_fp32 != 0;
-        struct Snap {
-            DevBuf<double> s1, s2; DevBuf<float> f1, f2; int64_t last_use = 0; bool need_s2 = false;
-            void release() { s1.release(); s2.release(); f1.release(); f2.release(); }
+        struct Seg {
+            int64_t r0 = 0, r1 = 0;              // rows r0 + 1 .. r1 (1-based trace rows)
+            DevBuf<double> d1, d2; DevBuf<float> f1, f2;
+            bool need_s2 = false, stored = false, merged = false;
+            int64_t merge_at = 0;                // first check whose window A contains it (0 = none)
+            int64_t free_at = 0;                 // last check that needs its buffers
+            void release() { d1.release(); d2.release(); f1.release(); f2.release(); }
         };
-        std::map<int64_t, Snap> snaps;          // by row count r (rows 1..r summed); r <= 1 needs no buffer
+        std::vector<Seg> segs;                  // in row order
         std::vector<int64_t> win_checks;
         auto rowsA = [](int64_t n) { return (int64_t)std::floor(0.1 * (double)n); };
         auto rowsB = [](int64_t n) { return (int64_t)std::ceil(0.5 * (double)n) - 1; };
         auto rowsU = [&](int64_t n) { return (int64_t)std::ceil((double)n * gp.buin_frac) - 1; };
         bool win = !exact && !element && gp.min_iter < T;
+        auto plan_segments = [&]() {
+            segs.clear();
+            std::vector<int64_t> cuts;
+            for (int64_t n : win_checks) {
+                const int64_t r3[3] = {rowsA(n), rowsB(n), rowsU(n)};
+                for (int q = 0; q < 3; ++q) if (r3[q] > 1 && r3[q] < T) cuts.push_back(r3[q]);   // rows <= 1 hold no sums
+            }
+            std::sort(cuts.begin(), cuts.end());
+            cuts.erase(std::unique(cuts.begin(), cuts.end()), cuts.end());
+            int64_t prev = 1;
+            for (int64_t r : cuts) {
+                Seg sg;
+                sg.r0 = prev; sg.r1 = r;
+                for (int64_t n : win_checks) {
+                    if (n < r) continue;
+                    const bool inA = r <= rowsA(n), inB = sg.r0 >= rowsB(n), inU = sg.r0 >= rowsU(n);
+                    if (inA && !sg.merge_at) sg.merge_at = n;
+                    if (inA || inB) sg.need_s2 = true;
+                    if (inB || inU) sg.free_at = std::max(sg.free_at, n);
+                }
+                sg.free_at = std::max(sg.free_at, sg.merge_at);
+                segs.push_back(std::move(sg));
+                prev = r;
+            }
+        };
         if (win) {
             for (int64_t n = ((gp.min_iter + check_every - 1) / check_every) * check_every; n <= T; n += check_every)
                 win_checks.push_back(n);
             if (win_checks.empty() || win_checks.back() != T) win_checks.push_back(T);
-            for (int64_t n : win_checks) {
-                const int64_t r3[3] = {rowsA(n), rowsB(n), rowsU(n)};
-                for (int q = 0; q < 3; ++q) {
-                    if (r3[q] <= 1) continue;
-                    Snap& sn = snaps[r3[q]];
-                    sn.last_use = std::max(sn.last_use, n);
-                    if (q < 2) sn.need_s2 = true;
-                }
-            }
-            // most buffers alive at once: snapshot r lives from row r to its last check
+            plan_segments();
+            // most arrays alive at once: a segment lives from its cut row to the last check that needs it
             double peak = 0.0;
-            for (const auto& kv : snaps) {
+            for (const Seg& at : segs) {
                 double live = 0.0;
-                for (const auto& kw : snaps)
-                    if (kw.first <= kv.first && kw.second.last_use >= kv.first) live += kw.second.need_s2 ? 2.0 : 1.0;
+                for (const Seg& q : segs)
+                    if (q.r1 <= at.r1 && q.free_at >= at.r1) live += q.need_s2 ? 2.0 : 1.0;
                 peak = std::max(peak, live);
             }
-            if ((peak * (snap32 ? 0.5 : 1.0) + 2.0) * (double)M * (double)K * 8.0 > (double)gp.trace_budget_bytes) {
-                win = false; snaps.clear();
+            // + the running pair, the window-A pair and the two temporaries of a check, all fp64
+            if ((peak * (snap32 ? 0.5 : 1.0) + 6.0) * (double)M * (double)K * 8.0 > (double)gp.trace_budget_bytes) {
+                win = false; segs.clear();
             }
         }
+        DevBuf<double> winA1, winA2, winB1, winB2;      // window-A sums (folded), per-check temporaries
+        DevBuf<const void*> seg_ptrs;
 
         // ---- a chain's life in three steps, each on whatever stream h->st currently is ----
         auto start_chain = [&](int c, SweepArgs& a) -> std::unique_ptr<Chain> {
@@ -872,7 +909,7 @@ int cdl_gibbs_run(cdl_handle h, const double* Config, int32_t K, const double* P
             ch.part_d.alloc(tgrid * 4); ch.part_u.alloc(tgrid * 8);
             ch.ticket.alloc(1); ch.ticket.zero(h->st);
             ch.work.alloc(2); ch.work.zero(h->st);
-            ch.stats_work.alloc((size_t)d.n_cb); ch.stats_work.zero(h->st);
+            ch.stats_work.alloc((size_t)d.n_cb + 1); ch.stats_work.zero(h->st);       // + the statistic kernels' ticket
             ch.tab_g.alloc((size_t)N);
             ch.dev.scal = ch.scal.p; ch.dev.l1 = ch.l1.p; ch.dev.l1c = ch.l1c.p; ch.dev.mask = ch.mask.p;
             ch.dev.z = ch.z.p; ch.dev.sab = ch.sab.p;
@@ -887,6 +924,7 @@ int cdl_gibbs_run(cdl_handle h, const double* Config, int32_t K, const double* P
             ch.dev.el_l1 = ch.el_l1.p; ch.dev.el_l1c = ch.el_l1c.p; ch.dev.sd1 = ch.sd1.p;
             ch.dev.work = ch.work.p;
             ch.dev.stats_work = ch.stats_work.p;
+            ch.dev.stats_ticket = ch.stats_work.p + d.n_cb;
             ch.chg_ctl.alloc(4); ch.chg_ctl.zero(h->st);
             ch.dev.chg_ctl = ch.chg_ctl.p; ch.dev.chg_list = nullptr; ch.dev.chg_old = nullptr;
             if (a.incremental) {
@@ -923,7 +961,7 @@ int cdl_gibbs_run(cdl_handle h, const double* Config, int32_t K, const double* P
             if (element) launch_el_init(h->donor, a, ch.dev, h->st);
             return chp;
         };
-        const void* win_burn_s1 = nullptr;      // windows mode: snapshot at row ceil(it * buin_frac) - 1 of the final it
+        bool win_burn_ready = false;            // windows mode: winB1 holds the sum over the burn-in rows of the final it
         auto finish_chain = [&](Chain& ch, SweepArgs& a, int64_t it_final, double frac) {
             const int64_t itf = it_final;
             if (exact) frac = geweke_fraction(h, ch, itf, gcounts);
@@ -951,7 +989,10 @@ int cdl_gibbs_run(cdl_handle h, const double* Config, int32_t K, const double* P
             // posterior means (:645-653)
             ch.prob_mean.alloc((size_t)(M * K));
             if (exact) launch_col_means_d(ch.prob_all.p, M * K, r0, r1, ch.prob_mean.p, h->st);
-            else if (win) launch_window_mean(ch.prob_acc.p, win_burn_s1, snap32, M * K, 1.0 / (double)(r1 - r0), ch.prob_mean.p, h->st);
+            else if (win) {
+                if (!win_burn_ready) throw Error(CDL_ERR_STATE, "windowed stop rule: burn-in sums missing");
+                launch_window_mean(winB1.p, nullptr, false, M * K, 1.0 / (double)(r1 - r0), ch.prob_mean.p, h->st);
+            }
             else {
                 // accumulator holds the sum over rows [n_buin_planned, T]
                 CDL_CUDA(cudaMemcpyAsync(ch.prob_mean.p, ch.prob_acc.p, sizeof(double) * (size_t)(M * K),
@@ -994,7 +1035,7 @@ int cdl_gibbs_run(cdl_handle h, const double* Config, int32_t K, const double* P
                            h->world == 1 && !rp && !element && gp.incremental_stats != 1 && small_path_fits(d, K, gp.wise) &&
                            per_chain_bytes * gp.n_chain <= (double)gp.trace_budget_bytes &&
                            (exact || !win);    // without the trace the stop rule needs the window snapshots (three-kernel path)
-        if (small) { win = false; snaps.clear(); a.incremental = 0; }
+        if (small) { win = false; segs.clear(); a.incremental = 0; }
         const bool concurrent = concurrent_ok && !win;     // the windowed stop rule runs one chain at a time
         if (h->cells_layout == CDL_CELLS_SMALL && !small)
             throw Error(CDL_ERR_UNSUPPORTED, "the small-donor path does not apply (size, replay, sharding, element or incremental mode)");
@@ -1053,10 +1094,35 @@ int cdl_gibbs_run(cdl_handle h, const double* Config, int32_t K, const double* P
                 Chain& ch = *chp;
                 int64_t it_final = T;
                 double frac = NAN;
-                if (win && c > 0)       // every chain walks the same snapshot schedule
-                    for (auto& kv : snaps) kv.second.release();
+                if (win) {              // every chain walks the same segment schedule
+                    plan_segments();
+                    const size_t cols = (size_t)(M * K);
+                    if (!winA1.p) { winA1.alloc(cols); winA2.alloc(cols); winB1.alloc(cols); winB2.alloc(cols); seg_ptrs.alloc(2 * segs.size() + 4); }
+                    winA1.zero(h->st); winA2.zero(h->st);
+                }
                 size_t next_check = 0;
-                win_burn_s1 = nullptr;
+                win_burn_ready = false;
+                // sum of the stored segments whose rows lie after `from_row`, plus the running pair -> winB1 (and winB2)
+                auto sum_after = [&](int64_t from_row, bool squares) {
+                    std::vector<const void*> p1, p2;
+                    for (const Seg& q : segs) {
+                        if (!q.stored || q.r0 < from_row) continue;
+                        p1.push_back(snap32 ? (const void*)q.f1.p : (const void*)q.d1.p);
+                        if (squares) {
+                            if (!q.need_s2) throw Error(CDL_ERR_STATE, "windowed stop rule: a segment lacks its squares");
+                            p2.push_back(snap32 ? (const void*)q.f2.p : (const void*)q.d2.p);
+                        }
+                    }
+                    std::vector<const void*> all(p1);
+                    all.insert(all.end(), p2.begin(), p2.end());
+                    if (!all.empty()) {
+                        CDL_CUDA(cudaMemcpyAsync(seg_ptrs.p, all.data(), sizeof(void*) * all.size(), cudaMemcpyHostToDevice, h->st));
+                        CDL_CUDA(cudaStreamSynchronize(h->st));      // `all` is a stack vector
+                    }
+                    launch_segment_sum(seg_ptrs.p, (int)p1.size(), snap32, false, ch.prob_acc.p, M * K, winB1.p, h->st);
+                    if (squares) launch_segment_sum(seg_ptrs.p + p1.size(), (int)p2.size(), snap32, true, ch.prob_sq.p, M * K, winB2.p, h->st);
+                };
+                size_t next_seg = 0;
                 for (int64_t it = 2; it <= T; ++it) {
                     if (win) { ch.dev.prob_acc = ch.prob_acc.p; ch.dev.prob_sq = ch.prob_sq.p; }
                     else ch.dev.prob_acc = (!exact && it >= n_buin_planned) ? ch.prob_acc.p : nullptr;
@@ -1069,36 +1135,34 @@ int cdl_gibbs_run(cdl_handle h, const double* Config, int32_t K, const double* P
                         notify(gp.chain_offset + c, it, NAN);
                     }
                     if (!win) continue;
-                    auto sn = snaps.find(it);
-                    if (sn != snaps.end()) {           // the sums over rows 1..it, kept for a later window
-                        const size_t nb = sizeof(double) * (size_t)(M * K);
-                        if (snap32) {
-                            sn->second.f1.alloc((size_t)(M * K));
-                            launch_to_float(ch.prob_acc.p, sn->second.f1.p, M * K, h->st);
-                            if (sn->second.need_s2) {
-                                sn->second.f2.alloc((size_t)(M * K));
-                                launch_to_float(ch.prob_sq.p, sn->second.f2.p, M * K, h->st);
-                            }
+                    if (next_seg < segs.size() && segs[next_seg].r1 == it) {
+                        // a cut row: the running sums become the segment (previous cut, it] and start again from zero
+                        Seg& sg = segs[next_seg++];
+                        const size_t cols = (size_t)(M * K);
+                        if (sg.free_at == 0) {          // rows no window of any check covers: just start again from zero
+                            launch_segment_store(ch.prob_acc.p, ch.prob_sq.p, nullptr, nullptr, snap32, M * K, h->st);
+                        } else if (snap32) {
+                            sg.f1.alloc(cols);
+                            if (sg.need_s2) sg.f2.alloc(cols);
+                            launch_segment_store(ch.prob_acc.p, ch.prob_sq.p, sg.f1.p, sg.need_s2 ? sg.f2.p : nullptr, true, M * K, h->st);
                         } else {
-                            sn->second.s1.alloc((size_t)(M * K));
-                            CDL_CUDA(cudaMemcpyAsync(sn->second.s1.p, ch.prob_acc.p, nb, cudaMemcpyDeviceToDevice, h->st));
-                            if (sn->second.need_s2) {
-                                sn->second.s2.alloc((size_t)(M * K));
-                                CDL_CUDA(cudaMemcpyAsync(sn->second.s2.p, ch.prob_sq.p, nb, cudaMemcpyDeviceToDevice, h->st));
-                            }
+                            sg.d1.alloc(cols);
+                            if (sg.need_s2) sg.d2.alloc(cols);
+                            launch_segment_store(ch.prob_acc.p, ch.prob_sq.p, sg.d1.p, sg.need_s2 ? sg.d2.p : nullptr, false, M * K, h->st);
                         }
+                        sg.stored = sg.free_at != 0;
                     }
                     if (next_check < win_checks.size() && it == win_checks[next_check]) {
                         ++next_check;
-                        auto buf = [&](int64_t r, bool sq) -> const void* {
-                            if (r <= 1) return nullptr;
-                            const Snap& q = snaps.at(r);
-                            if (snap32) return sq ? (const void*)q.f2.p : (const void*)q.f1.p;
-                            return sq ? (const void*)q.s2.p : (const void*)q.s1.p;
-                        };
-                        launch_geweke_sums(buf(rowsA(it), false), buf(rowsA(it), true), buf(rowsB(it), false),
-                                           buf(rowsB(it), true), snap32, ch.prob_acc.p, ch.prob_sq.p, M * K, it, gcounts.p,
-                                           h->st);
+                        // window A only grows: fold the segments it has reached into the fp64 pair
+                        for (Seg& q : segs) {
+                            if (!q.stored || q.merged || q.r1 > rowsA(it)) continue;
+                            launch_segment_add(winA1.p, snap32 ? (const void*)q.f1.p : (const void*)q.d1.p, snap32, false, M * K, h->st);
+                            launch_segment_add(winA2.p, snap32 ? (const void*)q.f2.p : (const void*)q.d2.p, snap32, true, M * K, h->st);
+                            q.merged = true;
+                        }
+                        sum_after(rowsB(it), true);
+                        launch_geweke_sums(winA1.p, winA2.p, nullptr, nullptr, false, winB1.p, winB2.p, M * K, it, gcounts.p, h->st);
                         if (h->world > 1) allreduce_u64(h, gcounts.p, 2);
                         unsigned long long cnt[2];
                         gcounts.download(cnt, 2, h->st);
@@ -1107,11 +1171,12 @@ int cdl_gibbs_run(cdl_handle h, const double* Config, int32_t K, const double* P
                         if (rule) notify(gp.chain_offset + c, it, frac);
                         if ((rule && frac > 0.995) || it == T) {
                             it_final = it;
-                            win_burn_s1 = buf(rowsU(it), false);
+                            sum_after(rowsU(it), false);          // burn-in rows ceil(it * buin_frac) .. it (:604,645)
+                            win_burn_ready = true;
                             break;
                         }
-                        for (auto& kv : snaps)         // snapshots no later check needs
-                            if (kv.second.last_use <= it) kv.second.release();
+                        for (Seg& q : segs)            // segments no later check needs
+                            if (q.stored && q.free_at <= it) { q.release(); q.stored = false; }
                     }
                 }
                 finish_chain(ch, a, it_final, frac);
@@ -1467,8 +1532,8 @@ int cdl_bench_sweeps(cdl_handle h, int32_t warmup, int32_t n, float* ms_total, f
                     ++q.epoch;
                     ch.dev.sab = q.arena + (size_t)(q.epoch & 1ull) * q.table_elems;
                     a.p2p = &q;
-                    launch_stats(h->donor, a, ch.dev, h->sm_count, h->st);
-                    launch_signal(q, h->st);
+                    if (a.incremental) launch_stats_incremental(h->donor, a, ch.dev, h->sm_count, h->st);
+                    else launch_stats(h->donor, a, ch.dev, h->sm_count, h->st);
                 } else {
                     a.p2p = nullptr;
                     if (a.incremental) launch_stats_incremental(h->donor, a, ch.dev, h->sm_count, h->st);

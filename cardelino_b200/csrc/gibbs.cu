@@ -202,7 +202,40 @@ __global__ void k_build_tab(int64_t N, int n_tab, const double* __restrict__ l1,
 }
 
 // ------------------------------------------------------------------------------------------------
+// "This rank's statistic table of sweep `epoch` is complete": release-store of the sweep number into every peer's flag
+// array (cell-sharded runs over peer memory; n_peer = 0 otherwise).  The table was written with device-scope atomics
+// into this GPU's memory and peers read it through NVLink from this GPU's L2, the coherence point, so a system-scope
+// fence + release store is sufficient.  Issued by the LAST CTA of whichever kernel completed the table (the last CTA
+// has seen every other CTA's ticket, each taken after a device-scope fence) -- no separate signalling kernel.
+struct PeerSignal {
+    int n_peer, my_rank;
+    unsigned long long* peer_flags[MAX_PEERS];   // flag arrays in the peers' memory
+    unsigned long long epoch;
+};
+__device__ __forceinline__ void signal_peers(const PeerSignal& S) {
+    if ((int)threadIdx.x < S.n_peer) {
+        __threadfence_system();
+        st_release_sys_u64(S.peer_flags[threadIdx.x] + S.my_rank, S.epoch);
+    }
+}
+// every CTA calls this once, after its last write to the table; true in the CTA that finishes last
+__device__ __forceinline__ bool last_cta_done(unsigned int* ticket) {
+    __shared__ bool s_last;
+    __threadfence();          // EVERY thread: its reductions (fire-and-forget RED) must have been performed at L2 before
+    __syncthreads();          // the CTA takes its ticket -- a barrier alone does not wait for outstanding REDs
+    if (threadIdx.x == 0) {
+        __threadfence();
+        const unsigned int t = atomicAdd(ticket, 1u);
+        s_last = (t == gridDim.x - 1);
+        if (s_last) { __threadfence(); *ticket = 0u; }
+    }
+    __syncthreads();
+    return s_last;
+}
+
 struct StatsParams {
+    PeerSignal sig;
+    unsigned int* done_ticket;      // zero between launches
     const uint32_t* seggrp;
     const uint16_t* flush;
     const uint16_t* vc;
@@ -416,6 +449,7 @@ __global__ void __launch_bounds__(STATS_THREADS, 2) k_stats_stream(const StatsPa
         }
     }
     if (!waited) pdl_wait();
+    if (P.sig.n_peer > 0 && last_cta_done(P.done_ticket)) signal_peers(P.sig);
 }
 
 // The same statistics for LARGE shards (many segments per warp): the warps pull whole variant segments (or
@@ -507,6 +541,7 @@ __global__ void __launch_bounds__(STATS_THREADS, 2) k_stats_units(const StatsPar
             if (since) stats_flush<KP>(bins, lane, P.K, sab_row);
         }
     }
+    if (P.sig.n_peer > 0 && last_cta_done(P.done_ticket)) signal_peers(P.sig);
 }
 
 // ---- incremental statistics (opt-in) ---------------------------------------------------------------
@@ -518,44 +553,52 @@ __global__ void __launch_bounds__(STATS_THREADS, 2) k_stats_units(const StatsPar
 struct IncrParams {
     const uint32_t* rowgrp; const void* vidx; const uint16_t* ca; const uint16_t* cb; int vidx32;
     const uint8_t* z; const uint32_t* chg_list; const uint8_t* chg_old;
-    unsigned int* ctl;            // [0] changed count, [1] need full pass (out), [2] force full pass, [3] full passes
+    unsigned int* ctl;            // [0] changed count, [1] need full pass (out), [2] force full flag, [3] full passes
     unsigned long long* sab;
     int64_t M, NK;
     int K;
     unsigned int threshold;
+    unsigned int* done_ticket;
+    PeerSignal sig;
 };
 
+// One kernel: the update itself, then -- in the CTA that finishes last -- the hand-over: either the table is complete
+// (re-arm the control words, tell the peers) or the full pass has to run (clear the table for it, raise its flag).
 __global__ void __launch_bounds__(256) k_stats_incr(const IncrParams P) {
+    pdl_enter();
     const unsigned int count = P.ctl[0];
     const bool full = P.ctl[2] != 0 || count > P.threshold;
-    if (blockIdx.x == 0 && threadIdx.x == 0) P.ctl[1] = full ? 1u : 0u;
-    if (full) return;
-    const int lane = threadIdx.x & 31;
-    const int64_t warp = (blockIdx.x * (int64_t)blockDim.x + threadIdx.x) >> 5;
-    const int64_t nwarps = ((int64_t)gridDim.x * blockDim.x) >> 5;
-    for (int64_t q = warp; q < (int64_t)count; q += nwarps) {
-        const int64_t j = P.chg_list[q];
-        const int zo = P.chg_old[q], zn = P.z[j];
-        const int64_t e0 = (int64_t)P.rowgrp[j] * GROUP, e1 = (int64_t)P.rowgrp[j + 1] * GROUP;
-        for (int64_t e = e0 + lane; e < e1; e += 32) {
-            const unsigned long long a = P.ca[e], b = P.cb[e];
-            if ((a | b) == 0) continue;
-            const int64_t v = P.vidx32 ? reinterpret_cast<const uint32_t*>(P.vidx)[e]
-                                       : reinterpret_cast<const uint16_t*>(P.vidx)[e];
-            const unsigned long long w = a | (b << 32);
-            atomicAdd(&P.sab[v * P.K + zn], w);
-            atomicAdd(&P.sab[v * P.K + zo], 0ull - w);     // the packed halves borrow and repay: net exact
+    if (!full) {
+        const int lane = threadIdx.x & 31;
+        const int64_t warp = (blockIdx.x * (int64_t)blockDim.x + threadIdx.x) >> 5;
+        const int64_t nwarps = ((int64_t)gridDim.x * blockDim.x) >> 5;
+        for (int64_t q = warp; q < (int64_t)count; q += nwarps) {
+            const int64_t j = P.chg_list[q];
+            const int zo = P.chg_old[q], zn = P.z[j];
+            const int64_t e0 = (int64_t)P.rowgrp[j] * GROUP, e1 = (int64_t)P.rowgrp[j + 1] * GROUP;
+            for (int64_t e = e0 + lane; e < e1; e += 32) {
+                const unsigned long long a = P.ca[e], b = P.cb[e];
+                if ((a | b) == 0) continue;
+                const int64_t v = P.vidx32 ? reinterpret_cast<const uint32_t*>(P.vidx)[e]
+                                           : reinterpret_cast<const uint16_t*>(P.vidx)[e];
+                const unsigned long long w = a | (b << 32);
+                atomicAdd(&P.sab[v * P.K + zn], w);
+                atomicAdd(&P.sab[v * P.K + zo], 0ull - w);     // the packed halves borrow and repay: net exact
+            }
         }
     }
-}
-
-// between the incremental update and the full pass: clear the table if the full pass is going to run, and
-// re-arm the control words for the next sweep
-__global__ void k_stats_prepare_full(unsigned int* ctl, unsigned long long* sab, int64_t NK) {
-    const bool full = ctl[1] != 0;
-    const int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
-    if (full && i < NK) sab[i] = 0ull;
-    if (i == 0) { ctl[0] = 0u; ctl[2] = 0u; if (full) ctl[3] += 1u; }
+    if (!last_cta_done(P.done_ticket)) return;
+    // every other CTA has read the control words and finished its updates
+    if (full) {
+        for (int64_t i = threadIdx.x; i < P.NK; i += blockDim.x) P.sab[i] = 0ull;     // the full pass accumulates from zero
+    } else {
+        signal_peers(P.sig);
+    }
+    if (threadIdx.x == 0) {
+        P.ctl[1] = full ? 1u : 0u;
+        P.ctl[0] = 0u; P.ctl[2] = 0u;
+        if (full) P.ctl[3] += 1u;
+    }
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -656,7 +699,7 @@ __global__ void __launch_bounds__(TABLE_THREADS) k_table(const TableParams P) {
     double ll = 0.0;
     uint32_t bitk = 0;
     if (P.n_peer > 0) {
-        // fused all-reduce: wait until every peer has published its table of this sweep (k_signal on the peer,
+        // fused all-reduce: wait until every peer has published its table of this sweep (last CTA of the peer's statistic kernel,
         // after its k_stats), then read the peers' tables straight over NVLink below.  Bounded spin: a peer
         // that died must not hang this GPU.
         if ((int)threadIdx.x < P.n_peer) {
@@ -838,22 +881,6 @@ __global__ void __launch_bounds__(TABLE_THREADS) k_table(const TableParams P) {
                                           : beta_from_gammas(s_gam[2 * VPB + 2], s_gam[2 * VPB + 3]);
         P.scal[SC_RELAX] = rr;
         P.relax_all[row + 1] = rr;
-    }
-}
-
-// After this rank's k_stats: tell every peer that the table of sweep `epoch` in this rank's arena is complete.
-// The table was written with device-scope atomics into this GPU's memory; peers read it through NVLink from
-// this GPU's L2, the coherence point, so a system-scope fence + release store of the flag is sufficient.
-struct SignalParams {
-    int n_peer, my_rank;
-    unsigned long long* peer_flags[MAX_PEERS];   // flag arrays in the peers' memory
-    unsigned long long epoch;
-};
-__global__ void k_signal(const SignalParams P) {
-    pdl_enter();
-    if ((int)threadIdx.x < P.n_peer) {
-        __threadfence_system();
-        st_release_sys_u64(P.peer_flags[threadIdx.x] + P.my_rank, P.epoch);
     }
 }
 
@@ -1069,15 +1096,25 @@ std::vector<int> stats_plan(const std::vector<int64_t>& groups_per_cb, int ctas)
     return plan;
 }
 
+static PeerSignal peer_signal(const SweepArgs& a) {
+    PeerSignal S{};
+    if (a.p2p && a.p2p->n_peer > 0) {
+        const P2PState& q = *a.p2p;
+        S.n_peer = q.n_peer; S.my_rank = q.my_rank; S.epoch = q.epoch;
+        for (int r = 0; r < q.n_peer; ++r) S.peer_flags[r] = q.peer_flags[r];
+    }
+    return S;
+}
+
 void launch_stats_incremental(const Donor& d, const SweepArgs& a, ChainDev& c, int sm_count, cudaStream_t st) {
     IncrParams P{};
     P.rowgrp = d.c_rowgrp; P.vidx = d.c_vidx; P.ca = d.c_a; P.cb = d.c_b; P.vidx32 = d.vidx32 ? 1 : 0;
     P.z = c.z; P.chg_list = c.chg_list; P.chg_old = c.chg_old; P.ctl = c.chg_ctl; P.sab = c.sab;
     P.M = d.M; P.NK = d.N * a.K; P.K = a.K;
     P.threshold = (unsigned int)std::max<int64_t>(1, d.M / 32);      // ~3 % of the cells
-    k_stats_incr<<<(unsigned)(sm_count * 4), 256, 0, st>>>(P);
-    CDL_CUDA(cudaGetLastError());
-    k_stats_prepare_full<<<(unsigned)((P.NK + 255) / 256), 256, 0, st>>>(c.chg_ctl, c.sab, P.NK);
+    P.done_ticket = c.stats_ticket;
+    P.sig = peer_signal(a);
+    launch_dep(k_stats_incr, dim3((unsigned)(sm_count * 4)), dim3(256), 0, st, P);
     CDL_CUDA(cudaGetLastError());
     launch_stats(d, a, c, sm_count, st);             // exits at once unless the full pass is needed
 }
@@ -1085,6 +1122,8 @@ void launch_stats_incremental(const Donor& d, const SweepArgs& a, ChainDev& c, i
 void launch_stats(const Donor& d, const SweepArgs& a, ChainDev& c, int sm_count, cudaStream_t st) {
     // c.sab is zero on entry: k_table clears it while it reads it (and the chain starts with a zeroed table)
     StatsParams P{};
+    P.sig = peer_signal(a);
+    P.done_ticket = c.stats_ticket;
     P.run_flag = a.incremental ? c.chg_ctl + 1 : nullptr;
     P.seggrp = d.v_seggrp; P.flush = d.v_flush; P.vc = d.v_cell; P.va = d.v_a; P.vb = d.v_b; P.z = c.z; P.sab = c.sab;
     P.N = d.N; P.M = d.M; P.K = a.K; P.n_cb = d.n_cb;
@@ -1135,14 +1174,6 @@ void launch_stats(const Donor& d, const SweepArgs& a, ChainDev& c, int sm_count,
         case 16: launch_stats_t<16>(P, grid, smem, units, st); break;
         default: launch_stats_t<32>(P, grid, smem, units, st); break;
     }
-    CDL_CUDA(cudaGetLastError());
-}
-
-void launch_signal(const P2PState& q, cudaStream_t st) {
-    SignalParams P{};
-    P.n_peer = q.n_peer; P.my_rank = q.my_rank; P.epoch = q.epoch;
-    for (int r = 0; r < q.n_peer; ++r) P.peer_flags[r] = q.peer_flags[r];
-    launch_dep(k_signal, dim3(1), dim3(32), 0, st, P);
     CDL_CUDA(cudaGetLastError());
 }
 

@@ -133,6 +133,7 @@ struct ChainDev {
     unsigned long long* dbg_sab;  // test hook: [N*K] copy of the local statistic table taken before the table kernel, or nullptr
     unsigned int* work;  // dynamic work-item counter of k_cells_sell
     unsigned int* stats_work;    // [n_cb] dynamic unit counters of k_stats
+    unsigned int* stats_ticket;  // "last CTA" ticket of the statistic kernels (zero between launches)
 };
 
 enum {
@@ -142,7 +143,7 @@ enum {
 
 // Peer-memory exchange of the statistic table between the ranks of one NVSwitch box (cell-sharded runs).
 // Every rank owns an arena [2][table_elems] (double-buffered by sweep parity) that the chain's k_stats fills,
-// and a flag array [world] that the PEERS write.  k_signal publishes "sweep `epoch` complete" into the peers'
+// and a flag array [world] that the PEERS write.  the last CTA of the statistic kernel publishes "sweep `epoch` complete" into the peers'
 // flag arrays; k_table waits for all flags and sums the peers' tables while it reads them -- the all-reduce
 // is fused into the table kernel, no NCCL call per sweep.
 struct P2PState {
@@ -190,7 +191,6 @@ void launch_cells_sell(const Donor& d, const SweepArgs& a, ChainDev& c, int sm_c
 void launch_stats(const Donor& d, const SweepArgs& a, ChainDev& c, int sm_count, cudaStream_t st);
 void launch_stats_incremental(const Donor& d, const SweepArgs& a, ChainDev& c, int sm_count, cudaStream_t st);
 void launch_table(const Donor& d, const SweepArgs& a, ChainDev& c, cudaStream_t st);
-void launch_signal(const P2PState& q, cudaStream_t st);
 // small donors: whole sweeps of all chains in one launch (small.cu)
 struct cdl_small_run {
     int n_chain, chain0, min_iter, exact;
@@ -214,7 +214,13 @@ void launch_geweke(const double* prob_all, int64_t cols, int64_t n_rows, unsigne
 void launch_geweke_sums(const void* s1a, const void* s2a, const void* s1b, const void* s2b, bool fp32, const double* s1n,
                         const double* s2n, int64_t cols, int64_t n_rows, unsigned long long* counts2, cudaStream_t st);
 void launch_window_mean(const double* s1n, const void* s1u, bool fp32, int64_t n, double inv, double* out, cudaStream_t st);
-void launch_to_float(const double* x, float* y, int64_t n, cudaStream_t st);
+// segment sums of the streaming stop rule: out = (S)acc then acc = 0 (out may be null: only clear); dst += src;
+// out = extra + sum of the listed arrays.  Segment arrays are fp32 or fp64 (`fp32`), everything else fp64.
+void launch_segment_store(double* acc1, double* acc2, void* out1, void* out2, bool fp32, int64_t n, cudaStream_t st);
+// (`squares`: the array holds sums of squares, which fp32 segments keep as their square root)
+void launch_segment_add(double* dst, const void* src, bool fp32, bool squares, int64_t n, cudaStream_t st);
+void launch_segment_sum(const void* const* ptrs, int count, bool fp32, bool squares, const double* extra, int64_t n,
+                        double* out, cudaStream_t st);
 // R/clone_id.R:624-644 on the device trace (prob_all [T][cell][clone], Config_all [T][i + k*N]); rows n_buin..it (1-based)
 void relabel_trace(double* prob_all, uint8_t* config_all, int64_t M, int64_t N, int K, int64_t n_buin, int64_t it,
                    cudaStream_t st);

@@ -299,10 +299,6 @@ __global__ void k_geweke_sums(const S* __restrict__ s1a, const S* __restrict__ s
     }
 }
 
-__global__ void k_to_float(const double* __restrict__ x, float* __restrict__ y, int64_t n) {
-    const int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
-    if (i < n) y[i] = (float)x[i];
-}
 
 // out = (s1n - s1u) * inv: column means over the rows after snapshot u
 template <typename S>
@@ -491,9 +487,68 @@ void launch_geweke_sums(const void* s1a, const void* s2a, const void* s1b, const
     CDL_CUDA(cudaGetLastError());
 }
 
-void launch_to_float(const double* x, float* y, int64_t n, cudaStream_t st) {
+// ---- segment sums of the streaming stop rule (api.cu): store + clear, fold, add up ----
+// fp32 segments keep the sum of SQUARES as its square root: a clone column that sits at 1e-25 has squares of 1e-50,
+// far below fp32's range (1e-38, denormals to 1e-45) but well inside the 1e-50 floor of the Z statistic's
+// denominator, where the verdict is decided; the root is representable down to sums of 1e-76.
+namespace {
+template <typename S> struct SegCodec {
+    static __device__ __forceinline__ S put(double v, bool sq) { return (S)(sq ? sqrt(v) : v); }
+    static __device__ __forceinline__ double get(S v, bool sq) { const double d = (double)v; return sq ? d * d : d; }
+};
+template <> struct SegCodec<double> {
+    static __device__ __forceinline__ double put(double v, bool) { return v; }
+    static __device__ __forceinline__ double get(double v, bool) { return v; }
+};
+template <typename S>
+__global__ void k_segment_store(double* __restrict__ acc1, double* __restrict__ acc2, S* __restrict__ out1,
+                                S* __restrict__ out2, int64_t n) {
+    const int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    if (out1) out1[i] = SegCodec<S>::put(acc1[i], false);
+    if (out2) out2[i] = SegCodec<S>::put(acc2[i], true);
+    acc1[i] = 0.0;
+    acc2[i] = 0.0;
+}
+template <typename S>
+__global__ void k_segment_add(double* __restrict__ dst, const S* __restrict__ src, bool squares, int64_t n) {
+    const int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+    if (i < n) dst[i] += SegCodec<S>::get(src[i], squares);
+}
+// out = extra + sum of `count` segment arrays, in list order (fixed rounding)
+template <typename S>
+__global__ void k_segment_sum(const void* const* __restrict__ ptrs, int count, bool squares,
+                              const double* __restrict__ extra, int64_t n, double* __restrict__ out) {
+    const int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    double s = 0.0;
+    for (int q = 0; q < count; ++q) s += SegCodec<S>::get(reinterpret_cast<const S*>(ptrs[q])[i], squares);
+    out[i] = s + (extra ? extra[i] : 0.0);
+}
+}  // namespace
+
+void launch_segment_store(double* acc1, double* acc2, void* out1, void* out2, bool fp32, int64_t n, cudaStream_t st) {
     if (n <= 0) return;
-    k_to_float<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(x, y, n);
+    const unsigned grid = (unsigned)((n + 255) / 256);
+    if (fp32) k_segment_store<float><<<grid, 256, 0, st>>>(acc1, acc2, (float*)out1, (float*)out2, n);
+    else k_segment_store<double><<<grid, 256, 0, st>>>(acc1, acc2, (double*)out1, (double*)out2, n);
+    CDL_CUDA(cudaGetLastError());
+}
+
+void launch_segment_add(double* dst, const void* src, bool fp32, bool squares, int64_t n, cudaStream_t st) {
+    if (n <= 0 || !src) return;
+    const unsigned grid = (unsigned)((n + 255) / 256);
+    if (fp32) k_segment_add<float><<<grid, 256, 0, st>>>(dst, (const float*)src, squares, n);
+    else k_segment_add<double><<<grid, 256, 0, st>>>(dst, (const double*)src, squares, n);
+    CDL_CUDA(cudaGetLastError());
+}
+
+void launch_segment_sum(const void* const* ptrs, int count, bool fp32, bool squares, const double* extra, int64_t n,
+                        double* out, cudaStream_t st) {
+    if (n <= 0) return;
+    const unsigned grid = (unsigned)((n + 255) / 256);
+    if (fp32) k_segment_sum<float><<<grid, 256, 0, st>>>(ptrs, count, squares, extra, n, out);
+    else k_segment_sum<double><<<grid, 256, 0, st>>>(ptrs, count, squares, extra, n, out);
     CDL_CUDA(cudaGetLastError());
 }
 

@@ -92,6 +92,7 @@ def clone_id_chain_groups(A, D, Config, n_chain, run_chains=None, **kwargs):
     _ci = importlib.import_module(__package__ + ".clone_id")     # the module (the package re-exports the function)
     rank, world = dist.get_rank(), dist.get_world_size()
     first, count = chain_groups(n_chain, world)[rank]
+    kwargs.setdefault("light", True)       # only prob / Config_prob / scalars are gathered: skip the big traces
     if run_chains is None:
         def run_chains(first, count):
             if count == 0:

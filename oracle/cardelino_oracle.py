@@ -194,10 +194,31 @@ def geweke_z(X, first=0.1, last=0.5):
         return (mA - mB) / np.sqrt(vA + vB + 1e-50)
 
 
-def geweke_z_running_sums(X, first=0.1, last=0.5):
-    """The same Z from RUNNING column sums of x and x^2, as the streaming mode of the CUDA path evaluates it
-    (csrc/post.cu::k_geweke_sums): prefix sums over rows 1..r snapshotted at r = floor(first n) and
-    r = ceil(last n) - 1, and current at r = n.  One-pass variances clamped at 0."""
+def geweke_z_segment_sums(X, first=0.1, last=0.5, storage=np.float64):
+    """The same Z from column sums of x and x^2 over SEGMENTS of rows, as the streaming mode of the CUDA path evaluates
+    it (csrc/api.cu, csrc/post.cu::k_geweke_sums): the rows are cut at floor(first n) and ceil(last n) - 1, each
+    window is the SUM of its segments (kept in `storage` precision: fp64, or fp32 like the default snapshots), and
+    the variances are one-pass, clamped at 0.  Nothing is ever obtained as a difference of two prefix sums."""
+    X = np.asarray(X, dtype=np.float64)
+    n = X.shape[0]
+    nA = math.floor(first * n)
+    rb = math.ceil(last * n) - 1
+    nB = n - rb
+    seg = lambda lo, hi: (X[lo:hi].sum(axis=0).astype(storage).astype(np.float64),
+                          (X[lo:hi] ** 2).sum(axis=0).astype(storage).astype(np.float64))
+    a1, a2 = seg(0, nA)
+    b1, b2 = seg(rb, n)
+    with np.errstate(invalid="ignore", divide="ignore"):
+        mA, mB = a1 / nA, b1 / nB
+        vA = np.maximum(a2 - nA * mA * mA, 0.0) / (nA - 1)
+        vB = np.maximum(b2 - nB * mB * mB, 0.0) / (nA - 1)
+        return (mA - mB) / np.sqrt(vA + vB + 1e-50)
+
+
+def geweke_z_prefix_differences(X, first=0.1, last=0.5):
+    """Round 1's form, kept as the counter-example: window B as a DIFFERENCE of prefix sums.  A column that held large
+    values in rows before the window (a cell that visited the clone early) and tiny ones inside it loses the
+    window's sums to cancellation; tests/test_oracle.py shows the verdicts that flip."""
     X = np.asarray(X, dtype=np.float64)
     n = X.shape[0]
     s1, s2 = np.cumsum(X, axis=0), np.cumsum(X * X, axis=0)

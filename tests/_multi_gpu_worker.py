@@ -32,10 +32,15 @@ def main():
     D.init_comm(h)
     h.synth_generate(N, M, K, cfg, cov, 99, cell_offset=lo, M_local=hi - lo)
     out = {}
-    for mode in ("nccl", "peer"):
-        h.set_exchange_mode(mode)
-        h.gibbs_run(cfg, None, min_iter=T, max_iter=T, seed=4, keep_prob_all=1, keep_assign_all=1)
-        assert h.exchange_is_peer() == (mode == "peer"), mode
+    full_passes = {}
+    # nccl: all-reduce per sweep (full statistic pass); peer: tables summed over peer memory inside the table kernel,
+    # incremental statistics on (the library default); peer_full: the same exchange with the full pass every sweep
+    for mode in ("nccl", "peer", "peer_full"):
+        h.set_exchange_mode(mode.split("_")[0])
+        h.gibbs_run(cfg, None, min_iter=T, max_iter=T, seed=4, keep_prob_all=1, keep_assign_all=1,
+                    incremental_stats=0 if mode == "peer_full" else -1)
+        assert h.exchange_is_peer() == (mode != "nccl"), mode
+        full_passes[mode] = h.incremental_full_passes()
         z = torch.from_numpy(h.fetch("assign_all").astype(np.int32)).cuda()          # T x M_local
         parts = [torch.empty((T, b - a), dtype=torch.int32, device="cuda") for a, b in D.shard_bounds(M, world)]
         dist.all_gather(parts, z)
@@ -58,7 +63,10 @@ def main():
             if not np.allclose(out[mode]["ll"], ref["ll"], rtol=1e-12, atol=0):
                 ok = False
                 msg.append("%s/logLik differs" % mode)
-        print(json.dumps({"ok": ok, "world": world, "messages": msg}))
+        if not (1 <= full_passes["peer"] <= T - 1) or full_passes["nccl"] != 0 or full_passes["peer_full"] != 0:
+            ok = False
+            msg.append("incremental statistics did not run as expected: %s" % full_passes)
+        print(json.dumps({"ok": ok, "world": world, "messages": msg, "full_statistic_passes": full_passes}))
     # ---- the stop rule on a sharded chain: the Geweke counts are summed over the ranks, so every rank stops at the
     # iteration the unsharded chain stops at -- with the whole trace (exact mode) and from the running sums and
     # window snapshots of streaming mode ----

@@ -167,3 +167,26 @@ def test_sparse_counts_from_sparse_and_mtx(tmp_path):
         cb.SparseCounts.from_sparse(sp.csc_matrix(DP + (DP > 0)), sp.csc_matrix(DP))
     with pytest.raises(ValueError, match="same size"):
         cb.SparseCounts.from_sparse(sp.csc_matrix(AD[:-1]), sp.csc_matrix(DP))
+
+
+def test_clone_id_accepts_compact_counts_up_to_the_device():
+    """clone_id(SparseCounts, None, ...) -- the documented large-donor input form -- passes the host-side checks of
+    R/clone_id.R:84-96 (round 1 raised TypeError in the integer check) and only stops where the device is needed."""
+    import scipy.sparse as sp
+    import cardelino_b200 as cb
+    rng = np.random.default_rng(0)
+    D = sp.random(30, 40, density=0.3, random_state=1, data_rvs=lambda n: rng.integers(1, 9, n).astype(float)).tocsc()
+    A = D.copy()
+    A.data = np.floor(A.data * rng.random(A.nnz))
+    counts = cb.SparseCounts.from_sparse(A, D)
+    try:
+        import torch
+        has_gpu = torch.cuda.is_available()
+    except Exception:
+        has_gpu = False
+    if has_gpu:
+        out = cb.clone_id(counts, None, n_clone=3, min_iter=5, max_iter=5, verbose=False)
+        assert out["prob"].shape == (40, 3)
+    else:
+        with pytest.raises(cb.CdlError):
+            cb.clone_id(counts, None, n_clone=3, min_iter=5, max_iter=5, verbose=False)

@@ -110,10 +110,10 @@ def test_geweke_matches_definition():
     assert np.all(np.isnan(O.geweke_z(X[:5])))            # first window empty -> NaN like R
 
 
-def test_geweke_from_running_sums_is_the_same_test():
-    """Streaming mode evaluates the stop rule from running sums and window snapshots: the
-    Z values agree with the definition to rounding, hence the same |Z| <= 2 decisions, on probability-like
-    traces including saturated (constant 1 / 0) and tiny-valued columns, first row zero as in prob_all."""
+def test_geweke_from_segment_sums_is_the_same_test():
+    """Streaming mode evaluates the stop rule from segment sums: the Z values agree with the
+    definition to rounding, hence the same |Z| <= 2 decisions, on probability-like traces including saturated
+    (constant 1 / 0) and tiny-valued columns, first row zero as in prob_all -- with fp64 and with fp32 segments."""
     rng = np.random.default_rng(11)
     n = 700
     X = np.column_stack([rng.random(n), 0.9 + 0.1 * rng.random(n), np.ones(n), np.zeros(n),
@@ -121,9 +121,34 @@ def test_geweke_from_running_sums_is_the_same_test():
                          np.r_[rng.random(n // 2), 0.2 * rng.random(n - n // 2)]])       # last column: a chain that drifts
     X[0] = 0.0
     for rows in (n, 500, 300):
-        Z, Zs = O.geweke_z(X[:rows]), O.geweke_z_running_sums(X[:rows])
-        assert np.allclose(Z, Zs, rtol=1e-6, atol=1e-9), (Z, Zs)
-        assert np.array_equal(np.abs(Z) <= 2, np.abs(Zs) <= 2)
+        Z = O.geweke_z(X[:rows])
+        for storage, rtol in ((np.float64, 1e-6), (np.float32, 1e-3)):
+            Zs = O.geweke_z_segment_sums(X[:rows], storage=storage)
+            assert np.allclose(Z, Zs, rtol=rtol, atol=1e-9), (Z, Zs)
+            assert np.array_equal(np.abs(Z) <= 2, np.abs(Zs) <= 2)
+
+
+def test_segment_sums_survive_what_prefix_differences_lose():
+    """Why the windows are sums of segments and not differences of running sums (round 1, advisor finding): columns
+    that held an ordinary probability in a few early rows OUTSIDE both windows and sit at 1e-10 .. 1e-30 afterwards.
+    The prefix-difference form loses window B's sums behind the early rows and flips verdicts; the segment form
+    reproduces the two-pass definition."""
+    rng = np.random.default_rng(0)
+    n, cols = 20, 20000
+    X = np.zeros((n, cols))
+    hot = rng.random(cols) < 0.2
+    for r in range(1, n):
+        eps = 10.0 ** (-rng.uniform(3, 30, cols)) * (0.05 if r > 3 else 1.0)
+        X[r] = np.where(hot, 1 - eps, eps)
+        if r < 4:
+            early = rng.random(cols) < 0.3
+            X[r] = np.where(early, rng.random(cols), X[r])
+    exact = np.abs(O.geweke_z(X)) <= 2
+    seg = np.abs(O.geweke_z_segment_sums(X)) <= 2
+    seg32 = np.abs(O.geweke_z_segment_sums(X, storage=np.float32)) <= 2
+    pre = np.abs(O.geweke_z_prefix_differences(X)) <= 2
+    assert (exact != seg).mean() == 0 and (exact != seg32).mean() < 1e-3
+    assert (exact != pre).mean() > 5e-3                  # the old form flips a visible share of the verdicts
 
 
 def test_deviance_ic():
