@@ -18,7 +18,11 @@
 #include "internal.h"
 #include "cells.cuh"
 #include <cub/cub.cuh>
+#include <algorithm>
 #include <cstdlib>
+#include <functional>
+#include <queue>
+#include <vector>
 
 namespace cdl {
 
@@ -29,6 +33,7 @@ constexpr int SELL_SIGMA = 4096;   // sorting window in cells (multiple of 32)
 
 struct SellParams {
     CellsParams c;
+    const int32_t* assign;       // one-round shards: slice of every (block, warp) [grid * warps], -1 = none; else nullptr
     const uint32_t* slice_off;   // [n_slices + 1] group-slot offsets
     const uint32_t* perm;        // [n_slices * 32] local cell id of each lane, 0xffffffff = empty lane
     const uint4* v8;
@@ -191,6 +196,14 @@ __global__ void __launch_bounds__(SELL_THREADS, 1) k_cells_sell(const SellParams
     // (strided by the grid, not blocked by CTA: slices are sorted by length inside 4096-cell windows, and on a shard
     // that is done in one round a CTA holding 28 neighbours would be all-long or all-short)
     unsigned int s_u = (threadIdx.x >> 5) * gridDim.x + blockIdx.x;
+    // A shard that is done in ONE round (at most one slice per warp: 27 per SM on a 1/8 shard of C4) has no dynamic part
+    // to even things out, and the four sub-partitions of an SM each share their fp64 pipe among their own warps: the
+    // host has dealt the slices to the (SM, sub-partition) bins so that every bin carries the same number of group
+    // slots (launch_cells_sell: longest-first into the least loaded bin), this warp's slice is assign[block][warp].
+    if (!SPLIT && P.assign) {
+        const int32_t sl = P.assign[blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5)];
+        s_u = sl < 0 ? 0xffffffffu : (unsigned int)sl;
+    }
     int64_t s = 0, g0 = 0, g1 = 0;
     int part = 0;
     uint32_t jl = 0xffffffffu;
@@ -245,6 +258,7 @@ __global__ void __launch_bounds__(SELL_THREADS, 1) k_cells_sell(const SellParams
     }
     const int K = C.K;
     auto advance = [&]() {
+        if (!SPLIT && P.assign) { have = false; return; }          // one round: nothing left to pull
         unsigned int u = 0;
         if (lane == 0) u = atomicAdd(P.work, 1u);
         s_u = __shfl_sync(0xffffffffu, u, 0) + n_static;
@@ -540,8 +554,9 @@ void launch_sell_v(const Donor& d, const SellParams& P, bool smem_tab, size_t sm
 }  // namespace
 
 void donor_free_sell(Donor& d) {
-    cudaFree(d.s_off); cudaFree(d.s_perm); cudaFree(d.s_vidx); cudaFree(d.s_a); cudaFree(d.s_b);
-    d.s_off = nullptr; d.s_perm = nullptr; d.s_vidx = nullptr; d.s_a = nullptr; d.s_b = nullptr;
+    cudaFree(d.s_off); cudaFree(d.s_perm); cudaFree(d.s_vidx); cudaFree(d.s_a); cudaFree(d.s_b); cudaFree(d.s_assign);
+    d.s_off = nullptr; d.s_perm = nullptr; d.s_vidx = nullptr; d.s_a = nullptr; d.s_b = nullptr; d.s_assign = nullptr;
+    d.s_assign_grid = 0; d.s_assign_warps = 0;
     d.s_slices = 0; d.s_slots = 0;
 }
 
@@ -662,6 +677,46 @@ void launch_cells_sell(const Donor& d, const SweepArgs& a, ChainDev& c, int sm_c
     const int threads = d.vidx32 ? 512 : (shape == 1 ? ((KP == 16 && a.skip0) ? 896 : 768) : 512);
     const int64_t max_useful = (d.s_slices + threads / 32 - 1) / (threads / 32);
     if (grid > max_useful) grid = std::max<int64_t>(max_useful, 1);
+    // one-round shard: balanced static assignment of the slices to the (SM, sub-partition) bins, cached with the layout
+    P.assign = nullptr;
+    if (P.parts == 1) {
+        const int warps = sell_warps(d.s_slices, (int)grid, threads / 32);
+        if (d.s_slices <= grid * warps && d.s_slices > 0) {
+            Donor& dm = const_cast<Donor&>(d);
+            if (!dm.s_assign || dm.s_assign_grid != (int)grid || dm.s_assign_warps != warps) {
+                std::vector<uint32_t> off((size_t)d.s_slices + 1);
+                CDL_CUDA(cudaMemcpyAsync(off.data(), d.s_off, 4 * off.size(), cudaMemcpyDeviceToHost, st));
+                CDL_CUDA(cudaStreamSynchronize(st));
+                std::vector<int32_t> order((size_t)d.s_slices);
+                for (int64_t q = 0; q < d.s_slices; ++q) order[(size_t)q] = (int32_t)q;
+                std::stable_sort(order.begin(), order.end(), [&](int32_t x, int32_t y) {
+                    return off[(size_t)x + 1] - off[(size_t)x] > off[(size_t)y + 1] - off[(size_t)y];
+                });
+                // longest slice first, each into the least loaded bin that still has a free warp
+                const int bins = (int)grid * 4;
+                std::vector<int> used((size_t)bins, 0);
+                typedef std::pair<uint64_t, int> LB;                 // (group slots so far, bin)
+                std::priority_queue<LB, std::vector<LB>, std::greater<LB>> heap;
+                auto cap = [&](int bin) { const int q = bin & 3; return (warps - q + 3) / 4; };
+                for (int b = 0; b < bins; ++b) if (cap(b) > 0) heap.push(LB(0, b));
+                std::vector<int32_t> assign((size_t)grid * warps, -1);
+                for (int32_t sl : order) {
+                    LB top = heap.top(); heap.pop();
+                    const int bin = top.second, k = used[(size_t)bin]++;
+                    assign[(size_t)(bin >> 2) * warps + (size_t)((bin & 3) + 4 * k)] = sl;
+                    top.first += off[(size_t)sl + 1] - off[(size_t)sl];
+                    if (used[(size_t)bin] < cap(bin)) heap.push(top);
+                }
+                cudaFree(dm.s_assign);
+                dm.s_assign = nullptr;
+                CDL_CUDA(cudaMalloc(&dm.s_assign, sizeof(int32_t) * assign.size()));
+                CDL_CUDA(cudaMemcpyAsync(dm.s_assign, assign.data(), sizeof(int32_t) * assign.size(), cudaMemcpyHostToDevice, st));
+                CDL_CUDA(cudaStreamSynchronize(st));
+                dm.s_assign_grid = (int)grid; dm.s_assign_warps = warps;
+            }
+            P.assign = d.s_assign;
+        }
+    }
     switch (KP) {
         case 4: launch_sell_v<4>(d, P, smem_tab, smem, (int)grid, shape, a.skip0 != 0, st); break;
         case 8: launch_sell_v<8>(d, P, smem_tab, smem, (int)grid, shape, a.skip0 != 0, st); break;

@@ -77,6 +77,8 @@ struct Donor {
     void* s_vidx = nullptr;
     uint16_t* s_a = nullptr;
     uint16_t* s_b = nullptr;
+    int32_t* s_assign = nullptr;        // one-round shards: slice of every (CTA, warp) of the cell kernel, built on first use
+    int s_assign_grid = 0, s_assign_warps = 0;
     int64_t s_slices = 0, s_slots = 0;
     int s_hi_shift = 0;                 // odd entries of a slice group store variant id << s_hi_shift (2 when N <= 13824)
     double W_log = 0.0;                 // local shard's sum(lchoose(D, A))
