@@ -74,7 +74,7 @@ struct Chain {
     DevBuf<double> prob_sq;              // running sum of squares beside prob_acc (streaming Geweke windows)
     DevBuf<uint32_t> mask;
     DevBuf<uint8_t> z, config_all, assign_all;
-    DevBuf<unsigned long long> sab, part_u;
+    DevBuf<unsigned long long> sab, part_u, sab_zero;
     DevBuf<unsigned int> ticket, work, sell_tickets, stats_work, chg_ctl;
     DevBuf<uint32_t> chg_list;
     DevBuf<uint8_t> chg_old;
@@ -389,21 +389,19 @@ void one_sweep(cdl_handle h, Chain& ch, SweepArgs& a, uint32_t it, const cdl_rep
     if (h->p2p_active) {
         // statistic table into this sweep's half of the peer-visible arena; publish; the table kernel sums
         // the peers' halves while it reads them (no collective call).  With incremental statistics the previous
-        // table kernel has left this rank's previous table in this half, for k_stats_incr to correct.
+        // table kernel has left this rank's previous table in this half, for the statistic kernel to correct.
         P2PState& q = h->p2p;
         ++q.epoch;
         ch.dev.sab = q.arena + (size_t)(q.epoch & 1ull) * q.table_elems;
         a.p2p = &q;
         // (the last CTA of the kernel that completes the table publishes it to the peers)
-        if (a.incremental) { launch_stats_incremental(h->donor, a, ch.dev, h->sm_count, h->st); h->launches += 1; }
-        else launch_stats(h->donor, a, ch.dev, h->sm_count, h->st);
+        launch_stats(h->donor, a, ch.dev, h->sm_count, h->st);     // incremental correction or the full pass
         capture();
         launch_table(h->donor, a, ch.dev, h->st);
         h->launches += 3;
     } else {
         a.p2p = nullptr;
-        if (a.incremental) { launch_stats_incremental(h->donor, a, ch.dev, h->sm_count, h->st); h->launches += 1; }
-        else launch_stats(h->donor, a, ch.dev, h->sm_count, h->st);
+        launch_stats(h->donor, a, ch.dev, h->sm_count, h->st);     // incremental correction or the full pass
         capture();
         allreduce_u64(h, ch.dev.sab, (size_t)(a.N * a.K));
         launch_table(h->donor, a, ch.dev, h->st);
@@ -927,9 +925,12 @@ int cdl_gibbs_run(cdl_handle h, const double* Config, int32_t K, const double* P
             ch.dev.stats_ticket = ch.stats_work.p + d.n_cb;
             ch.chg_ctl.alloc(4); ch.chg_ctl.zero(h->st);
             ch.dev.chg_ctl = ch.chg_ctl.p; ch.dev.chg_list = nullptr; ch.dev.chg_old = nullptr;
+            ch.dev.sab_zero = nullptr;
             if (a.incremental) {
                 ch.chg_list.alloc((size_t)M); ch.chg_old.alloc((size_t)M);
                 ch.dev.chg_list = ch.chg_list.p; ch.dev.chg_old = ch.chg_old.p;
+                ch.sab_zero.alloc((size_t)(N * K)); ch.sab_zero.zero(h->st);
+                ch.dev.sab_zero = ch.sab_zero.p;
                 const unsigned int ctl0[4] = {0u, 1u, 1u, 0u};          // the first sweep takes the full pass
                 ch.chg_ctl.upload(ctl0, 4, h->st);
                 CDL_CUDA(cudaStreamSynchronize(h->st));
@@ -1532,12 +1533,10 @@ int cdl_bench_sweeps(cdl_handle h, int32_t warmup, int32_t n, float* ms_total, f
                     ++q.epoch;
                     ch.dev.sab = q.arena + (size_t)(q.epoch & 1ull) * q.table_elems;
                     a.p2p = &q;
-                    if (a.incremental) launch_stats_incremental(h->donor, a, ch.dev, h->sm_count, h->st);
-                    else launch_stats(h->donor, a, ch.dev, h->sm_count, h->st);
+                    launch_stats(h->donor, a, ch.dev, h->sm_count, h->st);
                 } else {
                     a.p2p = nullptr;
-                    if (a.incremental) launch_stats_incremental(h->donor, a, ch.dev, h->sm_count, h->st);
-                    else launch_stats(h->donor, a, ch.dev, h->sm_count, h->st);
+                    launch_stats(h->donor, a, ch.dev, h->sm_count, h->st);
                     allreduce_u64(h, ch.dev.sab, (size_t)(a.N * a.K));
                 }
                 CDL_CUDA(cudaEventRecord(ev[2], h->st));

@@ -246,11 +246,68 @@ struct StatsParams {
     int64_t N, M;
     int K;
     int n_cb;             // cell blocks
-    const unsigned int* run_flag;   // incremental mode: the full pass runs only if *run_flag != 0 (else nullptr)
+    // incremental statistics (else ctl == nullptr): the same launch first tries to CORRECT the previous sweep's table
+    // from the cells whose label changed (rows layout below); only above the threshold does it run the full pass --
+    // into `zbuf`, a table that is all zero at rest, because the carried table cannot be cleared grid-wide first
+    unsigned int* ctl;              // [0] changed count, [1] 1 if the last sweep took the full pass, [2] force-full flag, [3] full passes
+    unsigned int threshold;
+    unsigned long long* zbuf;       // [N*K]
+    const uint32_t* rowgrp; const void* vidx; const uint16_t* ca; const uint16_t* cb; int vidx32;
+    const uint32_t* chg_list; const uint8_t* chg_old;
     const int* plan;      // [grid + 2 * n_cb]: home block of each CTA, first CTA and CTA count of each block
     int chunks_per_warp;  // k_stats_units: work units per segment (k_stats_stream takes one static range per warp)
     unsigned int* work;   // [n_cb] unit counters of k_stats_units; zero on entry (k_table's last block re-arms them)
 };
+
+
+// SA / SB are integer sums over the cells of each label, so when few labels changed in a sweep the table of the
+// previous sweep is corrected instead of recomputed: for every changed cell (list built by the cell kernel, one
+// atomic per warp), move its row's counts from the old label's column to the new one.  Exact (integers): the chain is
+// bit-identical to the full pass.  Returns true if the table is done (the caller returns), false if the full pass has
+// to run -- then into P.zbuf.
+__device__ __forceinline__ bool stats_try_incremental(const StatsParams& P) {
+    const unsigned int count = P.ctl[0];
+    if (P.ctl[2] != 0 || count > P.threshold) return false;
+    const int lane = threadIdx.x & 31;
+    const int64_t warp = (blockIdx.x * (int64_t)blockDim.x + threadIdx.x) >> 5;
+    const int64_t nwarps = ((int64_t)gridDim.x * blockDim.x) >> 5;
+    for (int64_t q = warp; q < (int64_t)count; q += nwarps) {
+        const int64_t j = P.chg_list[q];
+        const int zo = P.chg_old[q], zn = P.z[j];
+        const int64_t e0 = (int64_t)P.rowgrp[j] * GROUP, e1 = (int64_t)P.rowgrp[j + 1] * GROUP;
+        for (int64_t e = e0 + lane; e < e1; e += 32) {
+            const unsigned long long a = P.ca[e], b = P.cb[e];
+            if ((a | b) == 0) continue;
+            const int64_t v = P.vidx32 ? reinterpret_cast<const uint32_t*>(P.vidx)[e]
+                                       : reinterpret_cast<const uint16_t*>(P.vidx)[e];
+            const unsigned long long w = a | (b << 32);
+            atomicAdd(&P.sab[v * P.K + zn], w);
+            atomicAdd(&P.sab[v * P.K + zo], 0ull - w);     // the packed halves borrow and repay: net exact
+        }
+    }
+    if (last_cta_done(P.done_ticket)) {
+        // every other CTA has read the control words and finished its updates
+        if (threadIdx.x == 0) { P.ctl[0] = 0u; P.ctl[1] = 0u; P.ctl[2] = 0u; }
+        signal_peers(P.sig);
+    }
+    return true;
+}
+// end of the full pass: the CTA that finishes last hands the table over
+__device__ __forceinline__ void stats_finish_full(const StatsParams& P) {
+    if (!P.ctl && P.sig.n_peer == 0) return;
+    if (!last_cta_done(P.done_ticket)) return;
+    if (P.ctl) {
+        const int64_t NK = P.N * P.K;
+        for (int64_t i = threadIdx.x; i < NK; i += blockDim.x) {       // the table moves to where the sweep expects it;
+            P.sab[i] = P.zbuf[i];                                      // zbuf is all zero again for the next full pass
+            P.zbuf[i] = 0ull;
+        }
+        if (threadIdx.x == 0) { P.ctl[0] = 0u; P.ctl[1] = 1u; P.ctl[2] = 0u; P.ctl[3] += 1u; }
+        __threadfence();          // every thread's part of the copy is performed before anyone signals
+        __syncthreads();
+    }
+    signal_peers(P.sig);
+}
 
 // One 8-entry group of a variant segment into the lane-private clone bins.  A and B share one 32-bit bin
 // (A low half, B high half): one 32-bit shared load + store per entry.  The caller flushes the bins before
@@ -316,6 +373,14 @@ template <int KP>
 __global__ void __launch_bounds__(STATS_THREADS, 2) k_stats_stream(const StatsParams P) {
     pdl_trigger();
     extern __shared__ __align__(16) unsigned char smem_raw[];
+    bool waited = false;
+    unsigned long long* const sab = P.ctl ? P.zbuf : P.sab;      // where a full pass accumulates
+    if (P.ctl) {
+        // incremental statistics: the control words come from the cell kernel, so wait first; most sweeps end here
+        pdl_wait();
+        waited = true;
+        if (stats_try_incremental(P)) return;
+    }
     uint32_t* s_bins = reinterpret_cast<uint32_t*>(smem_raw);                  // [WARPS][KP][32]
     uint8_t* s_z = smem_raw + sizeof(uint32_t) * STATS_WARPS * KP * 32;        // [cells of the staged block]
     const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
@@ -340,7 +405,6 @@ __global__ void __launch_bounds__(STATS_THREADS, 2) k_stats_stream(const StatsPa
     // Everything up to pdl_wait() reads only the donor's layout (never written after the load), so under a
     // programmatic dependent launch it runs while the cell kernel is still draining: the warp's range, the
     // search for its first segment and the loads of its first 32 groups.
-    bool waited = false;
     for (; cb < P.n_cb; cb += cb_step) {
         const uint32_t* sg = P.seggrp + (int64_t)cb * P.N;       // sg[0..N]: group offsets of the block's segments
         const uint16_t* fl = P.flush + (int64_t)cb * P.N;
@@ -385,7 +449,6 @@ __global__ void __launch_bounds__(STATS_THREADS, 2) k_stats_stream(const StatsPa
         if (!waited) {
             pdl_wait();
             waited = true;
-            if (P.run_flag && *P.run_flag == 0) return;   // the incremental update already produced this sweep's table
         }
         __syncthreads();                       // all warps are done with the previous block's labels
         {
@@ -423,7 +486,7 @@ __global__ void __launch_bounds__(STATS_THREADS, 2) k_stats_stream(const StatsPa
                 const int64_t gi = min(nbase + lane, nsend - 1);
                 cn = ld_stream(c8 + gi); an = ld_stream(a8 + gi); bn = ld_stream(b8 + gi);
             }
-            unsigned long long* sab_row = P.sab + i * P.K;
+            unsigned long long* sab_row = sab + i * P.K;
             if (cur + lane < send) {
                 if (flush_every) stats_group(cw, aw, bw, s_z, bins + lane);
                 else {
@@ -449,7 +512,7 @@ __global__ void __launch_bounds__(STATS_THREADS, 2) k_stats_stream(const StatsPa
         }
     }
     if (!waited) pdl_wait();
-    if (P.sig.n_peer > 0 && last_cta_done(P.done_ticket)) signal_peers(P.sig);
+    stats_finish_full(P);
 }
 
 // The same statistics for LARGE shards (many segments per warp): the warps pull whole variant segments (or
@@ -461,7 +524,8 @@ __global__ void __launch_bounds__(STATS_THREADS, 2) k_stats_stream(const StatsPa
 template <int KP>
 __global__ void __launch_bounds__(STATS_THREADS, 2) k_stats_units(const StatsParams P) {
     pdl_enter();
-    if (P.run_flag && *P.run_flag == 0) return;      // the incremental update already produced this sweep's table
+    if (P.ctl && stats_try_incremental(P)) return;   // incremental statistics: most sweeps end here
+    unsigned long long* const sab = P.ctl ? P.zbuf : P.sab;      // where a full pass accumulates
     extern __shared__ __align__(16) unsigned char smem_raw[];
     uint32_t* s_bins = reinterpret_cast<uint32_t*>(smem_raw);                  // [WARPS][KP][32]
     uint8_t* s_z = smem_raw + sizeof(uint32_t) * STATS_WARPS * KP * 32;        // [cells of the staged block]
@@ -510,7 +574,7 @@ __global__ void __launch_bounds__(STATS_THREADS, 2) k_stats_units(const StatsPar
             }
             if (g0 >= g1) continue;
             const int flush_every = P.flush[seg];
-            unsigned long long* sab_row = P.sab + i * P.K;
+            unsigned long long* sab_row = sab + i * P.K;
             if (flush_every == 0) {
                 for (int64_t g = g0 + lane; g < g1; g += 32) {
                     const uint4 cw = ld_stream(c8 + g), aw = ld_stream(a8 + g), bw = ld_stream(b8 + g);
@@ -541,64 +605,7 @@ __global__ void __launch_bounds__(STATS_THREADS, 2) k_stats_units(const StatsPar
             if (since) stats_flush<KP>(bins, lane, P.K, sab_row);
         }
     }
-    if (P.sig.n_peer > 0 && last_cta_done(P.done_ticket)) signal_peers(P.sig);
-}
-
-// ---- incremental statistics (opt-in) ---------------------------------------------------------------
-// SA / SB are integer sums over the cells of each label, so when few labels changed in a sweep the table of the
-// previous sweep can be corrected instead of recomputed: for every changed cell, move its row's counts from the
-// old label's column to the new one.  Exact (integers), so the chain is bit-identical to the full pass.  A
-// converged chain on an informative donor changes a handful of labels per sweep; early sweeps, or donors whose
-// cells stay uncertain, exceed the threshold and take the full pass (k_stats_* with run_flag set).
-struct IncrParams {
-    const uint32_t* rowgrp; const void* vidx; const uint16_t* ca; const uint16_t* cb; int vidx32;
-    const uint8_t* z; const uint32_t* chg_list; const uint8_t* chg_old;
-    unsigned int* ctl;            // [0] changed count, [1] need full pass (out), [2] force full flag, [3] full passes
-    unsigned long long* sab;
-    int64_t M, NK;
-    int K;
-    unsigned int threshold;
-    unsigned int* done_ticket;
-    PeerSignal sig;
-};
-
-// One kernel: the update itself, then -- in the CTA that finishes last -- the hand-over: either the table is complete
-// (re-arm the control words, tell the peers) or the full pass has to run (clear the table for it, raise its flag).
-__global__ void __launch_bounds__(256) k_stats_incr(const IncrParams P) {
-    pdl_enter();
-    const unsigned int count = P.ctl[0];
-    const bool full = P.ctl[2] != 0 || count > P.threshold;
-    if (!full) {
-        const int lane = threadIdx.x & 31;
-        const int64_t warp = (blockIdx.x * (int64_t)blockDim.x + threadIdx.x) >> 5;
-        const int64_t nwarps = ((int64_t)gridDim.x * blockDim.x) >> 5;
-        for (int64_t q = warp; q < (int64_t)count; q += nwarps) {
-            const int64_t j = P.chg_list[q];
-            const int zo = P.chg_old[q], zn = P.z[j];
-            const int64_t e0 = (int64_t)P.rowgrp[j] * GROUP, e1 = (int64_t)P.rowgrp[j + 1] * GROUP;
-            for (int64_t e = e0 + lane; e < e1; e += 32) {
-                const unsigned long long a = P.ca[e], b = P.cb[e];
-                if ((a | b) == 0) continue;
-                const int64_t v = P.vidx32 ? reinterpret_cast<const uint32_t*>(P.vidx)[e]
-                                           : reinterpret_cast<const uint16_t*>(P.vidx)[e];
-                const unsigned long long w = a | (b << 32);
-                atomicAdd(&P.sab[v * P.K + zn], w);
-                atomicAdd(&P.sab[v * P.K + zo], 0ull - w);     // the packed halves borrow and repay: net exact
-            }
-        }
-    }
-    if (!last_cta_done(P.done_ticket)) return;
-    // every other CTA has read the control words and finished its updates
-    if (full) {
-        for (int64_t i = threadIdx.x; i < P.NK; i += blockDim.x) P.sab[i] = 0ull;     // the full pass accumulates from zero
-    } else {
-        signal_peers(P.sig);
-    }
-    if (threadIdx.x == 0) {
-        P.ctl[1] = full ? 1u : 0u;
-        P.ctl[0] = 0u; P.ctl[2] = 0u;
-        if (full) P.ctl[3] += 1u;
-    }
+    stats_finish_full(P);
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -1106,25 +1113,19 @@ static PeerSignal peer_signal(const SweepArgs& a) {
     return S;
 }
 
-void launch_stats_incremental(const Donor& d, const SweepArgs& a, ChainDev& c, int sm_count, cudaStream_t st) {
-    IncrParams P{};
-    P.rowgrp = d.c_rowgrp; P.vidx = d.c_vidx; P.ca = d.c_a; P.cb = d.c_b; P.vidx32 = d.vidx32 ? 1 : 0;
-    P.z = c.z; P.chg_list = c.chg_list; P.chg_old = c.chg_old; P.ctl = c.chg_ctl; P.sab = c.sab;
-    P.M = d.M; P.NK = d.N * a.K; P.K = a.K;
-    P.threshold = (unsigned int)std::max<int64_t>(1, d.M / 32);      // ~3 % of the cells
-    P.done_ticket = c.stats_ticket;
-    P.sig = peer_signal(a);
-    launch_dep(k_stats_incr, dim3((unsigned)(sm_count * 4)), dim3(256), 0, st, P);
-    CDL_CUDA(cudaGetLastError());
-    launch_stats(d, a, c, sm_count, st);             // exits at once unless the full pass is needed
-}
-
 void launch_stats(const Donor& d, const SweepArgs& a, ChainDev& c, int sm_count, cudaStream_t st) {
     // c.sab is zero on entry: k_table clears it while it reads it (and the chain starts with a zeroed table)
     StatsParams P{};
     P.sig = peer_signal(a);
     P.done_ticket = c.stats_ticket;
-    P.run_flag = a.incremental ? c.chg_ctl + 1 : nullptr;
+    P.ctl = nullptr;
+    if (a.incremental) {
+        P.ctl = c.chg_ctl;
+        P.threshold = (unsigned int)std::max<int64_t>(1, d.M / 32);      // ~3 % of the cells
+        P.zbuf = c.sab_zero;
+        P.rowgrp = d.c_rowgrp; P.vidx = d.c_vidx; P.ca = d.c_a; P.cb = d.c_b; P.vidx32 = d.vidx32 ? 1 : 0;
+        P.chg_list = c.chg_list; P.chg_old = c.chg_old;
+    }
     P.seggrp = d.v_seggrp; P.flush = d.v_flush; P.vc = d.v_cell; P.va = d.v_a; P.vb = d.v_b; P.z = c.z; P.sab = c.sab;
     P.N = d.N; P.M = d.M; P.K = a.K; P.n_cb = d.n_cb;
     const int KP = pad_k(a.K);

@@ -130,7 +130,8 @@ struct ChainDev {
     // incremental statistics (opt-in): cells whose label changed in this sweep, and control words
     uint32_t* chg_list;          // [M] local cell ids
     uint8_t* chg_old;            // [M] their previous labels
-    unsigned int* chg_ctl;       // [4]: changed count, need-full-pass flag, force-full flag, full passes done
+    unsigned int* chg_ctl;       // [4]: changed count, last sweep took the full pass, force-full flag, full passes done
+    unsigned long long* sab_zero;// [N*K] all zero at rest: where a full pass accumulates when the table is carried over
     unsigned long long* dbg_s34;  // test hook (cdl_debug_capture): [2N + 5] Beta shape increments of the last sweep, or nullptr
     unsigned long long* dbg_sab;  // test hook: [N*K] copy of the local statistic table taken before the table kernel, or nullptr
     unsigned int* work;  // dynamic work-item counter of k_cells_sell
@@ -191,7 +192,6 @@ void launch_init_chain(const SweepArgs& a, ChainDev& c, cudaStream_t st);
 void launch_cells(const Donor& d, const SweepArgs& a, ChainDev& c, int sm_count, cudaStream_t st);
 void launch_cells_sell(const Donor& d, const SweepArgs& a, ChainDev& c, int sm_count, cudaStream_t st);
 void launch_stats(const Donor& d, const SweepArgs& a, ChainDev& c, int sm_count, cudaStream_t st);
-void launch_stats_incremental(const Donor& d, const SweepArgs& a, ChainDev& c, int sm_count, cudaStream_t st);
 void launch_table(const Donor& d, const SweepArgs& a, ChainDev& c, cudaStream_t st);
 // small donors: whole sweeps of all chains in one launch (small.cu)
 struct cdl_small_run {
