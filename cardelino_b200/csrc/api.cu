@@ -179,6 +179,10 @@ void allreduce_u64(cdl_handle h, unsigned long long* buf, size_t n) {
     if (h->world <= 1) return;
     nccl_check(h, h->nccl.AllReduce(buf, buf, n, NCCL_U64, NCCL_SUM, h->comm, h->st), "ncclAllReduce(u64)");
 }
+void allreduce_d(cdl_handle h, double* buf, size_t n) {
+    if (h->world <= 1) return;
+    nccl_check(h, h->nccl.AllReduce(buf, buf, n, NCCL_F64, NCCL_SUM, h->comm, h->st), "ncclAllReduce(f64)");
+}
 double allreduce_scalar_d(cdl_handle h, double v) {
     if (h->world <= 1) return v;
     DevBuf<double> b(1);
@@ -370,10 +374,14 @@ void one_sweep(cdl_handle h, Chain& ch, SweepArgs& a, uint32_t it, const cdl_rep
         a.rp_relax_next = (rp_dev->relax_rate && (int64_t)it < a.T) ? rp_dev->relax_rate + row + 1 : nullptr;
     }
     if (a.wise == 2) {
-        // wise = element: per-entry theta1 (element.cu); single GPU
+        // wise = element: per-entry theta1 (element.cu)
         a.p2p = nullptr;
         launch_el_cells(h->donor, a, ch.dev, h->st);
         launch_el_stats(h->donor, a, ch.dev, h->st);
+        // cell shards: the read sums and the per-(variant, clone) log-odds sums over all ranks (every rank receives the
+        // same bits, so the redundant table steps stay in lockstep)
+        allreduce_u64(h, ch.dev.sab, (size_t)(a.N * a.K));
+        allreduce_d(h, ch.dev.sd1, (size_t)(a.N * a.K));
         launch_table(h->donor, a, ch.dev, h->st);
         launch_el_theta(h->donor, a, ch.dev, h->st);
         h->launches += 4;
@@ -682,8 +690,6 @@ int cdl_gibbs_run(cdl_handle h, const double* Config, int32_t K, const double* P
         if (gp.wise != CDL_WISE_GLOBAL && gp.wise != CDL_WISE_VARIANT && gp.wise != CDL_WISE_ELEMENT)
             throw Error(CDL_ERR_INVALID, "Input wise mode: unknown, while only supporting: element, variant, global");
         const bool element = gp.wise == CDL_WISE_ELEMENT;
-        if (element && h->world > 1)
-            throw Error(CDL_ERR_UNSUPPORTED, "wise = \"element\" runs on one GPU (per-entry parameters are not sharded)");
         if (gp.max_iter < 2) throw Error(CDL_ERR_INVALID, "max_iter must be at least 2");
         if (gp.relax_Config && gp.relax_rate_fixed_set && (gp.relax_rate_fixed > 1 || gp.relax_rate_fixed < 0))
             throw Error(CDL_ERR_INVALID, "relax_rate_fixed needs to be NULL or in [0, 1].");
@@ -746,6 +752,19 @@ int cdl_gibbs_run(cdl_handle h, const double* Config, int32_t K, const double* P
             a.skip0 = (col0_zero && (!gp.relax_Config || gp.keep_base_clone)) ? 1 : 0;
         }
         a.W_log = allreduce_scalar_d(h, d.W_log);
+        a.el_offset = 0;
+        if (element && h->world > 1) {
+            // every rank's covered-entry count -> this rank's first global element index
+            std::vector<unsigned long long> cnt((size_t)h->world, 0ull);
+            cnt[(size_t)h->rank] = (unsigned long long)d.nnz;
+            DevBuf<unsigned long long> b((size_t)h->world);
+            b.upload(cnt.data(), cnt.size(), h->st);
+            allreduce_u64(h, b.p, cnt.size());
+            b.download(cnt.data(), cnt.size(), h->st);
+            unsigned long long tot = 0;
+            for (int r = 0; r < h->world; ++r) { if (r == h->rank) a.el_offset = (int64_t)tot; tot += cnt[(size_t)r]; }
+            if (tot >= (1ull << 32)) throw Error(CDL_ERR_UNSUPPORTED, "wise = \"element\": more than 2^32 covered entries");
+        }
         if (h->p2p_active) {
             // The all-reduce above is also the barrier that makes this safe: every rank has returned from its previous
             // run (its last table kernel, which reads the peers' arenas, is complete).  A run with incremental

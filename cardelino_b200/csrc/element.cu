@@ -6,7 +6,9 @@
 // log(1 - theta1) beside every count of the row layout), a per-entry Beta draw every sweep and an
 // iterations x nnz trace, so this path is meant for the small donors the mode is usable on; it is written for
 // clarity (one warp per cell on the row layout, fp64 atomics for the per-(variant, clone) log-odds table), not
-// tuned like the global / variant path.
+// tuned like the global / variant path.  On cell shards every rank owns the parameters of its own entries (prior1
+// matrix rows and theta1 trace columns are the rank's entries); the two N x K tables are all-reduced with NCCL
+// (api.cu::one_sweep) and the Philox index of an entry is its position in the whole donor.
 //
 //   k_el_cells   logLik with per-entry weights -> softmax -> categorical draw            (:470-497)
 //   k_el_stats   SA / SB (integer) and SD[i,k] = sum_{j: z_j = k} A ln th1_ij + B ln(1 - th1_ij)   (:525-528)
@@ -33,6 +35,7 @@ struct ElParams {
     const uint16_t* cb;
     const int64_t* elem0;      // [M+1] element index of each cell's first covered entry
     int64_t M, N, cell_offset, n_el;
+    int64_t el_offset;         // covered entries of the ranks before this one (cell shards)
     int K, vidx32;
     double* el_l1;             // [padded entries] ln theta1
     double* el_l1c;            //                  ln(1 - theta1)
@@ -127,7 +130,7 @@ __global__ void __launch_bounds__(EL_THREADS) k_el_theta(const ElParams P) {
                 double pa = P.prior1_mat ? P.prior1_mat[el] : P.prior1[0];
                 double pb = P.prior1_mat ? P.prior1_mat[P.n_el + el] : P.prior1[1];
                 if (!INIT && ((P.mask[el_variant(P, e)] >> zj) & 1u)) { pa += (double)a; pb += (double)b; }
-                PhiloxSeq s(P.key, P.chain, P.it, STREAM_THETA1, (uint32_t)el);
+                PhiloxSeq s(P.key, P.chain, P.it, STREAM_THETA1, (uint32_t)(P.el_offset + el));
                 th = beta_draw(pa, pb, s);
             }
             P.theta1_row[el] = th;
@@ -140,7 +143,7 @@ __global__ void __launch_bounds__(EL_THREADS) k_el_theta(const ElParams P) {
 ElParams el_params(const Donor& d, const SweepArgs& a, ChainDev& c) {
     ElParams P{};
     P.rowgrp = d.c_rowgrp; P.vidx = d.c_vidx; P.ca = d.c_a; P.cb = d.c_b; P.elem0 = d.c_elem0;
-    P.M = d.M; P.N = d.N; P.cell_offset = d.cell_offset; P.n_el = d.nnz; P.K = a.K; P.vidx32 = d.vidx32 ? 1 : 0;
+    P.M = d.M; P.N = d.N; P.cell_offset = d.cell_offset; P.n_el = d.nnz; P.el_offset = a.el_offset; P.K = a.K; P.vidx32 = d.vidx32 ? 1 : 0;
     P.el_l1 = c.el_l1; P.el_l1c = c.el_l1c; P.scal = c.scal; P.mask = c.mask;
     for (int k = 0; k < KMAX; ++k) P.logPsi[k] = a.logPsi[k];
     const int64_t row = (int64_t)a.it - 1;

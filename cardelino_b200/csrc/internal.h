@@ -183,6 +183,8 @@ struct SweepArgs {
     const double* rp_u_assign; const double* rp_u_config;
     const double* rp_theta0; const double* rp_theta1; const double* rp_relax_next;
     const P2PState* p2p;        // non-null: statistic tables are exchanged over peer memory
+    int64_t el_offset;          // wise = element on a cell shard: covered entries of the ranks before this one (Philox index of
+                                // an entry = its position in the WHOLE donor's cell-major order, so draws match any GPU count)
 };
 
 struct KernelTimes { float cells = 0, stats = 0, table = 0; };

@@ -91,6 +91,39 @@ def main():
             ok = False
             msg.append("streaming and exact mode stop at different iterations: %s vs %s" % (stop[0][:2], stop[1][:2]))
         print(json.dumps({"ok": ok, "world": world, "messages": msg, "stop": [stop[1][:3], stop[0][:3]]}))
+    # ---- wise = "element" on cell shards (R/clone_id.R:413-416,557-571): every rank owns the theta1 of its own entries, the
+    # two N x K tables are all-reduced, the Philox index of an entry is its position in the whole donor ----
+    Ne, Me, Ke, Te = 120, 6000, 4, 12
+    cfg_e = bench.make_config(Ne, Ke, seed=5)
+    lo_e, hi_e = D.shard_bounds(Me, world)[rank]
+    he = cb.Handle(local)
+    D.init_comm(he)
+    he.synth_generate(Ne, Me, Ke, cfg_e, 0.3, 77, cell_offset=lo_e, M_local=hi_e - lo_e)
+    he.gibbs_run(cfg_e, None, min_iter=Te, max_iter=Te, seed=9, keep_prob_all=1, keep_assign_all=1, wise="element")
+    mine = {"z": he.fetch("assign_all"), "cfg": he.fetch("Config_all"), "t0": he.fetch("theta_traces")[0],
+            "t1": he.fetch("theta_traces")[1], "prob": he.fetch("prob"), "ll": he.fetch("logLik")}
+    gathered = [None] * world
+    dist.all_gather_object(gathered, mine)
+    if rank == 0:
+        fe = cb.Handle(local)
+        fe.synth_generate(Ne, Me, Ke, cfg_e, 0.3, 77)
+        fe.gibbs_run(cfg_e, None, min_iter=Te, max_iter=Te, seed=9, keep_prob_all=1, keep_assign_all=1, wise="element")
+        t0r, t1r = fe.fetch("theta_traces")
+        checks = {
+            "labels": np.array_equal(np.concatenate([g["z"] for g in gathered], axis=1), fe.fetch("assign_all")),
+            "Config_all": all(np.array_equal(g["cfg"], fe.fetch("Config_all")) for g in gathered),
+            "theta0": all(np.array_equal(g["t0"], t0r) for g in gathered),
+            "theta1 (per entry, shards side by side)": np.array_equal(np.concatenate([g["t1"] for g in gathered], axis=1), t1r),
+            "prob": np.allclose(np.concatenate([g["prob"] for g in gathered], axis=0), fe.fetch("prob"), rtol=0, atol=1e-9),
+            "logLik": all(np.allclose(g["ll"], fe.fetch("logLik"), rtol=1e-10, atol=0) for g in gathered),
+        }
+        for name, good in checks.items():
+            if not good:
+                ok = False
+                msg.append("wise=element: sharded %s differs from the single-GPU chain" % name)
+        print(json.dumps({"ok": ok, "world": world, "messages": msg, "element_entries": int(t1r.shape[1])}))
+        fe.close()
+    he.close()
     # ---- independent chains, one group per GPU (BASELINE config 5): the merged result equals the one of the same
     # chains (same Philox chain numbers) run in a single process ----
     d = np.load(os.path.join(ROOT, "tests", "golden", "example_donor.npz"))

@@ -15,10 +15,16 @@ $B > /dev/null 2>&1; echo plain rc=$?
 ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv --log-file gpurun_out/r2_launches_c4.csv $B > gpurun_out/ncu_l.log 2>&1; echo rc=$?
 # the first statistic launch of a run is a full pass (forced); later ones are the incremental correction
 ncu --set full --clock-control none -k regex:k_stats_units --launch-count 1 -o gpurun_out/r2_stats_full_c4 -f $B > gpurun_out/ncu_s1.log 2>&1; echo rc=$?
-ncu --set full --import-source on --clock-control none -k regex:"k_cells_sell|k_stats_units|k_table" --launch-skip 12 --launch-count 3 -o gpurun_out/r2_sweep_c4 -f $B > gpurun_out/ncu_s2.log 2>&1; echo rc=$?
+ncu --set full --clock-control none -k regex:"k_cells_sell|k_stats_units|k_table" --launch-skip 12 --launch-count 3 -o gpurun_out/r2_sweep_c4 -f $B > gpurun_out/ncu_s2.log 2>&1; echo rc=$?
 B3="python bench.py --workload C3 --steps 3 --warmup 3 --no-e2e --no-cpu --no-parity"
 $B3 > /dev/null 2>&1; echo plain rc=$?
 ncu --set full --clock-control none -k regex:k_stats_stream --launch-count 1 -o gpurun_out/r2_stats_full_c3 -f $B3 > gpurun_out/ncu_c31.log 2>&1; echo rc=$?
 ncu --set full --clock-control none -k regex:"k_cells_sell|k_stats_stream|k_table" --launch-skip 12 --launch-count 3 -o gpurun_out/r2_sweep_c3 -f $B3 > gpurun_out/ncu_c32.log 2>&1; echo rc=$?
 python tools/e2e_breakdown.py > gpurun_out/r2_e2e_breakdown.txt 2>&1; echo rc=$?
-python -m pytest tests -m gpu -q > gpurun_out/pytest_r2_final.log 2>&1; tail -3 gpurun_out/pytest_r2_final.log
+# gpurun_out/ comes back only if it stays below 64 MiB: summarise the reports ON the box (ncu reads them without a GPU too),
+# bring the summaries back, drop the reports
+python tools/summarize_profiles.py > gpurun_out/summarize.log 2>&1; echo rc=$?
+cp profiles/r2_ncu_full_c4_summary.txt profiles/r2_ncu_full_c3_summary.txt profiles/ncu_traffic.json gpurun_out/
+rm -f gpurun_out/*.ncu-rep
+if [ "$1" = "--tests" ]; then python -m pytest tests -m gpu -q > gpurun_out/pytest_r2_final.log 2>&1; tail -3 gpurun_out/pytest_r2_final.log; fi
+du -sh gpurun_out
