@@ -81,6 +81,7 @@ struct Chain {
     DevBuf<double> sell_scratch;
     DevBuf<double2> tab_g;
     DevBuf<unsigned long long> dbg_s34, dbg_sab;   // test hooks (cdl_debug_capture)
+    DevBuf<unsigned long long> tl;                 // device timeline of the last sweep (CDL_TIMELINE=1)
     // summaries
     DevBuf<double> prob_mean, config_prob, theta1_mean;
     double theta0_mean = 0.0, relax_mean = 0.0;
@@ -305,12 +306,12 @@ bool p2p_ensure(cdl_handle h, size_t elems) {
     struct Pack { cudaIpcMemHandle_t arena, flags; };
     Pack mine{};
     q.table_elems = elems; q.my_rank = h->rank; q.n_peer = h->world - 1;
-    if (cudaMalloc(&q.arena, sizeof(unsigned long long) * 2 * elems) != cudaSuccess ||
-        cudaMalloc(&q.my_flags, sizeof(unsigned long long) * (size_t)h->world) != cudaSuccess ||
+    if (cudaMalloc(&q.arena, sizeof(unsigned long long) * 3 * elems) != cudaSuccess ||
+        cudaMalloc(&q.my_flags, sizeof(unsigned long long) * 2 * (size_t)h->world) != cudaSuccess ||
         cudaMalloc(&q.error, sizeof(unsigned int)) != cudaSuccess) ok = 0;
     if (ok) {
-        cudaMemsetAsync(q.arena, 0, sizeof(unsigned long long) * 2 * elems, h->st);
-        cudaMemsetAsync(q.my_flags, 0, sizeof(unsigned long long) * (size_t)h->world, h->st);
+        cudaMemsetAsync(q.arena, 0, sizeof(unsigned long long) * 3 * elems, h->st);
+        cudaMemsetAsync(q.my_flags, 0, sizeof(unsigned long long) * 2 * (size_t)h->world, h->st);
         cudaMemsetAsync(q.error, 0, sizeof(unsigned int), h->st);
         if (cudaIpcGetMemHandle(&mine.arena, q.arena) != cudaSuccess ||
             cudaIpcGetMemHandle(&mine.flags, q.my_flags) != cudaSuccess) ok = 0;
@@ -424,6 +425,68 @@ double geweke_fraction(cdl_handle h, Chain& ch, int64_t n_rows, DevBuf<unsigned 
     counts.download(c, 2, h->st);
     if (c[0] == 0) return NAN;
     return (double)c[1] / (double)c[0];
+}
+
+// CDL_TIMELINE=1: where the LAST sweep of a bench pass spent its time, from %globaltimer stamps the kernels left
+// (common.cuh::tl_stamp).  Microseconds after the first CTA of the cell kernel started; "first" / "last" over the CTAs.
+void print_timeline(cdl_handle h, Chain& ch) {
+    std::vector<unsigned long long> t((size_t)3 * TL_ROWS * TL_SLOTS);
+    ch.tl.download(t.data(), t.size(), h->st);
+    auto at = [&](int kern, int row, int slot) { return t[((size_t)kern * TL_ROWS + (size_t)row) * TL_SLOTS + (size_t)slot]; };
+    unsigned long long t0 = ~0ull;
+    for (int r = 0; r < TL_ROWS; ++r) if (at(0, r, 0) && at(0, r, 0) < t0) t0 = at(0, r, 0);
+    if (t0 == ~0ull) return;
+    auto span = [&](int kern, int slot, double& lo, double& hi, int& n) {
+        lo = 1e30; hi = -1e30; n = 0;
+        for (int r = 0; r < TL_ROWS; ++r) {
+            const unsigned long long v = at(kern, r, slot);
+            if (!v) continue;
+            const double us = ((double)v - (double)t0) * 1e-3;
+            lo = std::min(lo, us); hi = std::max(hi, us); ++n;
+        }
+    };
+    static const char* names[3][TL_SLOTS] = {
+        {"cells: CTA start", "cells: previous kernel complete (griddepcontrol.wait)", "cells: weight table staged",
+         "cells: last warp of the CTA done", nullptr, nullptr, nullptr, nullptr},
+        {"stats: CTA start", "stats: cell kernel complete", nullptr, "stats: CTA done (table corrected / full pass done)",
+         nullptr, nullptr, nullptr, nullptr},
+        {"table: CTA start", "table: statistic kernel complete", "table: peers' tables published (flags)",
+         "table: flips + block sums done (ticket)", "table: LAST block, grid totals reduced", "table: Gamma jobs done",
+         "table: LAST block writes theta0 / relax rate", "table: Gamma candidates ready (before the wait)"}};
+    if (const char* e = getenv("CDL_TIMELINE")) {
+        if (atoi(e) >= 2) {          // raw rows of the cell kernel: CTA, SM, microseconds from the wait to the CTA's last warp
+            std::vector<int32_t> asg;
+            std::vector<uint32_t> off;
+            const Donor& d = h->donor;
+            if (d.s_assign && d.s_off) {
+                asg.resize((size_t)d.s_assign_grid * d.s_assign_warps);
+                off.resize((size_t)d.s_slices + 1);
+                cudaMemcpy(asg.data(), d.s_assign, 4 * asg.size(), cudaMemcpyDeviceToHost);
+                cudaMemcpy(off.data(), d.s_off, 4 * off.size(), cudaMemcpyDeviceToHost);
+            }
+            for (int r = 0; r < TL_ROWS; ++r) {
+                if (!at(0, r, 0)) continue;
+                long long work = 0, longest = 0;
+                if (!asg.empty() && r < d.s_assign_grid)
+                    for (int w = 0; w < d.s_assign_warps; ++w) {
+                        const int32_t sl = asg[(size_t)r * d.s_assign_warps + w];
+                        if (sl >= 0) { const long long l = off[(size_t)sl + 1] - off[(size_t)sl]; work += l; longest = std::max(longest, l); }
+                    }
+                std::fprintf(stderr, "[cdl cta] %d sm %llu staged %.2f done %.2f slots %lld longest %lld\n", r, at(0, r, 4),
+                             ((double)at(0, r, 2) - (double)t0) * 1e-3, ((double)at(0, r, 3) - (double)t0) * 1e-3, work, longest);
+            }
+        }
+    }
+    std::fprintf(stderr, "[cdl timeline] last sweep, microseconds after the first cell-kernel CTA started (rank %d)\n", h->rank);
+    static const int order[3][TL_SLOTS] = {{0, 1, 2, 3, -1, -1, -1, -1}, {0, 1, 3, -1, -1, -1, -1, -1}, {0, 7, 1, 2, 3, 4, 5, 6}};
+    for (int k = 0; k < 3; ++k)
+        for (int q = 0; q < TL_SLOTS; ++q) {
+            const int sl = order[k][q];
+            if (sl < 0 || !names[k][sl]) continue;
+            double lo, hi; int n;
+            span(k, sl, lo, hi, n);
+            if (n) std::fprintf(stderr, "[cdl timeline]   %-58s first %9.2f  last %9.2f  (%d CTAs)\n", names[k][sl], lo, hi, n);
+        }
 }
 
 double r_round3_percent(double frac) {   // round(x, 3) * 100 (R/clone_id.R:585,595)
@@ -769,7 +832,7 @@ int cdl_gibbs_run(cdl_handle h, const double* Config, int32_t K, const double* P
             // The all-reduce above is also the barrier that makes this safe: every rank has returned from its previous
             // run (its last table kernel, which reads the peers' arenas, is complete).  A run with incremental
             // statistics leaves its carried table in the arena; every run starts from cleared halves.
-            CDL_CUDA(cudaMemsetAsync(h->p2p.arena, 0, sizeof(unsigned long long) * 2 * h->p2p.table_elems, h->st));
+            CDL_CUDA(cudaMemsetAsync(h->p2p.arena, 0, sizeof(unsigned long long) * 3 * h->p2p.table_elems, h->st));
             CDL_CUDA(cudaStreamSynchronize(h->st));
             allreduce_scalar_d(h, 0.0);      // nobody starts sweeping (and reading a peer's arena) before all are cleared
         }
@@ -955,6 +1018,13 @@ int cdl_gibbs_run(cdl_handle h, const double* Config, int32_t K, const double* P
                 CDL_CUDA(cudaStreamSynchronize(h->st));
             }
             ch.dev.dbg_s34 = nullptr; ch.dev.dbg_sab = nullptr;
+            ch.dev.tl = nullptr;
+            if (const char* e = getenv("CDL_TIMELINE")) {
+                if (atoi(e) != 0) {
+                    ch.tl.alloc((size_t)3 * TL_ROWS * TL_SLOTS); ch.tl.zero(h->st);
+                    ch.dev.tl = ch.tl.p;
+                }
+            }
             if (h->debug_capture) {
                 ch.dbg_s34.alloc((size_t)(2 * N + 5)); ch.dbg_s34.zero(h->st);
                 ch.dbg_sab.alloc((size_t)(N * K)); ch.dbg_sab.zero(h->st);
@@ -1534,6 +1604,7 @@ int cdl_bench_sweeps(cdl_handle h, int32_t warmup, int32_t n, float* ms_total, f
         CDL_CUDA(cudaEventElapsedTime(&tot, e0, e1));
         if (ms_total) *ms_total = tot;
         if (launches) *launches = h->launches - l0;
+        if (ch.dev.tl && n > 0) print_timeline(h, ch);
         // per-kernel breakdown (separate pass so the events do not perturb the total)
         float tc = 0, ts = 0, tt = 0;
         if (ms_cells || ms_stats || ms_table) {

@@ -39,6 +39,7 @@ struct CellsParams {
     uint32_t chain, it;
     int tab_in_smem;
     int zero;                  // always 0; a kernel parameter so it lives in a register (see accumulate_entry)
+    unsigned long long* tl;    // device timeline (common.cuh::tl_stamp) or nullptr
 };
 
 // R's revsort (src/main/sort.c) on a tiny array: used only when positive probabilities tie exactly,

@@ -188,6 +188,12 @@ __global__ void __launch_bounds__(SELL_THREADS, 1) k_cells_sell(const SellParams
     extern __shared__ __align__(16) unsigned char smem_raw[];
     pdl_trigger();
     const CellsParams& C = P.c;
+    tl_stamp(C.tl, 0, 0);
+    if (C.tl && threadIdx.x == 0 && blockIdx.x < TL_ROWS) {
+        unsigned int smid;
+        asm volatile("mov.u32 %0, %%smid;" : "=r"(smid));
+        C.tl[(size_t)blockIdx.x * TL_SLOTS + 4] = smid;
+    }
     const int lane = threadIdx.x & 31;
     // Work items (slices, or 1/parts of one) are dealt dynamically, except each warp's FIRST one, which is its
     // own index: its header and first group slots are donor layout only, so under a programmatic dependent
@@ -230,6 +236,7 @@ __global__ void __launch_bounds__(SELL_THREADS, 1) k_cells_sell(const SellParams
     };
     bool have = item_begin();
     pdl_wait();
+    tl_stamp(C.tl, 0, 1);
     uint32_t tab_sa = 0, msk_sa = 0;
     const double2* tab_g = nullptr;
     const uint32_t* msk_g = C.mask;
@@ -268,6 +275,7 @@ __global__ void __launch_bounds__(SELL_THREADS, 1) k_cells_sell(const SellParams
             }
         }
         __syncthreads();
+        tl_stamp(C.tl, 0, 2);
         tab_sa = (uint32_t)__cvta_generic_to_shared(s_tab);
         msk_sa = (uint32_t)__cvta_generic_to_shared(s_msk);
     } else {
@@ -420,6 +428,11 @@ __global__ void __launch_bounds__(SELL_THREADS, 1) k_cells_sell(const SellParams
             sel = perm[jj];
         }
         store_label(C, valid, (int64_t)jl, sel);
+    }
+    if (C.tl && (threadIdx.x & 31) == 0 && blockIdx.x < TL_ROWS) {      // when the block's last warp ran out of slices
+        unsigned long long t;
+        asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+        atomicMax(C.tl + (size_t)blockIdx.x * TL_SLOTS + 3, t);
     }
 }
 
@@ -656,6 +669,7 @@ void launch_cells_sell(const Donor& d, const SweepArgs& a, ChainDev& c, int sm_c
     C.rp_u = a.rp_u_assign;
     C.key = a.key; C.chain = a.chain; C.it = a.rng_it;
     C.chg_list = a.incremental ? c.chg_list : nullptr; C.chg_old = c.chg_old; C.chg_count = c.chg_ctl;
+    C.tl = c.tl;
     P.slice_off = d.s_off; P.perm = d.s_perm;
     P.v8 = nullptr; P.a8 = (const uint4*)d.s_a; P.b8 = (const uint4*)d.s_b;
     P.n_slices = d.s_slices;
@@ -692,8 +706,10 @@ void launch_cells_sell(const Donor& d, const SweepArgs& a, ChainDev& c, int sm_c
     if (const char* e = getenv("CDL_SELL_SHAPE")) shape = atoi(e);
     int64_t grid = sm_count;
     const int threads = d.vidx32 ? 512 : (shape == 1 ? ((KP == 16 && a.skip0) ? 896 : 768) : 512);
-    const int64_t max_useful = (d.s_slices + threads / 32 - 1) / (threads / 32);
-    if (grid > max_useful) grid = std::max<int64_t>(max_useful, 1);
+    // every SM gets a CTA as long as there is a work item for it: sell_warps() then sizes the CTAs so that the items fill
+    // them evenly (a 1/8 shard of C4: 148 CTAs of 27 warps, not 140 full ones beside 8 idle SMs)
+    const int64_t n_items = d.s_slices * P.parts;
+    if (grid > n_items) grid = std::max<int64_t>(n_items, 1);
     // one-round shard: balanced static assignment of the slices to the (SM, sub-partition) bins, cached with the layout
     P.assign = nullptr;
     if (P.parts == 1) {

@@ -79,6 +79,38 @@ struct PhiloxSeq {
 };
 
 // Marsaglia & Tsang (2000) Gamma(a, 1); a < 1 handled with the U^(1/a) boost.
+// One attempt consumes two Philox blocks and is split in two so that the part that does not depend on the shape -- the
+// normal deviate and the acceptance uniform, most of the work -- can be made before the shape is known (k_table makes
+// the candidates of every draw of the sweep while it waits for the statistic kernel / the peers' tables):
+//   gamma_candidate  blocks sub, sub + 1  ->  x ~ N(0, 1), u3 ~ U(0, 1)
+//   gamma_accept     the squeeze and the log test for shape parameter d = a - 1/3, c = 1 / sqrt(9 d); v = (1 + c x)^3
+__host__ __device__ inline void gamma_candidate(PhiloxSeq& s, double& x, double& u3) {
+    double u1, u2, u4;
+    s.next2(u1, u2);
+    s.next2(u3, u4);
+#ifdef __CUDA_ARCH__
+    x = sqrt(-2.0 * log(u1)) * cospi(2.0 * u2);
+#else
+    x = sqrt(-2.0 * log(u1)) * cos(6.283185307179586 * u2);
+#endif
+}
+__host__ __device__ inline bool gamma_accept(double d, double c, double x, double u3, double& v) {
+    v = 1.0 + c * x;
+    if (v <= 0.0) return false;
+    v = v * v * v;
+    const double x2 = x * x;
+    if (u3 < 1.0 - 0.0331 * x2 * x2) return true;
+    return log(u3) < 0.5 * x2 + d * (1.0 - v + log(v));
+}
+// the attempts from the sequence's current position on (at most `max_attempts`)
+__host__ __device__ inline double gamma_mt_attempts(double d, double c, PhiloxSeq& s, int max_attempts) {
+    for (int attempt = 0; attempt < max_attempts; ++attempt) {
+        double x, u3, v;
+        gamma_candidate(s, x, u3);
+        if (gamma_accept(d, c, x, u3, v)) return d * v;
+    }
+    return d;  // unreachable in practice (acceptance > 95 %)
+}
 __host__ __device__ inline double gamma_mt(double a, PhiloxSeq& s) {
     double boost = 1.0;
     if (a < 1.0) {
@@ -89,23 +121,7 @@ __host__ __device__ inline double gamma_mt(double a, PhiloxSeq& s) {
     }
     const double d = a - 1.0 / 3.0;
     const double c = 1.0 / sqrt(9.0 * d);
-    for (int attempt = 0; attempt < 1000; ++attempt) {
-        double u1, u2, u3, u4;
-        s.next2(u1, u2);
-        s.next2(u3, u4);
-#ifdef __CUDA_ARCH__
-        const double x = sqrt(-2.0 * log(u1)) * cospi(2.0 * u2);
-#else
-        const double x = sqrt(-2.0 * log(u1)) * cos(6.283185307179586 * u2);
-#endif
-        double v = 1.0 + c * x;
-        if (v <= 0.0) continue;
-        v = v * v * v;
-        const double x2 = x * x;
-        if (u3 < 1.0 - 0.0331 * x2 * x2) return boost * d * v;
-        if (log(u3) < 0.5 * x2 + d * (1.0 - v + log(v))) return boost * d * v;
-    }
-    return boost * d;  // unreachable in practice (acceptance > 95 %)
+    return boost * gamma_mt_attempts(d, c, s, 1000);
 }
 
 // Beta(a, b) as X / (X + Y); clamped strictly inside (0,1) so both logs stay finite
@@ -164,6 +180,17 @@ __device__ __forceinline__ void pdl_trigger() { asm volatile("griddepcontrol.lau
 __device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
 __device__ __forceinline__ void pdl_enter() { pdl_trigger(); pdl_wait(); }
 
+// Device timeline (CDL_TIMELINE=1, api.cu::cdl_bench_sweeps prints it): thread 0 of a block stores %globaltimer into slot
+// `slot` of its block's row; `tl` is nullptr in ordinary runs (one predictable branch per stamp).  TL_ROWS blocks of
+// TL_SLOTS stamps per kernel (cell, statistic, table kernel in that order).
+constexpr int TL_SLOTS = 8, TL_ROWS = 1024;
+__device__ __forceinline__ void tl_stamp(unsigned long long* tl, int kernel, int slot) {
+    if (tl && threadIdx.x == 0 && blockIdx.x < TL_ROWS) {
+        unsigned long long t;
+        asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+        tl[((size_t)kernel * TL_ROWS + blockIdx.x) * TL_SLOTS + slot] = t;
+    }
+}
 // exact u16 -> double without the (slow) I2F.F64 path: 2^52 + a has `a` in the low mantissa bits
 __device__ __forceinline__ double u16_to_double(uint32_t a) {
     return __hiloint2double(0x43300000, (int)a) - 4503599627370496.0;

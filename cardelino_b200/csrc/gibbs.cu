@@ -208,15 +208,36 @@ __global__ void k_build_tab(int64_t N, int n_tab, const double* __restrict__ l1,
 // fence + release store is sufficient.  Issued by the LAST CTA of whichever kernel completed the table (the last CTA
 // has seen every other CTA's ticket, each taken after a device-scope fence) -- no separate signalling kernel.
 struct PeerSignal {
-    int n_peer, my_rank;
-    unsigned long long* peer_flags[MAX_PEERS];   // flag arrays in the peers' memory
+    int n_peer, my_rank, world;
+    unsigned long long* peer_flags[MAX_PEERS];   // flag arrays in the peers' memory ([2 * world] each, P2PState::my_flags)
     unsigned long long epoch;
+    // Carried sum (incremental statistics on cell shards, nullptr = off).  Every rank keeps a copy G of the table summed
+    // over ALL ranks.  A rank that corrects its own table from its changed cells applies the same corrections to every
+    // copy of G (remote atomics over NVLink: integer adds commute, so the copies stay identical), and when no rank took the
+    // full pass the table kernel reads G from local memory instead of seven peers' tables (9 MB per rank per sweep at
+    // C4 on 8 GPUs).  After a full pass anywhere the table kernel sums the ranks' own tables as before and rewrites G.
+    unsigned long long* g_own;
+    unsigned long long* g_peer[MAX_PEERS];
+    const unsigned long long* my_flags;          // this rank's flag array (the peers write it)
+    int peer_rank[MAX_PEERS];
 };
-__device__ __forceinline__ void signal_peers(const PeerSignal& S) {
+// `full`: the table was recomputed (1) or corrected (0); the flag carries 2 * epoch + full
+__device__ __forceinline__ void signal_peers(const PeerSignal& S, unsigned int full) {
     if ((int)threadIdx.x < S.n_peer) {
         __threadfence_system();
-        st_release_sys_u64(S.peer_flags[threadIdx.x] + S.my_rank, S.epoch);
+        st_release_sys_u64(S.peer_flags[threadIdx.x] + S.my_rank, 2ull * S.epoch + full);
     }
+}
+// bounded wait for a flag that a peer writes into this rank's memory (a peer that died must not hang this GPU)
+__device__ __forceinline__ unsigned long long wait_flag(const unsigned long long* f, unsigned long long at_least,
+                                                        unsigned int* error) {
+    const long long t0 = clock64();
+    unsigned long long v;
+    while ((v = ld_acquire_sys_u64(f)) < at_least) {
+        if (clock64() - t0 > 20000000000ll) { if (error) atomicExch(error, 1u); break; }   // ~10 s
+        __nanosleep(100);
+    }
+    return v;
 }
 // every CTA calls this once, after its last write to the table; true in the CTA that finishes last
 __device__ __forceinline__ bool last_cta_done(unsigned int* ticket) {
@@ -235,6 +256,7 @@ __device__ __forceinline__ bool last_cta_done(unsigned int* ticket) {
 
 struct StatsParams {
     PeerSignal sig;
+    unsigned int* p2p_error;        // set to 1 if a peer's flag did not arrive in time
     unsigned int* done_ticket;      // zero between launches
     const uint32_t* seggrp;
     const uint16_t* flush;
@@ -257,6 +279,7 @@ struct StatsParams {
     const int* plan;      // [grid + 2 * n_cb]: home block of each CTA, first CTA and CTA count of each block
     int chunks_per_warp;  // k_stats_units: work units per segment (k_stats_stream takes one static range per warp)
     unsigned int* work;   // [n_cb] unit counters of k_stats_units; zero on entry (k_table's last block re-arms them)
+    unsigned long long* tl;   // device timeline or nullptr
 };
 
 
@@ -271,6 +294,14 @@ __device__ __forceinline__ bool stats_try_incremental(const StatsParams& P) {
     const int lane = threadIdx.x & 31;
     const int64_t warp = (blockIdx.x * (int64_t)blockDim.x + threadIdx.x) >> 5;
     const int64_t nwarps = ((int64_t)gridDim.x * blockDim.x) >> 5;
+    const bool push = P.sig.g_own != nullptr;        // cell shards: the same corrections go into every rank's carried sum
+    if (push && count > 0) {
+        // a peer's copy may be written once that peer's previous table kernel has read it (flag world + r, set by that
+        // kernel's last block; it has long arrived: the peer ran a whole cell kernel since)
+        if ((int)threadIdx.x < P.sig.n_peer)
+            wait_flag(P.sig.my_flags + P.sig.world + P.sig.peer_rank[threadIdx.x], P.sig.epoch, P.p2p_error);
+        __syncthreads();
+    }
     for (int64_t q = warp; q < (int64_t)count; q += nwarps) {
         const int64_t j = P.chg_list[q];
         const int zo = P.chg_old[q], zn = P.z[j];
@@ -283,17 +314,30 @@ __device__ __forceinline__ bool stats_try_incremental(const StatsParams& P) {
             const unsigned long long w = a | (b << 32);
             atomicAdd(&P.sab[v * P.K + zn], w);
             atomicAdd(&P.sab[v * P.K + zo], 0ull - w);     // the packed halves borrow and repay: net exact
+            if (push) {
+                atomicAdd(&P.sig.g_own[v * P.K + zn], w);
+                atomicAdd(&P.sig.g_own[v * P.K + zo], 0ull - w);
+#pragma unroll
+                for (int r = 0; r < MAX_PEERS; ++r)
+                    if (r < P.sig.n_peer) {
+                        atomicAdd_system(P.sig.g_peer[r] + v * P.K + zn, w);
+                        atomicAdd_system(P.sig.g_peer[r] + v * P.K + zo, 0ull - w);
+                    }
+            }
         }
     }
+    if (push && count > 0) __threadfence_system();       // the remote additions are performed before this CTA's ticket
     if (last_cta_done(P.done_ticket)) {
         // every other CTA has read the control words and finished its updates
         if (threadIdx.x == 0) { P.ctl[0] = 0u; P.ctl[1] = 0u; P.ctl[2] = 0u; }
-        signal_peers(P.sig);
+        signal_peers(P.sig, 0u);
     }
+    tl_stamp(P.tl, 1, 3);
     return true;
 }
 // end of the full pass: the CTA that finishes last hands the table over
 __device__ __forceinline__ void stats_finish_full(const StatsParams& P) {
+    tl_stamp(P.tl, 1, 3);
     if (!P.ctl && P.sig.n_peer == 0) return;
     if (!last_cta_done(P.done_ticket)) return;
     if (P.ctl) {
@@ -306,7 +350,7 @@ __device__ __forceinline__ void stats_finish_full(const StatsParams& P) {
         __threadfence();          // every thread's part of the copy is performed before anyone signals
         __syncthreads();
     }
-    signal_peers(P.sig);
+    signal_peers(P.sig, 1u);
 }
 
 // One 8-entry group of a variant segment into the lane-private clone bins.  A and B share one 32-bit bin
@@ -375,9 +419,11 @@ __global__ void __launch_bounds__(STATS_THREADS, 2) k_stats_stream(const StatsPa
     extern __shared__ __align__(16) unsigned char smem_raw[];
     bool waited = false;
     unsigned long long* const sab = P.ctl ? P.zbuf : P.sab;      // where a full pass accumulates
+    tl_stamp(P.tl, 1, 0);
     if (P.ctl) {
         // incremental statistics: the control words come from the cell kernel, so wait first; most sweeps end here
         pdl_wait();
+        tl_stamp(P.tl, 1, 1);
         waited = true;
         if (stats_try_incremental(P)) return;
     }
@@ -523,7 +569,10 @@ __global__ void __launch_bounds__(STATS_THREADS, 2) k_stats_stream(const StatsPa
 // others, helping wherever units are left.
 template <int KP>
 __global__ void __launch_bounds__(STATS_THREADS, 2) k_stats_units(const StatsParams P) {
-    pdl_enter();
+    pdl_trigger();
+    tl_stamp(P.tl, 1, 0);
+    pdl_wait();
+    tl_stamp(P.tl, 1, 1);
     if (P.ctl && stats_try_incremental(P)) return;   // incremental statistics: most sweeps end here
     unsigned long long* const sab = P.ctl ? P.zbuf : P.sab;      // where a full pass accumulates
     extern __shared__ __align__(16) unsigned char smem_raw[];
@@ -648,6 +697,12 @@ struct TableParams {
     int peer_rank[MAX_PEERS];
     unsigned long long epoch;
     unsigned int* p2p_error;                  // set to 1 if a peer's flag did not arrive in time
+    // carried sum over all ranks (PeerSignal): read instead of the peers' tables when no rank took the full pass
+    unsigned long long* g_own;                // nullptr = off
+    const unsigned int* ctl;                  // chg_ctl: [1] != 0 if this rank's statistic kernel took the full pass
+    unsigned long long* peer_flags[MAX_PEERS];
+    int my_rank, world;
+    unsigned long long* tl;                   // device timeline or nullptr
 };
 
 // Block totals of k_table's six per-thread terms.  On return sm_u[q * 32] (q = 0..4) and sm_d[0] hold them; every
@@ -676,6 +731,26 @@ __device__ __forceinline__ void table_block_sums(unsigned long long a0, unsigned
     if (threadIdx.x < 32) __syncwarp();
 }
 
+// Gamma jobs of a k_table block: two per variant of the block (theta1: X and Y of the Beta), then theta0 (2), the next
+// relax rate (2) and the global theta1 (2), which only the block that finishes last carries out.  The Philox identity
+// of job j -- false if this launch does not draw it -- depends on the launch parameters only.
+template <int KP>
+__host__ __device__ constexpr int table_njob() { return 2 * (TABLE_THREADS / KP) + 6; }
+template <int KP>
+__device__ __forceinline__ bool table_job(const TableParams& P, int j, uint32_t& stream, uint32_t& idx, uint32_t& it) {
+    constexpr int VPB = TABLE_THREADS / KP;
+    it = P.rng_it; idx = 0; stream = STREAM_THETA1;
+    if (j < 2 * VPB) {
+        const int64_t iv = (int64_t)blockIdx.x * VPB + (j >> 1);
+        idx = (uint32_t)iv;
+        return P.wise == 1 && iv < P.N && !P.rp_theta1;
+    }
+    const int q = j - 2 * VPB;
+    if (q < 2) { stream = STREAM_THETA0; return !P.rp_theta0; }
+    if (q < 4) { stream = STREAM_RELAX; it = P.rng_it + 1; return P.learn_relax_next && (int64_t)P.it < P.T && !P.rp_relax_next; }
+    return q < 6 && P.wise == 0 && !P.rp_theta1;
+}
+
 // One thread per (variant, clone) element; the KP lanes of a variant sit in one warp.
 //   phase A  Config flip of the element and its contribution to the theta statistics / logLik trace, reduced
 //            over the variant's lanes with shuffles; block partials go through a ticket and the last block
@@ -686,38 +761,62 @@ __device__ __forceinline__ void table_block_sums(unsigned long long a0, unsigned
 //            rejection sampler is ~10 cycles per dependent instruction, so the kernel's duration is one Gamma
 //            draw, not a chain of them.
 template <int KP>
-__global__ void __launch_bounds__(TABLE_THREADS) k_table(const TableParams P) {
+__global__ void __launch_bounds__(TABLE_THREADS, 5) k_table(const TableParams P) {
     constexpr int VPB = TABLE_THREADS / KP;          // variants per block
-    constexpr int NJOB = 2 * VPB + 6;
+    constexpr int NJOB = table_njob<KP>();
+    constexpr int NCAND = TABLE_THREADS / NJOB < 3 ? TABLE_THREADS / NJOB : 3;     // attempts prepared ahead per job
     static_assert(NJOB <= TABLE_THREADS, "one Gamma job per thread");
     __shared__ unsigned long long sm_u[5 * 32];
     __shared__ double sm_d[32];
     __shared__ unsigned long long s_s3[VPB], s_s4[VPB], s_tot[5];
     __shared__ double s_gam[NJOB];
+    __shared__ double s_cx[NJOB * NCAND], s_cu[NJOB * NCAND];      // Gamma candidates: normal deviate, acceptance uniform
     __shared__ bool is_last;
-    pdl_enter();
+    pdl_trigger();
+    tl_stamp(P.tl, 2, 0);
+    // The first NCAND attempts of every Gamma job of this block, as far as they do not depend on the shape (common.cuh:
+    // gamma_candidate -- two Philox blocks, a logarithm, a square root and a cosine each), one (job, attempt) per thread.
+    // They need nothing but the launch parameters, so they are made BEFORE the wait for the statistic kernel (and, on cell
+    // shards, for the peers' tables): the sweep's critical path keeps only the acceptance tests.  The six global jobs
+    // (theta0, next relax rate, global theta1) are prepared by every block, because which block finishes last is not
+    // known yet.
+    if ((int)threadIdx.x < NJOB * NCAND) {
+        const int j = (int)threadIdx.x / NCAND, t = (int)threadIdx.x - j * NCAND;
+        uint32_t stream, idx, it;
+        if (table_job<KP>(P, j, stream, idx, it)) {
+            PhiloxSeq sq(P.key, P.chain, it, stream, idx, ((uint32_t)(j & 1) << 31) + 2u * (uint32_t)t);
+            double x, u3;
+            gamma_candidate(sq, x, u3);
+            s_cx[threadIdx.x] = x; s_cu[threadIdx.x] = u3;
+        }
+    }
+    tl_stamp(P.tl, 2, 7);
+    pdl_wait();
+    tl_stamp(P.tl, 2, 1);
     const int k = threadIdx.x & (KP - 1);
     const int v = threadIdx.x / KP;
     const int64_t i = (int64_t)blockIdx.x * VPB + v;
-    const double l0 = P.scal[SC_L0], l0c = P.scal[SC_L0C], r = P.scal[SC_RELAX];
-    const double odd1 = log(1.0 - r) - log(r);   // Config == 1: log(prior) - log(1 - prior), prior = 1 - r
-    const double odd0 = log(r) - log(1.0 - r);   // Config == 0: prior = r
+    const double l0 = P.scal[SC_L0], l0c = P.scal[SC_L0C];
+    const double odd1 = P.scal[SC_ODD1];         // Config == 1: log(prior) - log(1 - prior), prior = 1 - r: log(1 - r) - log(r)
+    const double odd0 = -odd1;                   // Config == 0: prior = r: log(r) - log(1 - r), the exact negative
     unsigned long long S1 = 0, S2 = 0, S3 = 0, S4 = 0, diff1 = 0;
     double ll = 0.0;
     uint32_t bitk = 0;
+    bool use_sum = false;                      // block-uniform: the carried sum is current, no peer table is read
     if (P.n_peer > 0) {
-        // fused all-reduce: wait until every peer has published its table of this sweep (last CTA of the peer's statistic kernel,
-        // after its k_stats), then read the peers' tables straight over NVLink below.  Bounded spin: a peer
-        // that died must not hang this GPU.
+        // fused all-reduce: wait until every peer has published its table of this sweep (last CTA of the peer's statistic
+        // kernel), then read the peers' tables straight over NVLink below -- or, when every rank only corrected its
+        // table, the carried sum in local memory, which already holds every rank's corrections.
+        __shared__ unsigned int s_any_full;
+        if (threadIdx.x == 0) s_any_full = P.g_own ? (P.ctl[1] != 0u ? 1u : 0u) : 1u;
+        __syncthreads();
         if ((int)threadIdx.x < P.n_peer) {
-            const unsigned long long* f = P.my_flags + P.peer_rank[threadIdx.x];
-            const long long t0 = clock64();
-            while (ld_acquire_sys_u64(f) < P.epoch) {
-                if (clock64() - t0 > 20000000000ll) { atomicExch(P.p2p_error, 1u); break; }   // ~10 s
-                __nanosleep(100);
-            }
+            const unsigned long long v = wait_flag(P.my_flags + P.peer_rank[threadIdx.x], 2ull * P.epoch, P.p2p_error);
+            if (v & 1ull) atomicOr(&s_any_full, 1u);
         }
         __syncthreads();
+        use_sum = s_any_full == 0u;
+        tl_stamp(P.tl, 2, 2);
     }
     if (i < P.N && k < P.K) {
         const bool element = P.sd1 != nullptr;
@@ -727,13 +826,15 @@ __global__ void __launch_bounds__(TABLE_THREADS) k_table(const TableParams P) {
         const uint32_t c0 = P.cfg0[i];
         unsigned long long pk = P.sab[i * P.K + k];
         const unsigned long long pk_local = pk;
-        if (P.n_peer > 0) {
+        if (use_sum) pk = P.g_own[i * P.K + k];
+        else if (P.n_peer > 0) {
             // all peers' loads in flight together: one NVLink round trip, not one per peer
             unsigned long long pv[MAX_PEERS];
 #pragma unroll
             for (int q = 0; q < MAX_PEERS; ++q) pv[q] = q < P.n_peer ? ld_peer_u64(P.peer_sab[q] + i * P.K + k) : 0ull;
 #pragma unroll
             for (int q = 0; q < MAX_PEERS; ++q) pk += pv[q];
+            if (P.g_own) P.g_own[i * P.K + k] = pk;         // the carried sum starts over from this sweep's tables
         }
         if (P.sab_next) P.sab_next[i * P.K + k] = P.carry_local ? pk_local : 0ull;
         const double SA = (double)(uint32_t)pk, SB = (double)(uint32_t)(pk >> 32);
@@ -745,13 +846,20 @@ __global__ void __launch_bounds__(TABLE_THREADS) k_table(const TableParams P) {
             if (P.keep_base && k == 0) prior = cbit ? INFINITY : -INFINITY;
             else prior = cbit ? odd1 : odd0;
             double x = (element ? sd - (SA * l0 + SB * l0c) : SA * du + SB * dv) + prior;
-            x = x > 50.0 ? 50.0 : (x < -50.0 ? -50.0 : x);
-            const double ex = exp(x);
-            const double p = ex / (ex + 1.0);
-            const uint32_t idx = (uint32_t)(i + (int64_t)k * P.N);
-            const double u = P.rp_u_config ? P.rp_u_config[idx]
-                                           : philox_uniform(P.key, P.chain, P.rng_it, STREAM_CONFIG, idx);
-            bit = (uint32_t)rbinom1(p, u);
+            // Beyond +-40 the draw does not depend on its uniform: e^x + 1 == e^x in double, so p == 1.0 and rbinom
+            // returns 1 without a uniform (:533, nmath/rbinom.c); at the other end 1 - p == 1.0, every uniform is below it
+            // and the draw is 0.  With tens of thousands of cells behind each variant nearly every element is there: no
+            // exp, no division, no Philox block for it (counter-based streams: skipping a draw moves no other draw).
+            if (x >= 40.0) bit = 1u;
+            else if (x <= -40.0) bit = 0u;
+            else {
+                const double ex = exp(x);              // (the reference's clip to [-50, 50] cannot bind in here)
+                const double p = ex / (ex + 1.0);
+                const uint32_t idx = (uint32_t)(i + (int64_t)k * P.N);
+                const double u = P.rp_u_config ? P.rp_u_config[idx]
+                                               : philox_uniform(P.key, P.chain, P.rng_it, STREAM_CONFIG, idx);
+                bit = (uint32_t)rbinom1(p, u);
+            }
         }
         // Config_all row (:535); with relax off the row holds Config itself (the reference stops
         // with "object 'Config_new' not found" there)
@@ -788,6 +896,7 @@ __global__ void __launch_bounds__(TABLE_THREADS) k_table(const TableParams P) {
     }
     if (threadIdx.x < 32) {
         __syncwarp();
+        tl_stamp(P.tl, 2, 3);
         if (threadIdx.x == 0) {
             const unsigned int tk = atomicAdd(P.ticket, 1u);
             is_last = (tk == gridDim.x - 1);
@@ -797,13 +906,23 @@ __global__ void __launch_bounds__(TABLE_THREADS) k_table(const TableParams P) {
     const bool last = is_last;                        // block-uniform
     if (last) {
         __threadfence();
+        // every block has read (or rewritten) this rank's carried sum: the peers may correct it for the next sweep
+        if (P.g_own && (int)threadIdx.x < P.n_peer) {
+            __threadfence_system();
+            st_release_sys_u64(P.peer_flags[threadIdx.x] + P.world + P.my_rank, P.epoch + 1ull);
+        }
         // deterministic final reduction in block order
         unsigned long long t1 = 0, t2 = 0, t3 = 0, t4 = 0, td = 0;
         double tl = 0.0;
+        // (L2 loads, all of a thread's rows in flight together: this stretch is on the critical path of every sweep)
+#pragma unroll 4
         for (unsigned b = threadIdx.x; b < gridDim.x; b += blockDim.x) {
-            const volatile unsigned long long* pu = P.part_u + (size_t)b * 8;
-            t1 += pu[0]; t2 += pu[1]; t3 += pu[2]; t4 += pu[3]; td += pu[4];
-            tl += ((const volatile double*)P.part_d)[b];
+            const ulonglong2* pu = reinterpret_cast<const ulonglong2*>(P.part_u + (size_t)b * 8);
+            const ulonglong2 x01 = __ldcg(pu), x23 = __ldcg(pu + 1);
+            const unsigned long long x4 = __ldcg(P.part_u + (size_t)b * 8 + 4);
+            const double xl = __ldcg(P.part_d + b);
+            t1 += x01.x; t2 += x01.y; t3 += x23.x; t4 += x23.y; td += x4;
+            tl += xl;
         }
         table_block_sums(t1, t2, t3, t4, td, tl, sm_u, sm_d);
         if (threadIdx.x < 5) {
@@ -818,44 +937,62 @@ __global__ void __launch_bounds__(TABLE_THREADS) k_table(const TableParams P) {
         if (P.stats_work)
             for (int b = threadIdx.x; b < P.n_cb; b += blockDim.x) P.stats_work[b] = 0u;
         __syncthreads();
+        tl_stamp(P.tl, 2, 4);
     }
-    // ---- phase B: one Gamma job per thread ----
+    // ---- phase B: one Gamma job per thread; the candidates were made before the wait, what is left is the shape ----
     {
         const int j = threadIdx.x;
         double shape = -1.0;
         uint32_t stream = 0, idx = 0, it = P.rng_it;
-        if (j < 2 * VPB) {
-            const int64_t iv = (int64_t)blockIdx.x * VPB + (j >> 1);
-            if (P.wise == 1 && iv < P.N && !P.rp_theta1) {
+        if (j < NJOB && (j < 2 * VPB || last) && table_job<KP>(P, j, stream, idx, it)) {
+            if (j < 2 * VPB) {
+                const int64_t iv = (int64_t)blockIdx.x * VPB + (j >> 1);
                 const double pa = P.prior1_mat ? P.prior1_mat[iv] : P.prior1[0];
                 const double pb = P.prior1_mat ? P.prior1_mat[P.n_el + iv] : P.prior1[1];
                 shape = (j & 1) ? pb + (double)s_s4[j >> 1] : pa + (double)s_s3[j >> 1];
                 if (P.dbg_s34) P.dbg_s34[(j & 1) ? P.N + iv : iv] = (j & 1) ? s_s4[j >> 1] : s_s3[j >> 1];
-                stream = STREAM_THETA1; idx = (uint32_t)iv;
-            }
-        } else if (last && j < NJOB) {
-            const int q = j - 2 * VPB;               // 0,1 theta0; 2,3 next relax rate; 4,5 global theta1
-            if (q < 2 && !P.rp_theta0) {
-                shape = P.prior0[q] + (double)s_tot[q];
-                stream = STREAM_THETA0;
-            } else if (q >= 2 && q < 4 && P.learn_relax_next && (int64_t)P.it < P.T && !P.rp_relax_next) {
-                const double d1 = (double)s_tot[4];
-                shape = (q == 2) ? P.relax_prior[0] + d1
-                                 : P.relax_prior[1] + (double)P.N * (double)(P.K - 1) - d1;
-                stream = STREAM_RELAX; it = P.rng_it + 1;
-            } else if (q >= 4 && P.wise == 0 && !P.rp_theta1) {
-                const double pa = P.prior1_mat ? P.prior1_mat[0] : P.prior1[0];
-                const double pb = P.prior1_mat ? P.prior1_mat[1] : P.prior1[1];
-                shape = (q == 4) ? pa + (double)s_tot[2] : pb + (double)s_tot[3];
-                stream = STREAM_THETA1;
+            } else {
+                const int q = j - 2 * VPB;               // 0,1 theta0; 2,3 next relax rate; 4,5 global theta1
+                if (q < 2) shape = P.prior0[q] + (double)s_tot[q];
+                else if (q < 4) {
+                    const double d1 = (double)s_tot[4];
+                    shape = (q == 2) ? P.relax_prior[0] + d1
+                                     : P.relax_prior[1] + (double)P.N * (double)(P.K - 1) - d1;
+                } else {
+                    const double pa = P.prior1_mat ? P.prior1_mat[0] : P.prior1[0];
+                    const double pb = P.prior1_mat ? P.prior1_mat[1] : P.prior1[1];
+                    shape = (q == 4) ? pa + (double)s_tot[2] : pb + (double)s_tot[3];
+                }
             }
         }
         if (shape >= 0.0) {
-            PhiloxSeq sq(P.key, P.chain, it, stream, idx, (uint32_t)(j & 1) << 31);   // X and Y: disjoint halves
-            s_gam[j] = gamma_mt(shape, sq);
+            const uint32_t sub0 = (uint32_t)(j & 1) << 31;              // X and Y: disjoint halves
+            double g;
+            if (shape < 1.0) {
+                // the boost block comes first and shifts the attempts by one block: the serial sampler (rare: no read of
+                // the variant supports the allele in any cell of the clones that carry it)
+                PhiloxSeq sq(P.key, P.chain, it, stream, idx, sub0);
+                g = gamma_mt(shape, sq);
+            } else {
+                const double d = shape - 1.0 / 3.0;
+                const double c = 1.0 / sqrt(9.0 * d);
+                bool done = false;
+                double vv = 0.0;
+                g = d;
+#pragma unroll
+                for (int t = 0; t < NCAND; ++t) {
+                    if (!done && gamma_accept(d, c, s_cx[j * NCAND + t], s_cu[j * NCAND + t], vv)) { g = d * vv; done = true; }
+                }
+                if (!done) {                                            // (~1e-4 of the jobs with three candidates)
+                    PhiloxSeq sq(P.key, P.chain, it, stream, idx, sub0 + 2u * (uint32_t)NCAND);
+                    g = gamma_mt_attempts(d, c, sq, 1000);
+                }
+            }
+            s_gam[j] = g;
         }
     }
     __syncthreads();
+    tl_stamp(P.tl, 2, 5);
     if (P.wise == 1 && threadIdx.x < VPB) {
         const int64_t iv = (int64_t)blockIdx.x * VPB + threadIdx.x;
         if (iv < P.N) {
@@ -867,6 +1004,7 @@ __global__ void __launch_bounds__(TABLE_THREADS) k_table(const TableParams P) {
         }
     }
     if (!last) return;
+    tl_stamp(P.tl, 2, 6);                      // the block that finished last: its slot 4-6 stamps close the kernel
     const int64_t row = (int64_t)P.it - 1;
     if (threadIdx.x == 32) {
         const double th0 = P.rp_theta0 ? clamp_theta(P.rp_theta0[0])
@@ -887,6 +1025,7 @@ __global__ void __launch_bounds__(TABLE_THREADS) k_table(const TableParams P) {
         const double rr = P.rp_relax_next ? P.rp_relax_next[0]
                                           : beta_from_gammas(s_gam[2 * VPB + 2], s_gam[2 * VPB + 3]);
         P.scal[SC_RELAX] = rr;
+        P.scal[SC_ODD1] = log(1.0 - rr) - log(rr);
         P.relax_all[row + 1] = rr;
     }
 }
@@ -950,6 +1089,7 @@ __global__ void k_init(const InitParams P) {
             P.relax_all[1] = rr;
         }
         P.scal[SC_RELAX] = rr;
+        P.scal[SC_ODD1] = log(1.0 - rr) - log(rr);
     }
 }
 
@@ -1103,12 +1243,24 @@ std::vector<int> stats_plan(const std::vector<int64_t>& groups_per_cb, int ctas)
     return plan;
 }
 
+// CDL_CARRY_SUM=0: keep summing the peers' tables every sweep (A/B switch)
+static bool carry_sum_enabled() {
+    static const bool on = [] { const char* e = getenv("CDL_CARRY_SUM"); return !(e && e[0] == '0'); }();
+    return on;
+}
 static PeerSignal peer_signal(const SweepArgs& a) {
     PeerSignal S{};
     if (a.p2p && a.p2p->n_peer > 0) {
         const P2PState& q = *a.p2p;
-        S.n_peer = q.n_peer; S.my_rank = q.my_rank; S.epoch = q.epoch;
-        for (int r = 0; r < q.n_peer; ++r) S.peer_flags[r] = q.peer_flags[r];
+        S.n_peer = q.n_peer; S.my_rank = q.my_rank; S.world = q.n_peer + 1; S.epoch = q.epoch;
+        S.my_flags = q.my_flags;
+        const bool carry = a.incremental && carry_sum_enabled();
+        S.g_own = carry ? q.arena + 2 * q.table_elems : nullptr;
+        for (int r = 0; r < q.n_peer; ++r) {
+            S.peer_flags[r] = q.peer_flags[r];
+            S.peer_rank[r] = q.peer_rank[r];
+            S.g_peer[r] = carry ? q.peer_arena[r] + 2 * q.table_elems : nullptr;
+        }
     }
     return S;
 }
@@ -1117,17 +1269,21 @@ void launch_stats(const Donor& d, const SweepArgs& a, ChainDev& c, int sm_count,
     // c.sab is zero on entry: k_table clears it while it reads it (and the chain starts with a zeroed table)
     StatsParams P{};
     P.sig = peer_signal(a);
+    P.p2p_error = (a.p2p && a.p2p->n_peer > 0) ? a.p2p->error : nullptr;
     P.done_ticket = c.stats_ticket;
     P.ctl = nullptr;
     if (a.incremental) {
         P.ctl = c.chg_ctl;
         P.threshold = (unsigned int)std::max<int64_t>(1, d.M / 32);      // ~3 % of the cells
+        // (with the carried sum every correction is also made in the peers' copies: the full pass wins earlier)
+        if (P.sig.g_own) P.threshold = (unsigned int)std::max<int64_t>(1, d.M / (32 * (int64_t)(1 + (P.sig.n_peer + 1) / 2)));
         P.zbuf = c.sab_zero;
         P.rowgrp = d.c_rowgrp; P.vidx = d.c_vidx; P.ca = d.c_a; P.cb = d.c_b; P.vidx32 = d.vidx32 ? 1 : 0;
         P.chg_list = c.chg_list; P.chg_old = c.chg_old;
     }
     P.seggrp = d.v_seggrp; P.flush = d.v_flush; P.vc = d.v_cell; P.va = d.v_a; P.vb = d.v_b; P.z = c.z; P.sab = c.sab;
     P.N = d.N; P.M = d.M; P.K = a.K; P.n_cb = d.n_cb;
+    P.tl = c.tl;
     const int KP = pad_k(a.K);
     const int ncell_max = (int)std::min<int64_t>(CELL_BLOCK, d.M);
     const size_t smem = sizeof(uint32_t) * STATS_WARPS * KP * 32 + (size_t)((ncell_max + 15) / 16 * 16);
@@ -1202,6 +1358,7 @@ void launch_table(const Donor& d, const SweepArgs& a, ChainDev& c, cudaStream_t 
     P.carry_local = 0;
     P.dbg_s34 = c.dbg_s34; P.dbg_tot = c.dbg_s34 ? c.dbg_s34 + 2 * d.N : nullptr;
     P.n_peer = 0;
+    P.tl = c.tl;
     if (a.p2p && a.p2p->n_peer > 0) {
         const P2PState& q = *a.p2p;
         P.n_peer = q.n_peer;
@@ -1214,6 +1371,9 @@ void launch_table(const Donor& d, const SweepArgs& a, ChainDev& c, cudaStream_t 
         P.my_flags = q.my_flags;
         P.epoch = q.epoch;
         P.p2p_error = q.error;
+        const PeerSignal S = peer_signal(a);
+        P.g_own = S.g_own; P.ctl = c.chg_ctl; P.my_rank = S.my_rank; P.world = S.world;
+        for (int r = 0; r < q.n_peer; ++r) P.peer_flags[r] = S.peer_flags[r];
     }
     const int KP = pad_k(a.K);
     const int vpb = TABLE_THREADS / KP;

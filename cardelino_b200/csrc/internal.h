@@ -137,10 +137,14 @@ struct ChainDev {
     unsigned int* work;  // dynamic work-item counter of k_cells_sell
     unsigned int* stats_work;    // [n_cb] dynamic unit counters of k_stats
     unsigned int* stats_ticket;  // "last CTA" ticket of the statistic kernels (zero between launches)
+    unsigned long long* tl;      // device timeline of the last sweep (CDL_TIMELINE=1), else nullptr
 };
 
 enum {
     SC_THETA0 = 0, SC_L0 = 1, SC_L0C = 2, SC_RELAX = 3,   // relax rate used by the NEXT flip step
+    SC_ODD1 = 4,         // log(1 - r) - log(r) of that relax rate: the prior log-odds of an entry whose input Config is 1 (an
+                         // input 0 has exactly the negative); written wherever SC_RELAX is, so the table kernel's 160 000 threads do
+                         // not each evaluate four logarithms
     SC_N
 };
 
@@ -151,8 +155,11 @@ enum {
 // is fused into the table kernel, no NCCL call per sweep.
 struct P2PState {
     int n_peer = 0, my_rank = 0;
-    unsigned long long* arena = nullptr;             // this rank's [2][table_elems]
-    unsigned long long* my_flags = nullptr;          // [world]
+    unsigned long long* arena = nullptr;             // this rank's [3][table_elems]: its own table by sweep parity, then the
+                                                     // carried SUM over all ranks (incremental statistics, see gibbs.cu)
+    unsigned long long* my_flags = nullptr;          // [2 * world], written by the peers: [r] "rank r's table of sweep e is
+                                                     // complete" (2 e + 1 after a full pass, 2 e after a correction);
+                                                     // [world + r] "rank r has read its carried sum of sweep e - 1"
     unsigned long long* peer_arena[MAX_PEERS] = {};  // mapped with cudaIpcOpenMemHandle
     unsigned long long* peer_flags[MAX_PEERS] = {};
     int peer_rank[MAX_PEERS] = {};

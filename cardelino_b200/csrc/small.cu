@@ -245,7 +245,10 @@ __global__ void __launch_bounds__(SMALL_THREADS, 1) k_small_chain(const SmallPar
     // ---- state back to global memory (the next launch, or the three-kernel path / bench hook, resumes from it) ----
     for (int i = tid; i < n_tab; i += blockDim.x) { c.l1[i] = s_l1[i]; c.l1c[i] = s_l1c[i]; }
     for (int i = tid; i < N; i += blockDim.x) c.mask[i] = s_mask[i];
-    if (tid == 0) { c.scal[SC_L0] = s_l0; c.scal[SC_L0C] = s_l0c; c.scal[SC_RELAX] = s_relax; }
+    if (tid == 0) {
+        c.scal[SC_L0] = s_l0; c.scal[SC_L0C] = s_l0c; c.scal[SC_RELAX] = s_relax;
+        c.scal[SC_ODD1] = log(1.0 - s_relax) - log(s_relax);
+    }
 }
 
 }  // namespace
