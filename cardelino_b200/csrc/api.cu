@@ -364,6 +364,7 @@ void one_sweep(cdl_handle h, Chain& ch, SweepArgs& a, uint32_t it, const cdl_rep
                uint32_t rng_advance = 0) {
     a.it = it;
     a.rng_it = it + rng_advance;
+    if (ch.tl.p) ch.dev.tl = ch.tl.p + (size_t)(a.rng_it & 1u) * 3 * TL_ROWS * TL_SLOTS;   // timeline: two sweeps, by parity
     const cdl_gibbs_params& gp = h->gp;
     a.learn_relax_next = (a.relax && !a.relax_fixed_set && ((double)(it + 1) > 0.1 * gp.min_iter + 5.0)) ? 1 : 0;
     if (rp_dev) {
@@ -430,21 +431,20 @@ double geweke_fraction(cdl_handle h, Chain& ch, int64_t n_rows, DevBuf<unsigned 
 // CDL_TIMELINE=1: where the LAST sweep of a bench pass spent its time, from %globaltimer stamps the kernels left
 // (common.cuh::tl_stamp).  Microseconds after the first CTA of the cell kernel started; "first" / "last" over the CTAs.
 void print_timeline(cdl_handle h, Chain& ch) {
-    std::vector<unsigned long long> t((size_t)3 * TL_ROWS * TL_SLOTS);
+    const size_t per = (size_t)3 * TL_ROWS * TL_SLOTS;
+    std::vector<unsigned long long> t(2 * per);
     ch.tl.download(t.data(), t.size(), h->st);
-    auto at = [&](int kern, int row, int slot) { return t[((size_t)kern * TL_ROWS + (size_t)row) * TL_SLOTS + (size_t)slot]; };
-    unsigned long long t0 = ~0ull;
-    for (int r = 0; r < TL_ROWS; ++r) if (at(0, r, 0) && at(0, r, 0) < t0) t0 = at(0, r, 0);
-    if (t0 == ~0ull) return;
-    auto span = [&](int kern, int slot, double& lo, double& hi, int& n) {
-        lo = 1e30; hi = -1e30; n = 0;
-        for (int r = 0; r < TL_ROWS; ++r) {
-            const unsigned long long v = at(kern, r, slot);
-            if (!v) continue;
-            const double us = ((double)v - (double)t0) * 1e-3;
-            lo = std::min(lo, us); hi = std::max(hi, us); ++n;
-        }
+    auto at = [&](int sweep, int kern, int row, int slot) {
+        return t[(size_t)sweep * per + ((size_t)kern * TL_ROWS + (size_t)row) * TL_SLOTS + (size_t)slot];
     };
+    // the two halves hold the last two sweeps (by parity of the Philox iteration): the older one first
+    unsigned long long first[2] = {~0ull, ~0ull};
+    for (int sw = 0; sw < 2; ++sw)
+        for (int r = 0; r < TL_ROWS; ++r) if (at(sw, 0, r, 0) && at(sw, 0, r, 0) < first[sw]) first[sw] = at(sw, 0, r, 0);
+    if (first[0] == ~0ull && first[1] == ~0ull) return;
+    int order2[2] = {0, 1};
+    if (first[1] < first[0]) { order2[0] = 1; order2[1] = 0; }
+    const unsigned long long t0 = std::min(first[0], first[1]);
     static const char* names[3][TL_SLOTS] = {
         {"cells: CTA start", "cells: previous kernel complete (griddepcontrol.wait)", "cells: weight table staged",
          "cells: last warp of the CTA done", nullptr, nullptr, nullptr, nullptr},
@@ -453,8 +453,10 @@ void print_timeline(cdl_handle h, Chain& ch) {
         {"table: CTA start", "table: statistic kernel complete", "table: peers' tables published (flags)",
          "table: flips + block sums done (ticket)", "table: LAST block, grid totals reduced", "table: Gamma jobs done",
          "table: LAST block writes theta0 / relax rate", "table: Gamma candidates ready (before the wait)"}};
+    static const int order[3][TL_SLOTS] = {{0, 1, 2, 3, -1, -1, -1, -1}, {0, 1, 3, -1, -1, -1, -1, -1}, {0, 7, 1, 2, 3, 4, 5, 6}};
     if (const char* e = getenv("CDL_TIMELINE")) {
         if (atoi(e) >= 2) {          // raw rows of the cell kernel: CTA, SM, microseconds from the wait to the CTA's last warp
+            const int sw = order2[1];
             std::vector<int32_t> asg;
             std::vector<uint32_t> off;
             const Donor& d = h->donor;
@@ -465,28 +467,39 @@ void print_timeline(cdl_handle h, Chain& ch) {
                 cudaMemcpy(off.data(), d.s_off, 4 * off.size(), cudaMemcpyDeviceToHost);
             }
             for (int r = 0; r < TL_ROWS; ++r) {
-                if (!at(0, r, 0)) continue;
+                if (!at(sw, 0, r, 0)) continue;
                 long long work = 0, longest = 0;
                 if (!asg.empty() && r < d.s_assign_grid)
                     for (int w = 0; w < d.s_assign_warps; ++w) {
                         const int32_t sl = asg[(size_t)r * d.s_assign_warps + w];
                         if (sl >= 0) { const long long l = off[(size_t)sl + 1] - off[(size_t)sl]; work += l; longest = std::max(longest, l); }
                     }
-                std::fprintf(stderr, "[cdl cta] %d sm %llu staged %.2f done %.2f slots %lld longest %lld\n", r, at(0, r, 4),
-                             ((double)at(0, r, 2) - (double)t0) * 1e-3, ((double)at(0, r, 3) - (double)t0) * 1e-3, work, longest);
+                std::fprintf(stderr, "[cdl cta] %d sm %llu staged %.2f done %.2f slots %lld longest %lld\n", r, at(sw, 0, r, 4),
+                             ((double)at(sw, 0, r, 2) - (double)t0) * 1e-3, ((double)at(sw, 0, r, 3) - (double)t0) * 1e-3, work, longest);
             }
         }
     }
-    std::fprintf(stderr, "[cdl timeline] last sweep, microseconds after the first cell-kernel CTA started (rank %d)\n", h->rank);
-    static const int order[3][TL_SLOTS] = {{0, 1, 2, 3, -1, -1, -1, -1}, {0, 1, 3, -1, -1, -1, -1, -1}, {0, 7, 1, 2, 3, 4, 5, 6}};
-    for (int k = 0; k < 3; ++k)
-        for (int q = 0; q < TL_SLOTS; ++q) {
-            const int sl = order[k][q];
-            if (sl < 0 || !names[k][sl]) continue;
-            double lo, hi; int n;
-            span(k, sl, lo, hi, n);
-            if (n) std::fprintf(stderr, "[cdl timeline]   %-58s first %9.2f  last %9.2f  (%d CTAs)\n", names[k][sl], lo, hi, n);
-        }
+    std::fprintf(stderr, "[cdl timeline r%d] last two sweeps, microseconds after the first cell-kernel CTA of the earlier one started; "
+                         "first / last over the CTAs\n", h->rank);
+    for (int q2 = 0; q2 < 2; ++q2) {
+        const int sw = order2[q2];
+        if (first[sw] == ~0ull) continue;
+        for (int k = 0; k < 3; ++k)
+            for (int q = 0; q < TL_SLOTS; ++q) {
+                const int sl = order[k][q];
+                if (sl < 0 || !names[k][sl]) continue;
+                double lo = 1e30, hi = -1e30;
+                int n = 0;
+                for (int r = 0; r < TL_ROWS; ++r) {
+                    const unsigned long long v = at(sw, k, r, sl);
+                    if (!v || v < first[sw]) continue;            // (stamps of earlier sweeps: only the last block writes some slots)
+                    const double us = ((double)v - (double)t0) * 1e-3;
+                    lo = std::min(lo, us); hi = std::max(hi, us); ++n;
+                }
+                if (n) std::fprintf(stderr, "[cdl timeline r%d] sweep %c  %-58s first %9.2f  last %9.2f  (%d CTAs)\n", h->rank,
+                                    q2 ? 'B' : 'A', names[k][sl], lo, hi, n);
+            }
+    }
 }
 
 double r_round3_percent(double frac) {   // round(x, 3) * 100 (R/clone_id.R:585,595)
@@ -1018,11 +1031,12 @@ int cdl_gibbs_run(cdl_handle h, const double* Config, int32_t K, const double* P
                 CDL_CUDA(cudaStreamSynchronize(h->st));
             }
             ch.dev.dbg_s34 = nullptr; ch.dev.dbg_sab = nullptr;
-            ch.dev.tl = nullptr;
+            ch.dev.tl = nullptr; ch.dev.tl_hist = nullptr;
             if (const char* e = getenv("CDL_TIMELINE")) {
                 if (atoi(e) != 0) {
-                    ch.tl.alloc((size_t)3 * TL_ROWS * TL_SLOTS); ch.tl.zero(h->st);
+                    ch.tl.alloc((size_t)2 * 3 * TL_ROWS * TL_SLOTS + 1024); ch.tl.zero(h->st);
                     ch.dev.tl = ch.tl.p;
+                    ch.dev.tl_hist = ch.tl.p + (size_t)2 * 3 * TL_ROWS * TL_SLOTS;
                 }
             }
             if (h->debug_capture) {
@@ -1604,7 +1618,21 @@ int cdl_bench_sweeps(cdl_handle h, int32_t warmup, int32_t n, float* ms_total, f
         CDL_CUDA(cudaEventElapsedTime(&tot, e0, e1));
         if (ms_total) *ms_total = tot;
         if (launches) *launches = h->launches - l0;
-        if (ch.dev.tl && n > 0) print_timeline(h, ch);
+        if (ch.dev.tl && n > 0) {
+            print_timeline(h, ch);
+            // duration of every timed sweep: end of its table kernel minus the end of the previous one
+            std::vector<unsigned long long> hist(1024);
+            CDL_CUDA(cudaMemcpy(hist.data(), ch.dev.tl_hist, 8 * 1024, cudaMemcpyDeviceToHost));
+            std::string line = "[cdl sweeps r" + std::to_string(h->rank) + "] us per sweep (warm-up, then timed):";
+            const uint32_t first = it + adv - (uint32_t)(warmup + n) + 1;
+            for (uint32_t q = first + 1; q <= it + adv && q - first < 200; ++q) {
+                const unsigned long long a1 = hist[q & 1023u], a0 = hist[(q - 1) & 1023u];
+                char buf[32];
+                std::snprintf(buf, sizeof buf, "%s%.1f", (q - first == (uint32_t)warmup) ? " | " : " ", a1 && a0 ? ((double)a1 - (double)a0) * 1e-3 : -1.0);
+                line += buf;
+            }
+            std::fprintf(stderr, "%s\n", line.c_str());
+        }
         // per-kernel breakdown (separate pass so the events do not perturb the total)
         float tc = 0, ts = 0, tt = 0;
         if (ms_cells || ms_stats || ms_table) {

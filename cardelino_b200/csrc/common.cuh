@@ -209,6 +209,9 @@ __device__ __forceinline__ unsigned long long ld_acquire_sys_u64(const unsigned 
 __device__ __forceinline__ void st_release_sys_u64(unsigned long long* p, unsigned long long v) {
     asm volatile("st.release.sys.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
 }
+__device__ __forceinline__ void st_relaxed_sys_u64(unsigned long long* p, unsigned long long v) {
+    asm volatile("st.relaxed.sys.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
+}
 // streaming 128-bit load, bypassing L1 allocation (read-once data)
 __device__ __forceinline__ uint4 ld_stream(const uint4* p) {
     uint4 r;

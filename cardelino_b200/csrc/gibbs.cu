@@ -221,11 +221,14 @@ struct PeerSignal {
     const unsigned long long* my_flags;          // this rank's flag array (the peers write it)
     int peer_rank[MAX_PEERS];
 };
-// `full`: the table was recomputed (1) or corrected (0); the flag carries 2 * epoch + full
-__device__ __forceinline__ void signal_peers(const PeerSignal& S, unsigned int full) {
+// `full`: the table was recomputed (1) or corrected (0); the flag carries 2 * epoch + full.  `publish`: something was
+// written that the peers will read behind the flag (a release store, i.e. a system-scope fence: ~2 us on the sweep's
+// critical path); a rank whose labels did not move has nothing to publish and sends the flag as a relaxed store.
+__device__ __forceinline__ void signal_peers(const PeerSignal& S, unsigned int full, bool publish = true) {
     if ((int)threadIdx.x < S.n_peer) {
-        __threadfence_system();
-        st_release_sys_u64(S.peer_flags[threadIdx.x] + S.my_rank, 2ull * S.epoch + full);
+        unsigned long long* f = S.peer_flags[threadIdx.x] + S.my_rank;
+        if (publish) st_release_sys_u64(f, 2ull * S.epoch + full);
+        else st_relaxed_sys_u64(f, 2ull * S.epoch + full);
     }
 }
 // bounded wait for a flag that a peer writes into this rank's memory (a peer that died must not hang this GPU)
@@ -302,11 +305,19 @@ __device__ __forceinline__ bool stats_try_incremental(const StatsParams& P) {
             wait_flag(P.sig.my_flags + P.sig.world + P.sig.peer_rank[threadIdx.x], P.sig.epoch, P.p2p_error);
         __syncthreads();
     }
-    for (int64_t q = warp; q < (int64_t)count; q += nwarps) {
+    // One work item = 32 consecutive entries of a changed cell's row, one per lane: a row of ~500 entries is spread over
+    // 16 warps instead of being walked by one (its 16 dependent trips were ~12 us of pure latency on the sweep's
+    // critical path whenever a single label had moved; with the remote additions of the carried sum, ~55 us).
+    constexpr int CHUNKS = 32;                                   // chunks per cell and round: rows up to 1024 entries in one
+    const int64_t items = (int64_t)count * CHUNKS;
+    for (int64_t it = warp; it < items; it += nwarps) {
+        const int64_t q = it / CHUNKS;
+        const int c = (int)(it - q * CHUNKS);
         const int64_t j = P.chg_list[q];
-        const int zo = P.chg_old[q], zn = P.z[j];
         const int64_t e0 = (int64_t)P.rowgrp[j] * GROUP, e1 = (int64_t)P.rowgrp[j + 1] * GROUP;
-        for (int64_t e = e0 + lane; e < e1; e += 32) {
+        if (e0 + (int64_t)c * 32 >= e1) continue;
+        const int zo = P.chg_old[q], zn = P.z[j];
+        for (int64_t e = e0 + (int64_t)c * 32 + lane; e < e1; e += 32 * CHUNKS) {
             const unsigned long long a = P.ca[e], b = P.cb[e];
             if ((a | b) == 0) continue;
             const int64_t v = P.vidx32 ? reinterpret_cast<const uint32_t*>(P.vidx)[e]
@@ -330,7 +341,7 @@ __device__ __forceinline__ bool stats_try_incremental(const StatsParams& P) {
     if (last_cta_done(P.done_ticket)) {
         // every other CTA has read the control words and finished its updates
         if (threadIdx.x == 0) { P.ctl[0] = 0u; P.ctl[1] = 0u; P.ctl[2] = 0u; }
-        signal_peers(P.sig, 0u);
+        signal_peers(P.sig, 0u, count > 0);          // no label moved: nothing behind the flag
     }
     tl_stamp(P.tl, 1, 3);
     return true;
@@ -703,6 +714,7 @@ struct TableParams {
     unsigned long long* peer_flags[MAX_PEERS];
     int my_rank, world;
     unsigned long long* tl;                   // device timeline or nullptr
+    unsigned long long* tl_hist;
 };
 
 // Block totals of k_table's six per-thread terms.  On return sm_u[q * 32] (q = 0..4) and sm_d[0] hold them; every
@@ -907,10 +919,10 @@ __global__ void __launch_bounds__(TABLE_THREADS, 5) k_table(const TableParams P)
     if (last) {
         __threadfence();
         // every block has read (or rewritten) this rank's carried sum: the peers may correct it for the next sweep
-        if (P.g_own && (int)threadIdx.x < P.n_peer) {
-            __threadfence_system();
-            st_release_sys_u64(P.peer_flags[threadIdx.x] + P.world + P.my_rank, P.epoch + 1ull);
-        }
+        // (a relaxed store: every read of the sum has RETURNED -- its value went into the partials behind the tickets this
+        // block has just seen -- so nothing is left for a release fence to order, and this block is the sweep's critical path)
+        if (P.g_own && (int)threadIdx.x < P.n_peer)
+            st_relaxed_sys_u64(P.peer_flags[threadIdx.x] + P.world + P.my_rank, P.epoch + 1ull);
         // deterministic final reduction in block order
         unsigned long long t1 = 0, t2 = 0, t3 = 0, t4 = 0, td = 0;
         double tl = 0.0;
@@ -1020,6 +1032,11 @@ __global__ void __launch_bounds__(TABLE_THREADS, 5) k_table(const TableParams P)
         P.theta1_all[row] = th;
         P.l1[0] = log(th);
         P.l1c[0] = log(1.0 - th);
+    }
+    if (P.tl_hist && threadIdx.x == 0) {
+        unsigned long long t;
+        asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+        P.tl_hist[P.rng_it & 1023u] = t;
     }
     if (threadIdx.x == 96 && P.learn_relax_next && (int64_t)P.it < P.T) {
         const double rr = P.rp_relax_next ? P.rp_relax_next[0]
@@ -1358,7 +1375,7 @@ void launch_table(const Donor& d, const SweepArgs& a, ChainDev& c, cudaStream_t 
     P.carry_local = 0;
     P.dbg_s34 = c.dbg_s34; P.dbg_tot = c.dbg_s34 ? c.dbg_s34 + 2 * d.N : nullptr;
     P.n_peer = 0;
-    P.tl = c.tl;
+    P.tl = c.tl; P.tl_hist = c.tl_hist;
     if (a.p2p && a.p2p->n_peer > 0) {
         const P2PState& q = *a.p2p;
         P.n_peer = q.n_peer;

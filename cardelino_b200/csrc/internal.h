@@ -138,6 +138,7 @@ struct ChainDev {
     unsigned int* stats_work;    // [n_cb] dynamic unit counters of k_stats
     unsigned int* stats_ticket;  // "last CTA" ticket of the statistic kernels (zero between launches)
     unsigned long long* tl;      // device timeline of the last sweep (CDL_TIMELINE=1), else nullptr
+    unsigned long long* tl_hist; // [1024] end of the table kernel of sweep (rng_it & 1023), else nullptr
 };
 
 enum {
