@@ -181,10 +181,30 @@ __device__ __forceinline__ void sell_group(double (&acc)[KP], const Grp<VIdx>& q
     }
 }
 
-template <int KP, typename VIdx, bool SMEM, int SELL_THREADS, int SELL_DEPTH, bool SPLIT, bool SKIP0>
+// 16-byte asynchronous copy global -> shared (LDGSTS, L2 only) and the wait for all of this thread's copies
+__device__ __forceinline__ void cp_async16(uint32_t dst_sa, const void* src) {
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst_sa), "l"(src) : "memory");
+}
+__device__ __forceinline__ void cp_async_wait_all() {
+    asm volatile("cp.async.commit_group;\n\tcp.async.wait_group 0;" ::: "memory");
+}
+__device__ __forceinline__ uint4 lds128(uint32_t sa) {
+    uint4 r;
+    asm volatile("ld.shared.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(r.x), "=r"(r.y), "=r"(r.z), "=r"(r.w) : "r"(sa));
+    return r;
+}
+constexpr int SELL_STAGE_BYTES = 3 * 32 * 16;      // one group slot of a warp: variant ids, A, B (16 bytes per lane each)
+
+// ASYNC (fast path only): the next group slot of a warp travels HBM -> shared memory with cp.async while the current one
+// is accumulated from registers.  The copy is issued where it is written -- a whole group (~3000 cycles of this warp's
+// share of the fp64 pipe) before its data is needed -- which ptxas does not do for plain loads at this register budget
+// (it sinks them to a few instructions before their use: 19 % of the stall samples on that first use), and the look-ahead
+// group occupies shared memory instead of 12 registers.
+template <int KP, typename VIdx, bool SMEM, int SELL_THREADS, int SELL_DEPTH, bool SPLIT, bool SKIP0, bool ASYNC = false>
 __global__ void __launch_bounds__(SELL_THREADS, 1) k_cells_sell(const SellParams P) {
     constexpr bool PACKED = KP <= 16;
     constexpr bool FAST = SMEM && PACKED && sizeof(VIdx) == 2;     // see sell_group_fast
+    static_assert(!ASYNC || (FAST && !SPLIT), "the cp.async pipeline is written for the fast path");
     extern __shared__ __align__(16) unsigned char smem_raw[];
     pdl_trigger();
     const CellsParams& C = P.c;
@@ -214,6 +234,18 @@ __global__ void __launch_bounds__(SELL_THREADS, 1) k_cells_sell(const SellParams
     int part = 0;
     uint32_t jl = 0xffffffffu;
     Grp<VIdx> q[SELL_DEPTH];
+    // this lane's 16-byte cells of its warp's staging slot (behind the weight table): variant ids, A at + 512, B at + 1024
+    const uint32_t stage_sa = ASYNC ? (uint32_t)__cvta_generic_to_shared(smem_raw) + (uint32_t)(sizeof(double2) * (size_t)C.N) +
+                                          (uint32_t)((threadIdx.x >> 5) * SELL_STAGE_BYTES + lane * 16)
+                                    : 0u;
+    // `dep` is zero, but derived from what the previous occupant of the slot was read into: the copy cannot be issued
+    // before those reads have returned
+    auto stage_issue = [&](uint32_t g, uint32_t dep) {
+        const size_t i = (size_t)g * 32 + (size_t)lane;
+        cp_async16(stage_sa + dep, reinterpret_cast<const uint4*>(C.vidx) + i);
+        cp_async16(stage_sa + 512u + dep, P.a8 + i);
+        cp_async16(stage_sa + 1024u + dep, P.b8 + i);
+    };
     // header of item s_u and its first SELL_DEPTH group slots (the look-ahead index is clamped to the slice's last
     // slot so the loads need no predicate: a few redundant loads per slice); false when the items are used up
     auto item_begin = [&]() -> bool {
@@ -229,8 +261,12 @@ __global__ void __launch_bounds__(SELL_THREADS, 1) k_cells_sell(const SellParams
         }
         jl = P.perm[s * 32 + lane];
         if (g0 < g1) {
+            if constexpr (ASYNC) {
+                stage_issue((uint32_t)g0, 0u);
+            } else {
 #pragma unroll
-            for (int h = 0; h < SELL_DEPTH; ++h) q[h].load(C.vidx, P.a8, P.b8, min(g0 + h, g1 - 1) * 32 + lane);
+                for (int h = 0; h < SELL_DEPTH; ++h) q[h].load(C.vidx, P.a8, P.b8, min(g0 + h, g1 - 1) * 32 + lane);
+            }
         }
         return true;
     };
@@ -295,7 +331,19 @@ __global__ void __launch_bounds__(SELL_THREADS, 1) k_cells_sell(const SellParams
         double acc[KP];
 #pragma unroll
         for (int q_ = 0; q_ < KP; ++q_) acc[q_] = 0.0;
-        if (FAST) {
+        if constexpr (ASYNC) {
+            const uint32_t ge = (uint32_t)g1, gl = (uint32_t)g1 - 1u;
+#pragma unroll 2
+            for (uint32_t g = (uint32_t)g0; g < ge; ++g) {
+                cp_async_wait_all();
+                Grp<VIdx> cur;
+                cur.v = lds128(stage_sa); cur.a = lds128(stage_sa + 512u); cur.b = lds128(stage_sa + 1024u);
+                // (clamped to the slice's last slot: no predicate, one redundant copy per slice)
+                stage_issue(min(g + 1u, gl), cur.b.w & (uint32_t)C.zero);
+                sell_group_fast_any<KP, VIdx, SKIP0>(acc, cur, tab_sa);
+            }
+            cp_async_wait_all();               // the redundant last copy must have landed before the slot is reused
+        } else if (FAST) {
             // A ring of SELL_DEPTH + 1 group buffers, SELL_DEPTH + 1 groups per trip so that every index is static (no
             // register rotation): the loads of a group are written SELL_DEPTH groups before it is accumulated.  The
             // look-ahead index is clamped to the slice's last slot, so the loads need no predicate.  (ptxas places
@@ -558,6 +606,19 @@ template <int KP, typename VIdx, int THREADS, int DEPTH, bool SKIP0>
 void launch_sell_t(const SellParams& P, bool smem_tab, size_t smem, int grid, cudaStream_t st) {
     const int threads = 32 * sell_warps(P.n_slices * P.parts, grid, THREADS / 32);
     if (smem_tab) {
+        // CDL_SELL_ASYNC=1: the cp.async pipeline, where its staging slots fit behind the weight table (measured equal to
+        // plain loads at C4 and 1-4 % slower on small shards: the loop is bound by its arithmetic, not by load latency)
+        constexpr bool CAN_ASYNC = KP <= 16 && sizeof(VIdx) == 2 && DEPTH == 1;
+        static const bool async_on = [] { const char* e = getenv("CDL_SELL_ASYNC"); return e && e[0] == '1'; }();
+        const size_t smem_async = smem + (size_t)(threads / 32) * SELL_STAGE_BYTES;
+        if (CAN_ASYNC && async_on && P.parts == 1 && smem_async <= 227 * 1024) {
+            if constexpr (CAN_ASYNC) {
+                auto kern = k_cells_sell<KP, VIdx, true, THREADS, DEPTH, false, SKIP0, true>;
+                CDL_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_async));
+                launch_dep(kern, dim3(grid), dim3(threads), smem_async, st, P);
+                return;
+            }
+        }
         auto kern = P.parts > 1 ? k_cells_sell<KP, VIdx, true, THREADS, DEPTH, true, false>
                                 : k_cells_sell<KP, VIdx, true, THREADS, DEPTH, false, SKIP0>;
         CDL_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
