@@ -110,7 +110,7 @@ def gamma_mt(shape, seed, chain, iteration, stream, idx, sub0=0):
         x2 = x * x
         with np.errstate(invalid="ignore", divide="ignore"):
             acc = ok & ((u3 < 1.0 - 0.0331 * x2 * x2) | (np.log(u3) < 0.5 * x2 + d[t] * (1.0 - v3 + np.log(v3))))
-        out[t[acc]] = boost[t[acc]] * d[t[acc]] * v3[acc]
+        out[t[acc]] = boost[t[acc]] * (d[t[acc]] * v3[acc])     # gamma_mt: boost * gamma_mt_attempts(...) = boost * (d * v)
         todo[t[acc]] = False
     return out
 

@@ -21,6 +21,8 @@ $B3 > /dev/null 2>&1; echo plain rc=$?
 ncu --set full --clock-control none -k regex:k_stats_stream --launch-count 1 -o gpurun_out/r2_stats_full_c3 -f $B3 > gpurun_out/ncu_c31.log 2>&1; echo rc=$?
 ncu --set full --clock-control none -k regex:"k_cells_sell|k_stats_stream|k_table" --launch-skip 12 --launch-count 3 -o gpurun_out/r2_sweep_c3 -f $B3 > gpurun_out/ncu_c32.log 2>&1; echo rc=$?
 python tools/e2e_breakdown.py > gpurun_out/r2_e2e_breakdown.txt 2>&1; echo rc=$?
+# device timeline of the last two sweeps (%globaltimer stamps inside the kernels) and the duration of every sweep
+for w in C4 C4s8 C3; do CDL_TIMELINE=1 python bench.py --workload $w --steps 20 --warmup 5 --no-cpu --no-e2e --no-parity 2>&1 >/dev/null | grep "cdl " | head -45 > gpurun_out/r2_timeline_$w.txt; done
 # gpurun_out/ comes back only if it stays below 64 MiB: summarise the reports ON the box (ncu reads them without a GPU too),
 # bring the summaries back, drop the reports
 python tools/summarize_profiles.py > gpurun_out/summarize.log 2>&1; echo rc=$?
