@@ -307,11 +307,11 @@ bool p2p_ensure(cdl_handle h, size_t elems) {
     Pack mine{};
     q.table_elems = elems; q.my_rank = h->rank; q.n_peer = h->world - 1;
     if (cudaMalloc(&q.arena, sizeof(unsigned long long) * 3 * elems) != cudaSuccess ||
-        cudaMalloc(&q.my_flags, sizeof(unsigned long long) * 2 * (size_t)h->world) != cudaSuccess ||
+        cudaMalloc(&q.my_flags, sizeof(unsigned long long) * (size_t)h->world) != cudaSuccess ||
         cudaMalloc(&q.error, sizeof(unsigned int)) != cudaSuccess) ok = 0;
     if (ok) {
         cudaMemsetAsync(q.arena, 0, sizeof(unsigned long long) * 3 * elems, h->st);
-        cudaMemsetAsync(q.my_flags, 0, sizeof(unsigned long long) * 2 * (size_t)h->world, h->st);
+        cudaMemsetAsync(q.my_flags, 0, sizeof(unsigned long long) * (size_t)h->world, h->st);
         cudaMemsetAsync(q.error, 0, sizeof(unsigned int), h->st);
         if (cudaIpcGetMemHandle(&mine.arena, q.arena) != cudaSuccess ||
             cudaIpcGetMemHandle(&mine.flags, q.my_flags) != cudaSuccess) ok = 0;

@@ -208,27 +208,19 @@ __global__ void k_build_tab(int64_t N, int n_tab, const double* __restrict__ l1,
 // fence + release store is sufficient.  Issued by the LAST CTA of whichever kernel completed the table (the last CTA
 // has seen every other CTA's ticket, each taken after a device-scope fence) -- no separate signalling kernel.
 struct PeerSignal {
-    int n_peer, my_rank, world;
-    unsigned long long* peer_flags[MAX_PEERS];   // flag arrays in the peers' memory ([2 * world] each, P2PState::my_flags)
+    int n_peer, my_rank;
+    unsigned long long* peer_flags[MAX_PEERS];   // flag arrays in the peers' memory ([world] each, P2PState::my_flags)
     unsigned long long epoch;
-    // Carried sum (incremental statistics on cell shards, nullptr = off).  Every rank keeps a copy G of the table summed
-    // over ALL ranks.  A rank that corrects its own table from its changed cells applies the same corrections to every
-    // copy of G (remote atomics over NVLink: integer adds commute, so the copies stay identical), and when no rank took the
-    // full pass the table kernel reads G from local memory instead of seven peers' tables (9 MB per rank per sweep at
-    // C4 on 8 GPUs).  After a full pass anywhere the table kernel sums the ranks' own tables as before and rewrites G.
-    unsigned long long* g_own;
-    unsigned long long* g_peer[MAX_PEERS];
-    const unsigned long long* my_flags;          // this rank's flag array (the peers write it)
-    int peer_rank[MAX_PEERS];
 };
-// `full`: the table was recomputed (1) or corrected (0); the flag carries 2 * epoch + full.  `publish`: something was
-// written that the peers will read behind the flag (a release store, i.e. a system-scope fence: ~2 us on the sweep's
-// critical path); a rank whose labels did not move has nothing to publish and sends the flag as a relaxed store.
-__device__ __forceinline__ void signal_peers(const PeerSignal& S, unsigned int full, bool publish = true) {
+// `changed`: this rank's table differs from the one of the previous sweep (a full pass, or a correction that moved at least
+// one label); the flag carries 2 * epoch + changed.  A changed table is published with a release store (a system-scope
+// fence: ~2 us on the sweep's critical path); a rank whose labels did not move has nothing to publish and sends the flag
+// as a relaxed store.
+__device__ __forceinline__ void signal_peers(const PeerSignal& S, unsigned int changed) {
     if ((int)threadIdx.x < S.n_peer) {
         unsigned long long* f = S.peer_flags[threadIdx.x] + S.my_rank;
-        if (publish) st_release_sys_u64(f, 2ull * S.epoch + full);
-        else st_relaxed_sys_u64(f, 2ull * S.epoch + full);
+        if (changed) st_release_sys_u64(f, 2ull * S.epoch + 1ull);
+        else st_relaxed_sys_u64(f, 2ull * S.epoch);
     }
 }
 // bounded wait for a flag that a peer writes into this rank's memory (a peer that died must not hang this GPU)
@@ -259,7 +251,6 @@ __device__ __forceinline__ bool last_cta_done(unsigned int* ticket) {
 
 struct StatsParams {
     PeerSignal sig;
-    unsigned int* p2p_error;        // set to 1 if a peer's flag did not arrive in time
     unsigned int* done_ticket;      // zero between launches
     const uint32_t* seggrp;
     const uint16_t* flush;
@@ -274,7 +265,7 @@ struct StatsParams {
     // incremental statistics (else ctl == nullptr): the same launch first tries to CORRECT the previous sweep's table
     // from the cells whose label changed (rows layout below); only above the threshold does it run the full pass --
     // into `zbuf`, a table that is all zero at rest, because the carried table cannot be cleared grid-wide first
-    unsigned int* ctl;              // [0] changed count, [1] 1 if the last sweep took the full pass, [2] force-full flag, [3] full passes
+    unsigned int* ctl;              // [0] changed count, [1] 1 if the last sweep took the full pass (2: corrected a changed table), [2] force-full flag, [3] full passes
     unsigned int threshold;
     unsigned long long* zbuf;       // [N*K]
     const uint32_t* rowgrp; const void* vidx; const uint16_t* ca; const uint16_t* cb; int vidx32;
@@ -297,20 +288,11 @@ __device__ __forceinline__ bool stats_try_incremental(const StatsParams& P) {
     const int lane = threadIdx.x & 31;
     const int64_t warp = (blockIdx.x * (int64_t)blockDim.x + threadIdx.x) >> 5;
     const int64_t nwarps = ((int64_t)gridDim.x * blockDim.x) >> 5;
-    const bool push = P.sig.g_own != nullptr;        // cell shards: the same corrections go into every rank's carried sum
-    if (push && count > 0) {
-        // a peer's copy may be written once that peer's previous table kernel has read it (flag world + r, set by that
-        // kernel's last block; it has long arrived: the peer ran a whole cell kernel since)
-        if ((int)threadIdx.x < P.sig.n_peer)
-            wait_flag(P.sig.my_flags + P.sig.world + P.sig.peer_rank[threadIdx.x], P.sig.epoch, P.p2p_error);
-        __syncthreads();
-    }
     // One work item = 32 consecutive entries of a changed cell's row, one per lane: a row of ~500 entries is spread over
     // 16 warps instead of being walked by one (its 16 dependent trips were ~12 us of pure latency on the sweep's
-    // critical path whenever a single label had moved; with the remote additions of the carried sum, ~55 us).
+    // critical path whenever a single label had moved).
     constexpr int CHUNKS = 32;                                   // chunks per cell and round: rows up to 1024 entries in one
     const int64_t items = (int64_t)count * CHUNKS;
-    bool pushed = false;
     for (int64_t it = warp; it < items; it += nwarps) {
         const int64_t q = it / CHUNKS;
         const int c = (int)(it - q * CHUNKS);
@@ -326,26 +308,13 @@ __device__ __forceinline__ bool stats_try_incremental(const StatsParams& P) {
             const unsigned long long w = a | (b << 32);
             atomicAdd(&P.sab[v * P.K + zn], w);
             atomicAdd(&P.sab[v * P.K + zo], 0ull - w);     // the packed halves borrow and repay: net exact
-            if (push) {
-                pushed = true;
-                atomicAdd(&P.sig.g_own[v * P.K + zn], w);
-                atomicAdd(&P.sig.g_own[v * P.K + zo], 0ull - w);
-#pragma unroll
-                for (int r = 0; r < MAX_PEERS; ++r)
-                    if (r < P.sig.n_peer) {
-                        atomicAdd_system(P.sig.g_peer[r] + v * P.K + zn, w);
-                        atomicAdd_system(P.sig.g_peer[r] + v * P.K + zo, 0ull - w);
-                    }
-            }
         }
     }
-    // the remote additions are performed before this CTA's ticket -- a system-scope fence only in the threads that made
-    // any: executed by all 150 000 threads of the grid it cost ~35 us per sweep in which a label had moved
-    if (pushed) __threadfence_system();
     if (last_cta_done(P.done_ticket)) {
         // every other CTA has read the control words and finished its updates
-        if (threadIdx.x == 0) { P.ctl[0] = 0u; P.ctl[1] = 0u; P.ctl[2] = 0u; }
-        signal_peers(P.sig, 0u, count > 0);          // no label moved: nothing behind the flag
+        // ctl[1]: this sweep's table differs from the last one (the table kernel reads it: the carried sum is stale)
+        if (threadIdx.x == 0) { P.ctl[0] = 0u; P.ctl[1] = count > 0 ? 2u : 0u; P.ctl[2] = 0u; }
+        signal_peers(P.sig, count > 0 ? 1u : 0u);
     }
     tl_stamp(P.tl, 1, 3);
     return true;
@@ -712,11 +681,11 @@ struct TableParams {
     int peer_rank[MAX_PEERS];
     unsigned long long epoch;
     unsigned int* p2p_error;                  // set to 1 if a peer's flag did not arrive in time
-    // carried sum over all ranks (PeerSignal): read instead of the peers' tables when no rank took the full pass
-    unsigned long long* g_own;                // nullptr = off
-    const unsigned int* ctl;                  // chg_ctl: [1] != 0 if this rank's statistic kernel took the full pass
-    unsigned long long* peer_flags[MAX_PEERS];
-    int my_rank, world;
+    // Carried sum (incremental statistics on cell shards; nullptr = off): this rank's copy of the table summed over ALL
+    // ranks, rewritten whenever any rank's table changed and read INSTEAD of the seven peers' tables (9 MB per rank and
+    // sweep at C4 on 8 GPUs) when none did -- in a settled chain almost every sweep
+    unsigned long long* g_own;
+    const unsigned int* ctl;                  // chg_ctl: [1] != 0 if this rank's table changed in this sweep
     unsigned long long* tl;                   // device timeline or nullptr
     unsigned long long* tl_hist;
 };
@@ -821,17 +790,17 @@ __global__ void __launch_bounds__(TABLE_THREADS, 5) k_table(const TableParams P)
     bool use_sum = false;                      // block-uniform: the carried sum is current, no peer table is read
     if (P.n_peer > 0) {
         // fused all-reduce: wait until every peer has published its table of this sweep (last CTA of the peer's statistic
-        // kernel), then read the peers' tables straight over NVLink below -- or, when every rank only corrected its
-        // table, the carried sum in local memory, which already holds every rank's corrections.
-        __shared__ unsigned int s_any_full;
-        if (threadIdx.x == 0) s_any_full = P.g_own ? (P.ctl[1] != 0u ? 1u : 0u) : 1u;
+        // kernel), then read the peers' tables straight over NVLink below -- or, when no rank's table changed in this
+        // sweep, the carried sum in local memory.
+        __shared__ unsigned int s_any_changed;
+        if (threadIdx.x == 0) s_any_changed = P.g_own ? (P.ctl[1] != 0u ? 1u : 0u) : 1u;
         __syncthreads();
         if ((int)threadIdx.x < P.n_peer) {
             const unsigned long long v = wait_flag(P.my_flags + P.peer_rank[threadIdx.x], 2ull * P.epoch, P.p2p_error);
-            if (v & 1ull) atomicOr(&s_any_full, 1u);
+            if (v & 1ull) atomicOr(&s_any_changed, 1u);
         }
         __syncthreads();
-        use_sum = s_any_full == 0u;
+        use_sum = s_any_changed == 0u;
         tl_stamp(P.tl, 2, 2);
     }
     if (i < P.N && k < P.K) {
@@ -922,11 +891,6 @@ __global__ void __launch_bounds__(TABLE_THREADS, 5) k_table(const TableParams P)
     const bool last = is_last;                        // block-uniform
     if (last) {
         __threadfence();
-        // every block has read (or rewritten) this rank's carried sum: the peers may correct it for the next sweep
-        // (a relaxed store: every read of the sum has RETURNED -- its value went into the partials behind the tickets this
-        // block has just seen -- so nothing is left for a release fence to order, and this block is the sweep's critical path)
-        if (P.g_own && (int)threadIdx.x < P.n_peer)
-            st_relaxed_sys_u64(P.peer_flags[threadIdx.x] + P.world + P.my_rank, P.epoch + 1ull);
         // deterministic final reduction in block order
         unsigned long long t1 = 0, t2 = 0, t3 = 0, t4 = 0, td = 0;
         double tl = 0.0;
@@ -1273,15 +1237,8 @@ static PeerSignal peer_signal(const SweepArgs& a) {
     PeerSignal S{};
     if (a.p2p && a.p2p->n_peer > 0) {
         const P2PState& q = *a.p2p;
-        S.n_peer = q.n_peer; S.my_rank = q.my_rank; S.world = q.n_peer + 1; S.epoch = q.epoch;
-        S.my_flags = q.my_flags;
-        const bool carry = a.incremental && carry_sum_enabled();
-        S.g_own = carry ? q.arena + 2 * q.table_elems : nullptr;
-        for (int r = 0; r < q.n_peer; ++r) {
-            S.peer_flags[r] = q.peer_flags[r];
-            S.peer_rank[r] = q.peer_rank[r];
-            S.g_peer[r] = carry ? q.peer_arena[r] + 2 * q.table_elems : nullptr;
-        }
+        S.n_peer = q.n_peer; S.my_rank = q.my_rank; S.epoch = q.epoch;
+        for (int r = 0; r < q.n_peer; ++r) S.peer_flags[r] = q.peer_flags[r];
     }
     return S;
 }
@@ -1290,14 +1247,11 @@ void launch_stats(const Donor& d, const SweepArgs& a, ChainDev& c, int sm_count,
     // c.sab is zero on entry: k_table clears it while it reads it (and the chain starts with a zeroed table)
     StatsParams P{};
     P.sig = peer_signal(a);
-    P.p2p_error = (a.p2p && a.p2p->n_peer > 0) ? a.p2p->error : nullptr;
     P.done_ticket = c.stats_ticket;
     P.ctl = nullptr;
     if (a.incremental) {
         P.ctl = c.chg_ctl;
         P.threshold = (unsigned int)std::max<int64_t>(1, d.M / 32);      // ~3 % of the cells
-        // (with the carried sum every correction is also made in the peers' copies: the full pass wins earlier)
-        if (P.sig.g_own) P.threshold = (unsigned int)std::max<int64_t>(1, d.M / (32 * (int64_t)(1 + (P.sig.n_peer + 1) / 2)));
         P.zbuf = c.sab_zero;
         P.rowgrp = d.c_rowgrp; P.vidx = d.c_vidx; P.ca = d.c_a; P.cb = d.c_b; P.vidx32 = d.vidx32 ? 1 : 0;
         P.chg_list = c.chg_list; P.chg_old = c.chg_old;
@@ -1392,9 +1346,8 @@ void launch_table(const Donor& d, const SweepArgs& a, ChainDev& c, cudaStream_t 
         P.my_flags = q.my_flags;
         P.epoch = q.epoch;
         P.p2p_error = q.error;
-        const PeerSignal S = peer_signal(a);
-        P.g_own = S.g_own; P.ctl = c.chg_ctl; P.my_rank = S.my_rank; P.world = S.world;
-        for (int r = 0; r < q.n_peer; ++r) P.peer_flags[r] = S.peer_flags[r];
+        P.g_own = (a.incremental && carry_sum_enabled()) ? q.arena + 2 * q.table_elems : nullptr;
+        P.ctl = c.chg_ctl;
     }
     const int KP = pad_k(a.K);
     const int vpb = TABLE_THREADS / KP;

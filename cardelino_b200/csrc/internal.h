@@ -156,11 +156,10 @@ enum {
 // is fused into the table kernel, no NCCL call per sweep.
 struct P2PState {
     int n_peer = 0, my_rank = 0;
-    unsigned long long* arena = nullptr;             // this rank's [3][table_elems]: its own table by sweep parity, then the
-                                                     // carried SUM over all ranks (incremental statistics, see gibbs.cu)
-    unsigned long long* my_flags = nullptr;          // [2 * world], written by the peers: [r] "rank r's table of sweep e is
-                                                     // complete" (2 e + 1 after a full pass, 2 e after a correction);
-                                                     // [world + r] "rank r has read its carried sum of sweep e - 1"
+    unsigned long long* arena = nullptr;             // this rank's [3][table_elems]: its own table by sweep parity, then its
+                                                     // copy of the SUM over all ranks (carried sum, gibbs.cu::TableParams)
+    unsigned long long* my_flags = nullptr;          // [world], written by the peers: [r] = 2 e + c once rank r's table of sweep
+                                                     // e is complete; c = 1 if it differs from its table of sweep e - 1
     unsigned long long* peer_arena[MAX_PEERS] = {};  // mapped with cudaIpcOpenMemHandle
     unsigned long long* peer_flags[MAX_PEERS] = {};
     int peer_rank[MAX_PEERS] = {};
