@@ -480,14 +480,16 @@ def test_converged_posterior_matches_oracle_chains(gpu_handle, c2_donor, example
     assert np.abs(np.median([g["Config_prob"] for g in gs], axis=0) -
                   np.median([o["Config_prob"] for o in os_], axis=0)).mean() < 0.02
     assert abs(np.median([g["relax_rate"] for g in gs]) - np.median([o["relax_rate"] for o in os_])) < 0.02
-    # fixed tree on the real donor
+    # fixed tree on the real donor: the plain 0.02 bar.  Chain lengths are chosen so that Monte-Carlo error fits under it:
+    # two groups of 2 x 2000-sweep oracle chains differ by up to 0.030 from each other, these four 4000-sweep oracle
+    # chains are within 0.006 of the mean of sixteen more (measured on the host), 8 x 8000 sweeps here add ~0.004
     A, D, Z = example_donor
-    g = cb.clone_id(A, D, Z, min_iter=4000, max_iter=4000, n_chain=4, seed=3, relax_Config=False,
+    g = cb.clone_id(A, D, Z, min_iter=8000, max_iter=8000, n_chain=8, seed=3, relax_Config=False,
                     handle=gpu_handle, verbose=False, keep_prob_all=0)
-    os_ = [O.clone_id_Gibbs(A, D, Z, min_iter=2000, max_iter=2000, relax_Config=False,
-                            draws=O.NumpyDraws(200 + c)) for c in range(2)]
+    os_ = [O.clone_id_Gibbs(A, D, Z, min_iter=4000, max_iter=4000, relax_Config=False,
+                            draws=O.NumpyDraws(200 + c)) for c in range(4)]
     po = sum(o["prob"] for o in os_) / len(os_)
-    assert np.abs(g["prob"] - po).max() <= 0.03
+    assert np.abs(g["prob"] - po).max() <= 0.02
     sure = po.max(1) > 0.9
     assert np.array_equal(g["prob"][sure].argmax(1), po[sure].argmax(1))
     assert abs(g["theta0"] - np.mean([o["theta0"] for o in os_])) < 2e-3
