@@ -6,6 +6,7 @@
 #include <dlfcn.h>
 #include <algorithm>
 #include <cmath>
+#include <chrono>
 #include <cstdio>
 #include <cstring>
 #include <map>
@@ -120,6 +121,9 @@ struct cdl_handle_s {
     bool debug_capture = false;          // cdl_debug_capture
     int cells_layout = CDL_CELLS_AUTO;   // cdl_set_cells_layout
     bool use_sell = false;               // decided per run
+    // device scratch of the fetch calls that transpose into R's layout (kept: a clone_id(n_chain = 64) call makes 128 such
+    // fetches, and a cudaMalloc / cudaFree pair each cost more than the copy); at most 64 MB stay resident
+    DevBuf<double> fetch_scratch;
 };
 
 namespace {
@@ -144,6 +148,22 @@ int guard(cdl_handle h, F&& f) {
         return CDL_ERR_INVALID;
     }
 }
+
+// `count` doubles of device scratch for a fetch call: the handle's kept buffer when the request is small, a one-off
+// allocation (freed on scope exit) otherwise.  Every user synchronises the stream before it returns.
+struct ScratchUse {
+    double* p = nullptr;
+    DevBuf<double> own;
+    ScratchUse(cdl_handle h, size_t count) {
+        if (count * sizeof(double) <= ((size_t)64 << 20)) {
+            if (h->fetch_scratch.n < count) h->fetch_scratch.alloc(count);
+            p = h->fetch_scratch.p;
+        } else {
+            own.alloc(count);
+            p = own.p;
+        }
+    }
+};
 
 void nccl_load(cdl_handle h, const char* path) {
     if (h->nccl.lib) return;
@@ -1144,6 +1164,15 @@ int cdl_gibbs_run(cdl_handle h, const double* Config, int32_t K, const double* P
         if (h->cells_layout == CDL_CELLS_SMALL && !small)
             throw Error(CDL_ERR_UNSUPPORTED, "the small-donor path does not apply (size, replay, sharding, element or incremental mode)");
         if (small) {
+            // CDL_PHASES=1 (debugging switch, like CDL_TIMELINE): host seconds spent setting the chains up, in the sweep
+            // launches and the convergence checks between them, and in the per-chain summaries, on stderr
+            static const bool phases = [] { const char* e = getenv("CDL_PHASES"); return e && e[0] == '1'; }();
+            auto now = [] { return std::chrono::steady_clock::now(); };
+            auto secs = [](std::chrono::steady_clock::time_point x, std::chrono::steady_clock::time_point y) {
+                return std::chrono::duration<double>(y - x).count();
+            };
+            const auto ph0 = now();
+            double ph_checks = 0.0;
             std::vector<std::unique_ptr<Chain>> run;
             std::vector<SweepArgs> args((size_t)gp.n_chain, a);
             std::vector<ChainDev> devs((size_t)gp.n_chain);
@@ -1160,6 +1189,12 @@ int cdl_gibbs_run(cdl_handle h, const double* Config, int32_t K, const double* P
             std::vector<double> fr((size_t)gp.n_chain, NAN);
             int n_active = gp.n_chain;
             int64_t it = 2;
+            DevBuf<const double*> gw_ptrs((size_t)gp.n_chain);
+            DevBuf<unsigned long long> gw_counts(2 * (size_t)gp.n_chain);
+            std::vector<const double*> gw_list;
+            std::vector<int> gw_chain;
+            std::vector<unsigned long long> gw_host;
+            const auto ph1 = now();
             while (it <= T && n_active > 0) {
                 // up to the next point at which the reference checks convergence (:580), at most 1000 sweeps a launch
                 int64_t end = T;
@@ -1176,22 +1211,38 @@ int cdl_gibbs_run(cdl_handle h, const double* Config, int32_t K, const double* P
                 launch_small_chains(d, a, r, h->st);
                 h->launches += 1;
                 if (exact && end >= gp.min_iter && end % check_every == 0) {
-                    for (int c = 0; c < gp.n_chain; ++c) {
-                        if (!active[(size_t)c]) continue;
-                        fr[(size_t)c] = geweke_fraction(h, *run[(size_t)c], end, gcounts);
+                    if (phases) CDL_CUDA(cudaStreamSynchronize(h->st));
+                    const auto pc0 = now();
+                    // the test of every chain that is still running, in one launch and one read-back
+                    gw_list.clear(); gw_chain.clear();
+                    for (int c = 0; c < gp.n_chain; ++c)
+                        if (active[(size_t)c]) { gw_list.push_back(run[(size_t)c]->dev.prob_all); gw_chain.push_back(c); }
+                    gw_ptrs.upload(gw_list.data(), gw_list.size(), h->st);
+                    gw_host.assign(2 * gw_list.size(), 0ull);
+                    const bool batched = launch_geweke_batch(gw_ptrs.p, (int)gw_list.size(), M * K, end, gw_counts.p, h->st);
+                    if (batched) gw_counts.download(gw_host.data(), gw_host.size(), h->st);
+                    for (size_t q = 0; q < gw_chain.size(); ++q) {
+                        const int c = gw_chain[q];
+                        if (batched) fr[(size_t)c] = gw_host[2 * q] ? (double)gw_host[2 * q + 1] / (double)gw_host[2 * q] : NAN;
+                        else fr[(size_t)c] = geweke_fraction(h, *run[(size_t)c], end, gcounts);      // wide traces: one by one
                         notify(gp.chain_offset + c, end, fr[(size_t)c]);
                         if (fr[(size_t)c] > 0.995) { it_final[(size_t)c] = end; active[(size_t)c] = 0; --n_active; }
                     }
+                    ph_checks += secs(pc0, now());
                 } else {
                     notify(gp.chain_offset, end, NAN);
                 }
                 it = end + 1;
             }
             CDL_CUDA(cudaStreamSynchronize(h->st));
+            const auto ph2 = now();
             for (int c = 0; c < gp.n_chain; ++c) {
                 finish_chain(*run[(size_t)c], args[(size_t)c], it_final[(size_t)c], fr[(size_t)c]);
                 h->chains.push_back(std::move(run[(size_t)c]));
             }
+            if (phases)
+                std::fprintf(stderr, "[cdl phases] %d chains: set-up %.4f s, sweeps %.4f s (+ checks %.4f s), summaries %.4f s\n",
+                             gp.n_chain, secs(ph0, ph1), secs(ph1, ph2) - ph_checks, ph_checks, secs(ph2, now()));
         } else if (!concurrent) {
             for (int c = 0; c < gp.n_chain; ++c) {
                 std::unique_ptr<Chain> chp = start_chain(c, a);
@@ -1396,9 +1447,10 @@ int cdl_fetch_prob(cdl_handle h, int32_t chain, double* out) {
     return guard(h, [&] {
         Chain& ch = get_chain(h, chain);
         const int64_t M = h->donor.M, K = h->K;
-        DevBuf<double> t((size_t)(M * K));                           // [cell][clone] -> R's column-major M x K
+        ScratchUse t(h, (size_t)(M * K));                            // [cell][clone] -> R's column-major M x K
         launch_transpose_scale(ch.prob_mean.p, M, K, 1.0, t.p, h->st);
-        t.download(out, (size_t)(M * K), h->st);
+        CDL_CUDA(cudaMemcpyAsync(out, t.p, sizeof(double) * (size_t)(M * K), cudaMemcpyDeviceToHost, h->st));
+        CDL_CUDA(cudaStreamSynchronize(h->st));
     });
 }
 
@@ -1424,9 +1476,10 @@ int cdl_fetch_theta_traces(cdl_handle h, int32_t chain, double* theta0_all, doub
         if (theta0_all) ch.theta0_all.download(theta0_all, n, h->st);
         if (theta1_all) {
             // R shape n_iter x n_element column-major
-            DevBuf<double> t(n * (size_t)h->n_el);
+            ScratchUse t(h, n * (size_t)h->n_el);
             launch_transpose_scale(ch.theta1_all.p, (int64_t)n, h->n_el, 1.0, t.p, h->st);
-            t.download(theta1_all, n * (size_t)h->n_el, h->st);
+            CDL_CUDA(cudaMemcpyAsync(theta1_all, t.p, sizeof(double) * n * (size_t)h->n_el, cudaMemcpyDeviceToHost, h->st));
+            CDL_CUDA(cudaStreamSynchronize(h->st));
         }
     });
 }

@@ -221,6 +221,10 @@ void launch_el_theta(const Donor& d, const SweepArgs& a, ChainDev& c, cudaStream
 // post-processing
 void launch_geweke(const double* prob_all, int64_t cols, int64_t n_rows, unsigned long long* counts2,
                    cudaStream_t st);  // counts2[0] = #non-NaN, counts2[1] = #|Z|<=2
+// the same on n_traces traces of one shape in one launch; counts[2 t], counts[2 t + 1].  Small traces only: returns false
+// without launching anything when they are too wide
+bool launch_geweke_batch(const double* const* traces_dev, int n_traces, int64_t cols, int64_t n_rows,
+                         unsigned long long* counts, cudaStream_t st);
 // window snapshots (s1a .. s2b) are fp32 or fp64 arrays, the running sums s1n / s2n always fp64
 void launch_geweke_sums(const void* s1a, const void* s2a, const void* s1b, const void* s2b, bool fp32, const double* s1n,
                         const double* s2n, int64_t cols, int64_t n_rows, unsigned long long* counts2, cudaStream_t st);

@@ -35,6 +35,89 @@ __global__ void k_geweke(const double* __restrict__ X, int64_t cols, int64_t n, 
     }
 }
 
+// The same test for SMALL traces (a few thousand columns: the C1 / C2 / C5 donors).  One thread per column leaves such
+// a trace on 7 CTAs with ~2000 dependent trips per pass -- 0.5 ms per check, and the 64 chains x 30 checks of a
+// clone_id(n_chain = 64) call on example_donor spent 0.65 of their 1.1 s there.  Here a CTA owns GW_TILE columns and
+// deals the rows of each window to GW_TILE row lanes (partials added in lane order: deterministic; the sums differ from
+// the one-thread walk by rounding only), and blockIdx.y walks the traces of several chains in one launch
+// (counts[2 y], counts[2 y + 1]).
+constexpr int GW_TILE = 32;
+__global__ void __launch_bounds__(GW_TILE * GW_TILE)
+k_geweke_tiled(const double* __restrict__ X0, const double* const* __restrict__ Xs, int64_t cols, int64_t n,
+               unsigned long long* counts) {
+    __shared__ double red[2][GW_TILE][GW_TILE + 1];
+    __shared__ double mean[2][GW_TILE];
+    const double* __restrict__ X = Xs ? Xs[blockIdx.y] : X0;
+    const int tx = threadIdx.x, ty = threadIdx.y;
+    const int64_t c = blockIdx.x * (int64_t)GW_TILE + tx;
+    const bool in = c < cols;
+    const int64_t nA = (int64_t)floor(0.1 * (double)n);
+    const int64_t bs = (int64_t)ceil(0.5 * (double)n) - 1;
+    const int64_t nB = n - bs;
+    double sA = 0.0, sB = 0.0;
+    if (in) {
+#pragma unroll 4
+        for (int64_t r = ty; r < nA; r += GW_TILE) sA += X[r * cols + c];
+#pragma unroll 4
+        for (int64_t r = bs + ty; r < n; r += GW_TILE) sB += X[r * cols + c];
+    }
+    red[0][ty][tx] = sA; red[1][ty][tx] = sB;
+    __syncthreads();
+    if (ty == 0) {
+        double a = 0.0, b = 0.0;
+        for (int q = 0; q < GW_TILE; ++q) { a += red[0][q][tx]; b += red[1][q][tx]; }
+        mean[0][tx] = a / (double)nA; mean[1][tx] = b / (double)nB;
+    }
+    __syncthreads();
+    const double mA = mean[0][tx], mB = mean[1][tx];
+    double vA = 0.0, vB = 0.0;
+    if (in) {
+#pragma unroll 4
+        for (int64_t r = ty; r < nA; r += GW_TILE) { const double d = X[r * cols + c] - mA; vA += d * d; }
+#pragma unroll 4
+        for (int64_t r = bs + ty; r < n; r += GW_TILE) { const double d = X[r * cols + c] - mB; vB += d * d; }
+    }
+    red[0][ty][tx] = vA; red[1][ty][tx] = vB;       // (the partial sums were read before the barrier above)
+    __syncthreads();
+    if (ty == 0) {                                  // warp 0: one lane per column of the tile
+        double a = 0.0, b = 0.0;
+        for (int q = 0; q < GW_TILE; ++q) { a += red[0][q][tx]; b += red[1][q][tx]; }
+        a /= (double)(nA - 1);
+        b /= (double)(nA - 1);                      // nrow(A) - 1, as the reference has it
+        const double Z = (mA - mB) / sqrt(a + b + 1e-50);
+        unsigned ok = 0, conv = 0;
+        if (in && !isnan(Z)) { ok = 1; conv = fabs(Z) <= 2.0; }
+        const unsigned okw = __popc(__ballot_sync(0xffffffffu, ok));
+        const unsigned cvw = __popc(__ballot_sync(0xffffffffu, conv));
+        if (tx == 0) {
+            if (okw) atomicAdd(&counts[2 * blockIdx.y], (unsigned long long)okw);
+            if (cvw) atomicAdd(&counts[2 * blockIdx.y + 1], (unsigned long long)cvw);
+        }
+    }
+}
+// traces up to this many columns take the tiled kernels (beyond it one thread per column fills the GPU by itself)
+constexpr int64_t TILED_MAX_COLS = 1 << 16;
+
+template <typename T>
+__global__ void __launch_bounds__(GW_TILE * GW_TILE)
+k_col_means_tiled(const T* __restrict__ X, int64_t cols, int64_t r0, int64_t r1, double* __restrict__ out) {
+    __shared__ double red[GW_TILE][GW_TILE + 1];
+    const int tx = threadIdx.x, ty = threadIdx.y;
+    const int64_t c = blockIdx.x * (int64_t)GW_TILE + tx;
+    double s = 0.0;
+    if (c < cols) {
+#pragma unroll 4
+        for (int64_t r = r0 + ty; r < r1; r += GW_TILE) s += (double)X[r * cols + c];
+    }
+    red[ty][tx] = s;
+    __syncthreads();
+    if (ty == 0 && c < cols) {
+        double a = 0.0;
+        for (int q = 0; q < GW_TILE; ++q) a += red[q][tx];
+        out[c] = a / (double)(r1 - r0);
+    }
+}
+
 template <typename T>
 __global__ void k_col_means(const T* __restrict__ X, int64_t cols, int64_t r0, int64_t r1, double* __restrict__ out) {
     const int64_t c = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
@@ -470,8 +553,26 @@ void launch_scale(double* x, int64_t n, double s, cudaStream_t st) {
 void launch_geweke(const double* prob_all, int64_t cols, int64_t n_rows, unsigned long long* counts2,
                    cudaStream_t st) {
     CDL_CUDA(cudaMemsetAsync(counts2, 0, 2 * sizeof(unsigned long long), st));
-    k_geweke<<<(unsigned)((cols + 255) / 256), 256, 0, st>>>(prob_all, cols, n_rows, counts2);
+    if (cols <= TILED_MAX_COLS)
+        k_geweke_tiled<<<dim3((unsigned)((cols + GW_TILE - 1) / GW_TILE), 1), dim3(GW_TILE, GW_TILE), 0, st>>>(
+            prob_all, nullptr, cols, n_rows, counts2);
+    else
+        k_geweke<<<(unsigned)((cols + 255) / 256), 256, 0, st>>>(prob_all, cols, n_rows, counts2);
     CDL_CUDA(cudaGetLastError());
+}
+
+// The test on `n_traces` traces of the same shape in one launch (the chains of a small donor at a convergence check):
+// traces_dev is a DEVICE array of their pointers, counts gets 2 * n_traces values (tested columns, columns with |Z| <= 2).
+// Returns false (nothing launched) when the traces are too wide for the tiled kernel: the caller tests them one by one.
+bool launch_geweke_batch(const double* const* traces_dev, int n_traces, int64_t cols, int64_t n_rows,
+                         unsigned long long* counts, cudaStream_t st) {
+    if (cols > TILED_MAX_COLS || n_traces > 65535) return false;
+    if (n_traces <= 0) return true;
+    CDL_CUDA(cudaMemsetAsync(counts, 0, 2 * sizeof(unsigned long long) * (size_t)n_traces, st));
+    k_geweke_tiled<<<dim3((unsigned)((cols + GW_TILE - 1) / GW_TILE), (unsigned)n_traces), dim3(GW_TILE, GW_TILE), 0, st>>>(
+        nullptr, traces_dev, cols, n_rows, counts);
+    CDL_CUDA(cudaGetLastError());
+    return true;
 }
 
 void launch_geweke_sums(const void* s1a, const void* s2a, const void* s1b, const void* s2b, bool fp32, const double* s1n,
@@ -560,13 +661,19 @@ void launch_window_mean(const double* s1n, const void* s1u, bool fp32, int64_t n
     CDL_CUDA(cudaGetLastError());
 }
 
-void launch_col_means_d(const double* X, int64_t cols, int64_t r0, int64_t r1, double* out, cudaStream_t st) {
-    k_col_means<double><<<(unsigned)((cols + 255) / 256), 256, 0, st>>>(X, cols, r0, r1, out);
+template <typename T>
+static void launch_col_means_t(const T* X, int64_t cols, int64_t r0, int64_t r1, double* out, cudaStream_t st) {
+    if (cols <= TILED_MAX_COLS)
+        k_col_means_tiled<T><<<(unsigned)((cols + GW_TILE - 1) / GW_TILE), dim3(GW_TILE, GW_TILE), 0, st>>>(X, cols, r0, r1, out);
+    else
+        k_col_means<T><<<(unsigned)((cols + 255) / 256), 256, 0, st>>>(X, cols, r0, r1, out);
     CDL_CUDA(cudaGetLastError());
 }
+void launch_col_means_d(const double* X, int64_t cols, int64_t r0, int64_t r1, double* out, cudaStream_t st) {
+    launch_col_means_t<double>(X, cols, r0, r1, out, st);
+}
 void launch_col_means_u8(const uint8_t* X, int64_t cols, int64_t r0, int64_t r1, double* out, cudaStream_t st) {
-    k_col_means<uint8_t><<<(unsigned)((cols + 255) / 256), 256, 0, st>>>(X, cols, r0, r1, out);
-    CDL_CUDA(cudaGetLastError());
+    launch_col_means_t<uint8_t>(X, cols, r0, r1, out, st);
 }
 
 void launch_prob_variant(const Donor& d, int wise, const double* theta0_all, const double* theta1_all,
