@@ -44,7 +44,8 @@ enum {
  * every check_every sweeps; `fraction` is the converged fraction of the reference's Geweke check when one was made
  * at this iteration (R/clone_id.R:580-592; the host prints "x% converged." from it like the reference's cat()),
  * NaN otherwise.  A non-zero return value stops the run with CDL_ERR_INTERRUPTED.  The library prints nothing itself
- * (the debugging switch CDL_TIMELINE=1 makes cdl_bench_sweeps write a device timeline to stderr). */
+ * (two debugging switches write to stderr: CDL_TIMELINE=1, a device timeline from cdl_bench_sweeps, and CDL_PHASES=1, the
+ * host seconds of the phases of a small-donor run). */
 typedef int (*cdl_progress_fn)(void* user, int32_t chain, int32_t iteration, double fraction);
 
 enum { CDL_WISE_GLOBAL = 0, CDL_WISE_VARIANT = 1, CDL_WISE_ELEMENT = 2 };
