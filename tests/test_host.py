@@ -190,3 +190,31 @@ def test_clone_id_accepts_compact_counts_up_to_the_device():
     else:
         with pytest.raises(cb.CdlError):
             cb.clone_id(counts, None, n_clone=3, min_iter=5, max_iter=5, verbose=False)
+
+
+def test_committed_bench_lines_agree_on_the_parity_hashes():
+    """The bench lines committed under profiles/ for 1, 2, 4 and 8 GPUs (C4, cells sharded) carry hashes of the labels
+    of all 10^6 cells, the Config flips and the theta traces of the first sweeps of the bench chain: they must be the
+    same at every GPU count, and every sharded line must say that it equals the unsharded donor rerun on rank 0."""
+    import glob
+    import json
+    import os
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    lines = {}
+    for f in sorted(glob.glob(os.path.join(root, "profiles", "r2_bench_c4*.json"))):
+        for ln in open(f):
+            if ln.startswith("{"):
+                d = json.loads(ln)
+                if d.get("impl") != "reference" and d.get("parity") and d["config"]["workload"].startswith("C4:"):
+                    lines[d["n_gpus"]] = d
+    assert set(lines) >= {1, 2, 4, 8}, sorted(lines)
+    one = lines[1]["parity"]
+    for n, d in lines.items():
+        p = d["parity"]
+        assert p["sharded_equals_unsharded"] is True, n
+        for key in ("labels_hash", "config_hash", "theta_hash"):
+            assert p[key] == one[key], (n, key)
+        if n > 1:
+            assert p["label_mismatches"] == 0 and p["loglik_max_rel_diff"] < 1e-12
+            for key in ("labels_hash", "config_hash", "theta_hash"):
+                assert p["unsharded"][key] == one[key], (n, key)
