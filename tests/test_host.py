@@ -123,6 +123,27 @@ def test_bench_reference_arm_line():
     assert line["e2e"]["h2d_bytes_per_step"] == 0
 
 
+def test_bench_reference_arm_under_the_launcher():
+    """The driver starts the reference arm like ours: under torch.distributed.run for N > 1, which exports
+    OMP_NUM_THREADS=1.  Rank 0 alone works and prints ONE line, on all host threads (round 1 inherited the launcher's
+    single thread); the other ranks exit 0 without work."""
+    import json
+    import subprocess
+    import sys
+    env = dict(os.environ, OMP_NUM_THREADS="1")
+    r = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "2",
+                        "--master-addr", "127.0.0.1", "--master-port", "29561", os.path.join(ROOT, "bench.py"),
+                        "--impl", "reference", "--gpus", "2", "--workload", "tiny", "--steps", "2", "--warmup", "1"],
+                       capture_output=True, text=True, timeout=600, env=env)
+    assert r.returncode == 0, r.stderr[-2000:]
+    lines = [ln for ln in r.stdout.splitlines() if ln.startswith("{")]
+    assert len(lines) == 1, r.stdout
+    line = json.loads(lines[0])
+    assert line["impl"] == "reference" and line["n_gpus"] == 2 and line["steps"] == 2 and line["warmup"] == 1
+    assert line["cpu_baseline"]["cores"] == (os.cpu_count() or 1)
+    assert line["e2e"]["value"] == line["value"] and line["e2e"]["d2h_bytes_per_step"] == 0
+
+
 def test_r_shim_compiles_against_stub_headers():
     """The .Call shim cannot be built here (no R), but it must at least be valid C against the C ABI header: compile
     it with -fsyntax-only -Wall -Werror against stand-in declarations of the R API entry points it uses."""
